@@ -1,0 +1,143 @@
+"""The oracle restatement replayed against fixtures produced by the reference's own code
+(oracle/make_golden.py).  Same ATen build underneath => forward quantities must agree bit-for-bit;
+the hand-written backward/Adam is compared at 1e-6."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import moc_oracle as O
+
+SLIDE_CASES = ["slide_c2", "slide_c2_j64", "slide_c3", "slide_c30"]
+
+
+def T(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def feat_of(g, key):
+    return T(g[key]).float()
+
+
+def params_of(g, prefix):
+    return O.SenetParams(T(g[prefix + "model_0_weight"]).clone(), T(g[prefix + "model_0_bias"]).clone(),
+                         T(g[prefix + "model_2_weight"]).clone(), T(g[prefix + "model_2_bias"]).clone())
+
+
+@pytest.fixture(autouse=True)
+def _one_thread():
+    n = torch.get_num_threads()
+    torch.set_num_threads(1)
+    yield
+    torch.set_num_threads(n)
+
+
+@pytest.mark.parametrize("name", SLIDE_CASES)
+def test_scores_selectors_poolers(golden, name):
+    g = golden(name)
+    c, j, k = int(g["C"]), int(g["J"]), int(g["K"])
+    w, we = T(g["W"]), T(g["W_ext"])
+    for i in range(int(g["n_slides"])):
+        p = "s%d_" % i
+        x = feat_of(g, p + "feat")
+        lo, le = O.score(x, w, we)
+        assert torch.equal(lo, T(g[p + "L"])) and torch.equal(le, T(g[p + "Le"]))
+        assert torch.equal(O.index_topj(lo, [j]), T(g[p + "idx_topj"]))
+        assert torch.equal(O.index_delta_softmax(lo, [j]), T(g[p + "idx_dsoftmax"]))
+        assert torch.equal(O.index_delta_diff(lo, [j]), T(g[p + "idx_ddiff"]))
+        assert torch.equal(O.index_bottomk_irrel(le, [j], c), T(g[p + "idx_bottomk"]))
+        assert torch.equal(O.topj_pooling(lo, [k])[1][k], T(g[p + "pool_topj"]))
+        assert torch.equal(O.delta_softmax_pooling(lo, [k])[1][k], T(g[p + "pool_dsoftmax"]))
+        assert torch.equal(O.delta_diff_pooling(lo, [k])[1][k], T(g[p + "pool_ddiff"]))
+        assert torch.equal(O.bottomk_irrel_pooling(le, [k], coords_list=c)[1][k], T(g[p + "pool_bottomk"]))
+
+
+@pytest.mark.parametrize("name", SLIDE_CASES)
+def test_slide_process_gate_and_bag_logits(golden, name):
+    g = golden(name)
+    c, j, k = int(g["C"]), int(g["J"]), int(g["K"])
+    w, we = T(g["W"]), T(g["W_ext"])
+    prm = params_of(g, "sd_")
+    for i in range(int(g["n_slides"])):
+        x = feat_of(g, "s%d_feat" % i)
+        for di, disc in enumerate(g["discards"]):
+            disc = tuple(d for d in str(disc).split("|") if d)
+            q = "s%d_d%d_" % (i, di)
+            r = O.slide_process(x, w, we, c, j, discard_classifiers=disc)
+            assert r["selected_index"] == g[q + "selected_index"].tolist()
+            assert torch.equal(r["logits_top_classifier"], T(g[q + "plane_top"]))
+            assert torch.equal(r["logits_delta_softmax_classifier"], T(g[q + "plane_dsoftmax"]))
+            assert torch.equal(r["logits_delta_diff_classifier"], T(g[q + "plane_ddiff"]))
+            assert torch.equal(r["logits_bottomk_irrel_classifier"], T(g[q + "plane_bottomk"]))
+            gate, _ = O.senet_forward(prm, r["selected_feat"])
+            torch.testing.assert_close(gate, T(g[q + "gate"]), rtol=0, atol=1e-7)
+            f = O.combine(gate, r, O.active_classifiers(disc, "eval"))
+            torch.testing.assert_close(f, T(g[q + "final"]), rtol=1e-6, atol=1e-7)
+            torch.testing.assert_close(O.bag_logits(f, k), T(g[q + "bag_logits"]), rtol=1e-6, atol=1e-7)
+
+
+def test_selection_set_identities(golden):
+    """Facts the CUDA design leans on: delta-diff columns are identical; the bottom-k index set is the
+    bottom-maxj of the background sum."""
+    for name in SLIDE_CASES:
+        g = golden(name)
+        c, j = int(g["C"]), int(g["J"])
+        for i in range(int(g["n_slides"])):
+            p = "s%d_" % i
+            dd = g[p + "idx_ddiff"]
+            assert all(set(dd[:, 0]) == set(dd[:, cc]) for cc in range(dd.shape[1]))
+            bg = g[p + "Le"][:, c:].sum(axis=1)
+            maxj = min(j, bg.shape[0])
+            thr = O.rank_threshold(bg, maxj, largest=False)
+            got = set(g[p + "idx_bottomk"].flatten().tolist())
+            assert len(got) == maxj
+            assert all(bg[r] <= thr for r in got)
+            assert set(np.nonzero(bg < thr)[0].tolist()) <= got
+
+
+@pytest.mark.parametrize("name", ["loop_c2", "loop_c3_discard"])
+def test_train_eval_loops(golden, name):
+    g = golden(name)
+    c, j, k = int(g["C"]), int(g["J"]), int(g["K"])
+    disc = tuple(d for d in str(g["discard"]).split("|") if d)
+    w, we = T(g["W"]), T(g["W_ext"])
+    tr = O.BagList([feat_of(g, "train_feat_%d" % i) for i in range(int(g["n_train"]))],
+                   g["train_labels"].tolist(), repeat_num=int(g["repeat_num"]))
+    va = O.BagList([feat_of(g, "val_feat_%d" % i) for i in range(int(g["n_val"]))], g["val_labels"].tolist())
+
+    def ev(d):
+        return np.asarray([d["loss"], d["acc"], d["auc"]])
+
+    np.testing.assert_allclose(ev(O.zs_evaluation(tr, w, we, c, k)), g["zs_train"], rtol=1e-6)
+    np.testing.assert_allclose(ev(O.zs_evaluation(va, w, we, c, k)), g["zs_val"], rtol=1e-6)
+    np.testing.assert_allclose(ev(O.zs_evaluation(va, w, we, c, k, "delta_softmax")), g["zs_val_dsoftmax"], rtol=1e-6)
+    np.testing.assert_allclose(ev(O.zs_evaluation(va, w, we, c, k, "delta_diff")), g["zs_val_ddiff"], rtol=1e-6)
+    np.testing.assert_allclose(ev(O.zs_evaluation(va, w, we, c, k, "bottomk_irrel")), g["zs_val_bottomk"], rtol=1e-6)
+    for how in ("avg", "sum", "max"):
+        rows = [O.ablation_logits(x, w, we, c, j, k, how) for x in va.bags]
+        loss = sum(float(O.cross_entropy(r, y)) for r, y in zip(rows, va.labels))
+        m = O._metrics(torch.cat(rows, 0), va.labels, loss, len(va), va.real_len())
+        np.testing.assert_allclose(ev(m), g["ablation_val_" + how], rtol=1e-6)
+
+    prm = params_of(g, "sd0_")
+    st = O.AdamState()
+    masks = [T(g["mask_%d" % i]) for i in range(int(g["n_masks"]))]
+    per = int(g["repeat_num"])
+    for e in range(int(g["epochs"])):
+        losses = O.train_epoch(prm, st, tr, w, we, c, j, k, disc, masks[e * per:(e + 1) * per])
+        np.testing.assert_allclose(losses, g["train_losses_e%d" % e], rtol=2e-6)
+        for key, t in prm.state_dict().items():
+            np.testing.assert_allclose(t.numpy(), g["sd_e%d_" % e + key.replace(".", "_")], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(ev(O.evaluation(prm, tr, w, we, c, j, k, disc)), g["eval_train_e%d" % e], rtol=2e-6)
+        np.testing.assert_allclose(ev(O.evaluation(prm, va, w, we, c, j, k, disc)), g["eval_val_e%d" % e], rtol=2e-6)
+    assert st.step == int(g["adam_step"])
+    for gi in range(4):
+        np.testing.assert_allclose(st.m[gi].numpy(), g["adam_m_%d" % gi], rtol=1e-4, atol=1e-9)
+        np.testing.assert_allclose(st.v[gi].numpy(), g["adam_v_%d" % gi], rtol=1e-4, atol=1e-12)
+
+
+def test_senet_init_matches_linear_default():
+    """SenetParams.init reproduces nn.Linear's default distribution bounds (not the stream)."""
+    p = O.SenetParams.init(0)
+    assert p.w1.shape == (64, 512) and p.b1.shape == (64,) and p.w2.shape == (4, 64) and p.b2.shape == (4,)
+    assert float(p.w1.abs().max()) <= 1 / np.sqrt(512) and float(p.w2.abs().max()) <= 1 / 8
+    assert sum(t.numel() for t in p.tensors()) == 33092
