@@ -1,0 +1,164 @@
+/*
+ * moc_b200.h - C ABI of the B200 (sm_100a) MOC per-slide hot path.
+ *
+ * The reference (xmed-lab/MOC) is pure Python/PyTorch and has no FFI of its
+ * own; its "operator interface" for this path is a handful of Python functions
+ * in main_moc.py and utils/patch_selection_classifier*.py.  Each entry point
+ * below names the reference code it replaces (file:line relative to the
+ * reference checkout).  The Python mirror of those functions lives in the
+ * moc_b200 package and calls this library through ctypes; INTEGRATION.md shows
+ * the binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - extern "C", no exceptions, no torch types.  Every function returns
+ *    MOC_OK (0) or a negative MOC_E_* code; moc_last_error() gives the text.
+ *  - All pointers are DEVICE pointers unless the name ends in _h.
+ *  - Every call is asynchronous on `stream` (a cudaStream_t passed as void*;
+ *    from PyTorch: torch.cuda.current_stream().cuda_stream).  No hidden
+ *    synchronisation, no hidden allocation: the caller owns every buffer,
+ *    including workspaces sized by the *_workspace_bytes() queries.
+ *  - Bags ("slides") live in one ragged row-major fp32 buffer feat[total_rows][512];
+ *    slide i owns rows offsets[i] .. offsets[i+1]-1.
+ *  - Keys are stored as planes (structure of arrays): plane p, row r is
+ *    keys[p * key_stride + r].  For C classes the planes are
+ *       [0,C)    L[:,c]            patch-prompt similarity        (main_moc.py:336)
+ *       [C,2C)   softmax(L)[:,c]   row softmax over classes       (_index.py:34)
+ *       2C       |top1 - top2| of the row of L                    (_index.py:46-48)
+ *       2C+1     sum of background similarities  Le[:, C:]        (_index.py:71-75)
+ *       2C+2     max of background similarities  Le[:, C:]        (main_moc.py:365)
+ */
+#ifndef MOC_B200_H
+#define MOC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MOC_FEAT_DIM 512   /* CONCH embedding width                          */
+#define MOC_HIDDEN 64      /* senet hidden width            main_moc.py:302  */
+#define MOC_GATES 4        /* one gate per classifier       main_moc.py:315  */
+#define MOC_MAX_COLS 64    /* C + number of background prompts, this build   */
+
+#define MOC_OK 0
+#define MOC_E_ARG (-1)        /* null pointer / negative size / bad flag      */
+#define MOC_E_SHAPE (-2)      /* shape outside what this build supports       */
+#define MOC_E_WORKSPACE (-3)  /* workspace too small                          */
+#define MOC_E_CUDA (-4)       /* a CUDA runtime call failed                   */
+
+/* discard / active bit masks: bit m set = classifier m is discarded / active.
+ * Order follows --discard_classifiers (main_moc.py:39). */
+#define MOC_CLS_TOPK 1u
+#define MOC_CLS_DELTA_SOFTMAX 2u
+#define MOC_CLS_DELTA_DIFF 4u
+#define MOC_CLS_BOTTOMK 8u
+#define MOC_CLS_ALL 15u
+
+const char* moc_last_error(void);
+int moc_version(void);
+/* number of key planes for C classes: 2C+3 */
+int moc_num_key_planes(int n_classes);
+
+/* ---- prompt matrices ------------------------------------------------------
+ * Packs W [512,C] and the background columns of W_ext [512,C_ext] (both
+ * row-major as torch.stack(..., dim=1) leaves them, utils/zeroshot_utils.py:50)
+ * into the K-major layout the scoring kernel keeps on chip:
+ * packed[col][512], col < C from W, then the C_ext-C background columns of
+ * W_ext, zero-padded to moc_packed_cols() columns.  The first C columns of
+ * W_ext never influence slide_process (they only re-order rows inside the
+ * bottom-k set, _index.py:82-86) and are not packed. */
+int moc_packed_cols(int n_classes, int n_ext);
+int moc_pack_prompts(const float* w, int n_classes, const float* w_ext, int n_ext,
+                     float* packed, void* stream);
+
+/* ---- a2 + selection keys: the streaming kernel ----------------------------
+ * Replaces `feat @ zeroshot_weights`, `feat @ zeroshot_weights_ext`
+ * (main_moc.py:336-337) and the per-row arithmetic of the four selectors
+ * (_index.py:34, :46-48, :71-75) and of the score planes (main_moc.py:359-366).
+ * Reads every row of feat exactly once (2048 B / patch).  normalize != 0
+ * L2-normalises each row first (models/model_adapters.py:188; off in MOC). */
+int moc_score_keys(const float* feat, int64_t n_rows, const float* packed, int n_classes, int n_ext,
+                   int normalize, float* keys, int64_t key_stride, void* stream);
+
+/* ---- a3..a7: four top-J selections, union, ascending compaction -----------
+ * Replaces index_{topj,delta_softmax,delta_diff,bottomk_irrel}_classifier
+ * (_index.py:17-87) plus the set union / sort of main_moc.py:341-354, for
+ * n_slides bags at once.  row_mask (nullable, one byte per row, 0 = dropped)
+ * plays the role of the random half mask (main_moc.py:329-331): dropped rows do
+ * not exist for the selection, maxj = min(topj, kept rows), and sel_local holds
+ * indices into the *masked* bag exactly like the reference's selected_index.
+ * Output region of slide i is [sel_base[i], sel_base[i+1]) (caller-computed
+ * prefix sums of moc_select_capacity(); n_slides+1 entries); sel_rows are
+ * absolute rows of feat, ascending, and the unused tail of a region is -1. */
+int64_t moc_select_capacity(int64_t n_rows_of_slide, int n_classes, int topj);
+size_t moc_select_workspace_bytes(int64_t total_rows, int n_slides);
+int moc_select_union(const float* keys, int64_t key_stride, const int64_t* offsets, int n_slides,
+                     int64_t total_rows, int n_classes, int topj, unsigned discard_mask, const uint8_t* row_mask,
+                     const int64_t* sel_base, int32_t* sel_rows, int32_t* sel_local, int32_t* sel_count,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- stand-alone sorted top-J (the selectors' public return value) --------
+ * values[i * ld] for i < n; writes the indices of the min(j,n) largest (or
+ * smallest) values in descending (ascending) value order, ties by lower index,
+ * as int64 to idx_out[r * out_ld].  n_cols independent columns per call:
+ * column c reads values + c * col_stride and writes idx_out + c.
+ * Replaces Tensor.topk(maxj, 0, largest, True) in _index.py:25,35,50,81,85. */
+int moc_topj_sorted(const float* values, int64_t n, int64_t ld, int n_cols, int64_t col_stride,
+                    int j, int largest, int64_t* idx_out, int64_t out_ld, float* val_out, void* stream);
+
+/* ---- a8..a11: head forward -------------------------------------------------
+ * For every selected row: gather the 512-vector, senet gate
+ * sigmoid(W2 relu(W1 x + b1) + b2) (main_moc.py:299-312,:390), the gated sum of
+ * the four score planes (main_moc.py:391-403 / :482-492, planes chosen by
+ * active_mask), then per (slide, class) the mean of the min(topk, S) largest
+ * (topj_pooling, utils/patch_selection_classifier.py:18-32).
+ * gate [S_total,4], final [S_total,C], bag_logits [n_slides,C],
+ * pool_pos [n_slides,C,topk] (positions inside the slide's selected list,
+ * -1 padded), all indexed through sel_base/sel_count. gate may be null. */
+int moc_head_forward(const float* feat, const float* keys, int64_t key_stride, int n_classes,
+                     const int64_t* sel_base, const int32_t* sel_rows, const int32_t* sel_count,
+                     int n_slides, int64_t sel_capacity_total,
+                     const float* w1, const float* b1, const float* w2, const float* b2,
+                     unsigned active_mask, int topk,
+                     float* gate, float* final_scores, float* bag_logits, int32_t* pool_pos,
+                     void* stream);
+
+/* per-(slide,class) top-K mean of one plane selected by another plane:
+ * zs_evaluation's pooling (main_moc.py:427-432) with
+ * select plane == value plane (topj_pooling) or softmax / delta planes. */
+int moc_pool_topk(const float* keys, int64_t key_stride, const int64_t* offsets, int n_slides,
+                  int n_classes, int topk, int select_plane0, int select_plane_step, int select_smallest,
+                  int value_plane0, int value_plane_step, float* bag_logits, void* stream);
+
+/* ---- a12: loss, backward, optimiser ----------------------------------------
+ * cross_entropy on [n,C] rows without temperature (main_moc.py:406,:494):
+ * loss[i], optional dlogits[i,:] = grad_scale * (softmax - onehot), optional pred[i]. */
+int moc_cross_entropy(const float* bag_logits, const int64_t* labels, int n_slides, int n_classes,
+                      float grad_scale, float* loss, float* dlogits, int32_t* pred, void* stream);
+
+/* d(sum_i <dlogits_i, bag_logits_i>) / d(senet parameters), written (not
+ * accumulated) to grads laid out [w1 64x512 | b1 64 | w2 4x64 | b2 4] =
+ * MOC_NUM_PARAMS floats.  Only the <= topk*C pooled rows of each slide carry
+ * gradient (autograd through topk/mean/mul/sigmoid/Linear, main_moc.py:390-409). */
+#define MOC_NUM_PARAMS (MOC_HIDDEN * MOC_FEAT_DIM + MOC_HIDDEN + MOC_GATES * MOC_HIDDEN + MOC_GATES)
+size_t moc_head_backward_workspace_bytes(int n_slides, int n_classes, int topk);
+int moc_head_backward(const float* feat, const float* keys, int64_t key_stride, int n_classes,
+                      const int64_t* sel_base, const int32_t* sel_rows, const int32_t* sel_count,
+                      int n_slides,
+                      const float* w1, const float* b1, const float* w2, const float* b2,
+                      unsigned active_mask, int topk, const int32_t* pool_pos, const float* dlogits,
+                      float* grads, void* workspace, size_t workspace_bytes, void* stream);
+
+/* torch.optim.Adam single step with L2 weight decay folded into the gradient
+ * (main_moc.py:316: lr 1e-3, weight_decay 1e-4; betas .9/.999, eps 1e-8).
+ * step is the 1-based step count after this update. */
+int moc_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                  int64_t step, float lr, float beta1, float beta2, float eps, float weight_decay,
+                  void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOC_B200_H */

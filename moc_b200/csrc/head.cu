@@ -1,0 +1,463 @@
+// Head of the MOC path: meta-learner gate on the selected patches, classifier-bank combination, top-K
+// pooling into bag logits, cross-entropy, backward and Adam.
+//
+// Replaces main_moc.py:299-312 (senet), :390-405 / :481-493 (gate, gated sum, topj_pooling), :406-410
+// (cross_entropy, backward, optimizer.step) and utils/patch_selection_classifier.py:18-32.
+//
+// The four score planes of a selected row are not recomputed from the features (main_moc.py:356-366 does
+// `selected_feat @ W` again): they are the key planes the streaming kernel already wrote for that row.
+// All arithmetic is fp32 with fp32 accumulation.  Reductions that decide results (pooling order, gradient
+// sums) run in a fixed order, so repeated runs are bit-identical.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace moc {
+
+constexpr int H = MOC_HIDDEN;  // 64
+constexpr int G = MOC_GATES;   // 4
+
+// ------------------------------------------------------------------------------------------------
+// Gate + combination for every selected row (slot).  Persistent CTAs keep W1 resident in shared memory.
+// Tile = 32 slots; 256 threads; thread (ty,tx) owns rows {ty, ty+16} x hidden units {tx, tx+16, tx+32, tx+48}.
+// ------------------------------------------------------------------------------------------------
+constexpr int HR_TM = 32;
+constexpr int HR_THREADS = 256;
+constexpr int HR_LD = D + 4;  // padded row stride (floats): 516/4 = 129 is odd -> conflict-free LDS.128
+
+__global__ void __launch_bounds__(HR_THREADS, 1)
+head_rows_kernel(const float* __restrict__ feat, const float* __restrict__ keys, int64_t key_stride, int C,
+                 const int32_t* __restrict__ sel_rows, int64_t n_slots, const float* __restrict__ w1,
+                 const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
+                 unsigned active_mask, float* __restrict__ gate, float* __restrict__ final_scores) {
+    extern __shared__ __align__(16) float hsm[];
+    float* w1s = hsm;                  // [64][516]
+    float* xs = hsm + H * HR_LD;       // [32][516]
+    __shared__ int32_t rows_s[HR_TM];
+    __shared__ float w2s[G * H], b1s[H], b2s[G];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ty = tid >> 4, tx = tid & 15;
+    for (int i = tid; i < H * (D / 4); i += HR_THREADS) {
+        const int j = i / (D / 4), k4 = i % (D / 4);
+        *reinterpret_cast<float4*>(w1s + j * HR_LD + k4 * 4) = __ldg(reinterpret_cast<const float4*>(w1) + i);
+    }
+    if (tid < G * H) w2s[tid] = w2[tid];
+    if (tid < H) b1s[tid] = b1[tid];
+    if (tid < G) b2s[tid] = b2[tid];
+    __syncthreads();
+
+    const float a0 = (active_mask & MOC_CLS_TOPK) ? 1.f : 0.f;
+    const float a1 = (active_mask & MOC_CLS_DELTA_SOFTMAX) ? 1.f : 0.f;
+    const float a2 = (active_mask & MOC_CLS_DELTA_DIFF) ? 1.f : 0.f;
+    const float a3 = (active_mask & MOC_CLS_BOTTOMK) ? 1.f : 0.f;
+
+    const int64_t n_tiles = (n_slots + HR_TM - 1) / HR_TM;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t slot0 = tile * HR_TM;
+        if (tid < HR_TM) {
+            const int64_t s = slot0 + tid;
+            rows_s[tid] = s < n_slots ? sel_rows[s] : -1;
+        }
+        __syncthreads();
+        // gather: warp w loads rows w, w+8, w+16, w+24 (2 KB each, coalesced)
+        bool any = false;
+#pragma unroll
+        for (int rr = 0; rr < HR_TM / 8; ++rr) {
+            const int r = warp + rr * 8;
+            const int32_t row = rows_s[r];
+            float4 v[4];
+            if (row >= 0) {
+                any = true;
+                const float4* src = reinterpret_cast<const float4*>(feat + (int64_t)row * D);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) v[q] = __ldg(src + q * 32 + lane);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(xs + r * HR_LD + q * 128 + lane * 4) = v[q];
+        }
+        const int tile_any = __syncthreads_or(any);
+        if (tile_any) {
+            float acc[2][4];
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                for (int u = 0; u < 4; ++u) acc[r][u] = 0.f;
+            const float* xa = xs + ty * HR_LD;
+            const float* xb = xs + (ty + 16) * HR_LD;
+            const float* wp = w1s + tx * HR_LD;
+#pragma unroll 4
+            for (int k4 = 0; k4 < D / 4; ++k4) {
+                const float4 va = *reinterpret_cast<const float4*>(xa + k4 * 4);
+                const float4 vb = *reinterpret_cast<const float4*>(xb + k4 * 4);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float4 wv = *reinterpret_cast<const float4*>(wp + u * 16 * HR_LD + k4 * 4);
+                    acc[0][u] = fmaf(va.x, wv.x, acc[0][u]);
+                    acc[0][u] = fmaf(va.y, wv.y, acc[0][u]);
+                    acc[0][u] = fmaf(va.z, wv.z, acc[0][u]);
+                    acc[0][u] = fmaf(va.w, wv.w, acc[0][u]);
+                    acc[1][u] = fmaf(vb.x, wv.x, acc[1][u]);
+                    acc[1][u] = fmaf(vb.y, wv.y, acc[1][u]);
+                    acc[1][u] = fmaf(vb.z, wv.z, acc[1][u]);
+                    acc[1][u] = fmaf(vb.w, wv.w, acc[1][u]);
+                }
+            }
+            // second layer: partial over this thread's 4 hidden units, then all-reduce over the 16 tx lanes
+            float z[2][G];
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+#pragma unroll
+                for (int m = 0; m < G; ++m) z[r][m] = 0.f;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int j = tx + 16 * u;
+                    const float h = fmaxf(acc[r][u] + b1s[j], 0.f);
+#pragma unroll
+                    for (int m = 0; m < G; ++m) z[r][m] = fmaf(h, w2s[m * H + j], z[r][m]);
+                }
+            }
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1)
+#pragma unroll
+                for (int r = 0; r < 2; ++r)
+#pragma unroll
+                    for (int m = 0; m < G; ++m) z[r][m] += __shfl_xor_sync(FULL, z[r][m], o);
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int rt = ty + 16 * r;
+                const int32_t row = rows_s[rt];
+                if (row < 0) continue;
+                const int64_t slot = slot0 + rt;
+                float g[G];
+#pragma unroll
+                for (int m = 0; m < G; ++m) g[m] = sigmoidf_exact(z[r][m] + b2s[m]);
+                if (gate != nullptr && tx < G) gate[slot * G + tx] = tx == 0 ? g[0] : tx == 1 ? g[1] : tx == 2 ? g[2] : g[3];
+                const float* kp = keys + row;
+                const float dlt = kp[(int64_t)(2 * C) * key_stride];
+                const float bgm = kp[(int64_t)(2 * C + 2) * key_stride];
+                for (int c = tx; c < C; c += 16) {
+                    // same association as the reference: ((g0*L + g1*P) + g2*delta) + g3*bg, no fma contraction
+                    float f = a0 * __fmul_rn(g[0], kp[(int64_t)c * key_stride]);
+                    f = __fadd_rn(f, a1 * __fmul_rn(g[1], kp[(int64_t)(C + c) * key_stride]));
+                    f = __fadd_rn(f, a2 * __fmul_rn(g[2], dlt));
+                    f = __fadd_rn(f, a3 * __fmul_rn(g[3], bgm));
+                    final_scores[slot * C + c] = f;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Per (slide, class): mean of the min(topk, S) largest combined scores; remembers which rows won.
+// One warp per (slide, class); K rounds of "largest key strictly below the previous winner".
+// ------------------------------------------------------------------------------------------------
+constexpr int POOL_WARPS = 4;
+__global__ void __launch_bounds__(POOL_WARPS * 32)
+pool_final_kernel(const float* __restrict__ final_scores, const int64_t* __restrict__ sel_base,
+                  const int32_t* __restrict__ sel_count, int n_slides, int C, int topk,
+                  float* __restrict__ bag_logits, int32_t* __restrict__ pool_pos) {
+    const int lane = threadIdx.x & 31;
+    const int64_t item = (int64_t)blockIdx.x * POOL_WARPS + (threadIdx.x >> 5);
+    if (item >= (int64_t)n_slides * C) return;
+    const int slide = (int)(item / C), c = (int)(item % C);
+    const int S = sel_count[slide];
+    const float* f = final_scores + sel_base[slide] * C + c;
+    const int k_eff = topk < S ? topk : S;
+    unsigned long long prev = ~0ull;
+    float sum = 0.f;
+    int32_t* pp = pool_pos ? pool_pos + ((int64_t)slide * C + c) * topk : nullptr;
+    for (int r = 0; r < k_eff; ++r) {
+        unsigned long long best = 0ull;
+        for (int i = lane; i < S; i += 32) {
+            const unsigned long long key =
+                ((unsigned long long)f2ord(f[(int64_t)i * C]) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)i);
+            if (key < prev && key > best) best = key;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(FULL, best, o);
+            best = other > best ? other : best;
+        }
+        prev = best;
+        const uint32_t pos = 0xffffffffu - (uint32_t)(best & 0xffffffffull);
+        sum += ord2f((uint32_t)(best >> 32));
+        if (pp && lane == 0) pp[r] = (int32_t)pos;
+    }
+    if (lane == 0) {
+        bag_logits[(int64_t)slide * C + c] = k_eff > 0 ? sum / (float)k_eff : 0.f;
+        if (pp)
+            for (int r = k_eff; r < topk; ++r) pp[r] = -1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// cross_entropy(logits[1,C], label) per slide; optional gradient and argmax.
+// ------------------------------------------------------------------------------------------------
+__global__ void cross_entropy_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels, int n, int C,
+                                     float grad_scale, float* __restrict__ loss, float* __restrict__ dlogits,
+                                     int32_t* __restrict__ pred) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* x = logits + (int64_t)i * C;
+    float m = x[0];
+    int am = 0;
+    for (int c = 1; c < C; ++c)
+        if (x[c] > m) { m = x[c]; am = c; }
+    float s = 0.f;
+    for (int c = 0; c < C; ++c) s += expf(x[c] - m);
+    const float lse = logf(s);
+    const int y = (int)labels[i];
+    if (loss) loss[i] = -((x[y] - m) - lse);
+    if (pred) pred[i] = am;
+    if (dlogits) {
+        for (int c = 0; c < C; ++c) {
+            const float p = expf((x[c] - m) - lse);
+            dlogits[(int64_t)i * C + c] = grad_scale * (p - (c == y ? 1.f : 0.f));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Backward.  Every pooled (slide, class, rank) entry is one "virtual row" carrying gradient
+// dlogits[slide,c]/k_eff in column c only; gradients are linear in it, so a row pooled for several classes
+// is simply handled once per class.  Stage 1 recomputes the gate of each virtual row and writes
+// dz1[64], dz2[4], h[64]; stage 2 reduces the outer products over virtual rows in a fixed order.
+// ------------------------------------------------------------------------------------------------
+constexpr int BW_THREADS = 256;
+struct BwdScratch {  // per virtual row
+    float dz1[H];
+    float h[H];
+    float dz2[G];
+    int32_t row;
+    int32_t pad[3];
+};
+
+__global__ void __launch_bounds__(BW_THREADS)
+head_bwd_rows_kernel(const float* __restrict__ feat, const float* __restrict__ keys, int64_t key_stride, int C,
+                     const int64_t* __restrict__ sel_base, const int32_t* __restrict__ sel_rows,
+                     const int32_t* __restrict__ sel_count, const float* __restrict__ w1,
+                     const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
+                     unsigned active_mask, int topk, const int32_t* __restrict__ pool_pos,
+                     const float* __restrict__ dlogits, BwdScratch* __restrict__ scratch) {
+    __shared__ float z1s[H], dz2s[G];
+    const int v = blockIdx.x;  // virtual row = (slide*C + c)*topk + r
+    const int r = v % topk, c = (v / topk) % C, slide = v / (topk * C);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    BwdScratch& out = scratch[v];
+    const int32_t pos = pool_pos[v];
+    if (pos < 0) {
+        if (tid == 0) out.row = -1;
+        return;
+    }
+    (void)r;
+    const int32_t row = sel_rows[sel_base[slide] + pos];
+    const float4* xp = reinterpret_cast<const float4*>(feat + (int64_t)row * D);
+    float4 x[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) x[q] = __ldg(xp + q * 32 + lane);
+    // z1: warp w computes hidden units w*8 .. w*8+7
+#pragma unroll
+    for (int jj = 0; jj < H / (BW_THREADS / 32); ++jj) {
+        const int j = warp * (H / (BW_THREADS / 32)) + jj;
+        const float4* wp = reinterpret_cast<const float4*>(w1 + (int64_t)j * D);
+        float a = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 wv = __ldg(wp + q * 32 + lane);
+            a = fmaf(x[q].x, wv.x, a);
+            a = fmaf(x[q].y, wv.y, a);
+            a = fmaf(x[q].z, wv.z, a);
+            a = fmaf(x[q].w, wv.w, a);
+        }
+        a = warp_sum(a);
+        if (lane == 0) z1s[j] = a + b1[j];
+    }
+    __syncthreads();
+    if (warp < G) {
+        const int m = warp;
+        float a = fmaxf(z1s[lane], 0.f) * w2[m * H + lane] + fmaxf(z1s[lane + 32], 0.f) * w2[m * H + lane + 32];
+        a = warp_sum(a);
+        if (lane == 0) {
+            const float g = sigmoidf_exact(a + b2[m]);
+            const int S = sel_count[slide];
+            const int k_eff = topk < S ? topk : S;
+            const float dF = dlogits[(int64_t)slide * C + c] / (float)k_eff;
+            const float* kp = keys + row;
+            float psi;
+            if (m == 0) psi = kp[(int64_t)c * key_stride];
+            else if (m == 1) psi = kp[(int64_t)(C + c) * key_stride];
+            else if (m == 2) psi = kp[(int64_t)(2 * C) * key_stride];
+            else psi = kp[(int64_t)(2 * C + 2) * key_stride];
+            const float act = ((active_mask >> m) & 1u) ? 1.f : 0.f;
+            dz2s[m] = act * dF * psi * g * (1.f - g);
+        }
+    }
+    __syncthreads();
+    if (tid < H) {
+        const float z = z1s[tid];
+        float dh = 0.f;
+#pragma unroll
+        for (int m = 0; m < G; ++m) dh = fmaf(dz2s[m], w2[m * H + tid], dh);
+        out.dz1[tid] = z > 0.f ? dh : 0.f;
+        out.h[tid] = fmaxf(z, 0.f);
+    }
+    if (tid < G) out.dz2[tid] = dz2s[tid];
+    if (tid == 0) out.row = row;
+}
+
+// grid H+1: block j < 64 -> dW1[j][:] and db1[j]; block 64 -> dW2, db2.
+__global__ void __launch_bounds__(128)
+head_bwd_reduce_kernel(const float* __restrict__ feat, const BwdScratch* __restrict__ scratch, int n_virtual,
+                       float* __restrict__ grads) {
+    const int tid = threadIdx.x;
+    float* dw1 = grads;
+    float* db1 = grads + H * D;
+    float* dw2 = db1 + H;
+    float* db2 = dw2 + G * H;
+    if (blockIdx.x < H) {
+        const int j = blockIdx.x;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        float bsum = 0.f;
+        for (int v = 0; v < n_virtual; ++v) {
+            const int32_t row = scratch[v].row;
+            if (row < 0) continue;
+            const float d = scratch[v].dz1[j];
+            const float4 xv = __ldg(reinterpret_cast<const float4*>(feat + (int64_t)row * D) + tid);
+            acc.x = fmaf(d, xv.x, acc.x);
+            acc.y = fmaf(d, xv.y, acc.y);
+            acc.z = fmaf(d, xv.z, acc.z);
+            acc.w = fmaf(d, xv.w, acc.w);
+            bsum += d;
+        }
+        reinterpret_cast<float4*>(dw1 + (int64_t)j * D)[tid] = acc;
+        if (tid == 0) db1[j] = bsum;
+    } else {
+        for (int o = tid; o < G * H; o += blockDim.x) {
+            const int m = o / H, j = o % H;
+            float a = 0.f;
+            for (int v = 0; v < n_virtual; ++v)
+                if (scratch[v].row >= 0) a = fmaf(scratch[v].dz2[m], scratch[v].h[j], a);
+            dw2[o] = a;
+        }
+        if (tid < G) {
+            float a = 0.f;
+            for (int v = 0; v < n_virtual; ++v)
+                if (scratch[v].row >= 0) a += scratch[v].dz2[tid];
+            db2[tid] = a;
+        }
+    }
+}
+
+// torch.optim.Adam, single tensor, weight decay folded into the gradient (torch/optim/adam.py _single_tensor_adam)
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, int64_t n, float lr, float beta1, float beta2, float eps,
+                            float wd, float step_size, float bc2_sqrt) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float pi = p[i];
+    const float gi = __fmaf_rn(wd, pi, g[i]);
+    // exp_avg.lerp_(grad, 1-beta1); exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1-beta2)
+    const float mi = __fmaf_rn(1.f - beta1, gi - m[i], m[i]);
+    const float vi = __fmaf_rn(__fmul_rn(gi, gi), 1.f - beta2, __fmul_rn(v[i], beta2));
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = __fadd_rn(__fdiv_rn(sqrtf(vi), bc2_sqrt), eps);
+    p[i] = pi - step_size * __fdiv_rn(mi, denom);
+}
+
+}  // namespace moc
+
+using namespace moc;
+
+extern "C" int moc_head_forward(const float* feat, const float* keys, int64_t key_stride, int n_classes,
+                                const int64_t* sel_base, const int32_t* sel_rows, const int32_t* sel_count,
+                                int n_slides, int64_t sel_capacity_total, const float* w1, const float* b1,
+                                const float* w2, const float* b2, unsigned active_mask, int topk, float* gate,
+                                float* final_scores, float* bag_logits, int32_t* pool_pos, void* stream) {
+    MOC_CHECK_ARG(feat && keys && sel_base && sel_rows && sel_count && w1 && b1 && w2 && b2 && final_scores &&
+                      bag_logits,
+                  "moc_head_forward: null pointer");
+    MOC_CHECK_ARG(n_slides >= 0 && sel_capacity_total >= 0 && topk >= 1, "moc_head_forward: bad sizes");
+    MOC_CHECK_SHAPE(n_classes >= 2 && n_classes < MOC_MAX_COLS, "moc_head_forward: bad class count %d", n_classes);
+    if (n_slides == 0) return MOC_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (sel_capacity_total > 0) {
+        const size_t smem = (size_t)(H + HR_TM) * HR_LD * sizeof(float);
+        MOC_CUDA(cudaFuncSetAttribute(head_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int64_t n_tiles = (sel_capacity_total + HR_TM - 1) / HR_TM;
+        const int grid = (int)(n_tiles < sm_count() ? n_tiles : sm_count());
+        head_rows_kernel<<<grid, HR_THREADS, smem, st>>>(feat, keys, key_stride, n_classes, sel_rows,
+                                                         sel_capacity_total, w1, b1, w2, b2, active_mask, gate,
+                                                         final_scores);
+        MOC_LAUNCH_CHECK("head_rows_kernel");
+    }
+    const int64_t items = (int64_t)n_slides * n_classes;
+    pool_final_kernel<<<(unsigned)((items + POOL_WARPS - 1) / POOL_WARPS), POOL_WARPS * 32, 0, st>>>(
+        final_scores, sel_base, sel_count, n_slides, n_classes, topk, bag_logits, pool_pos);
+    MOC_LAUNCH_CHECK("pool_final_kernel");
+    return MOC_OK;
+}
+
+extern "C" int moc_cross_entropy(const float* bag_logits, const int64_t* labels, int n_slides, int n_classes,
+                                 float grad_scale, float* loss, float* dlogits, int32_t* pred, void* stream) {
+    MOC_CHECK_ARG(bag_logits && labels, "moc_cross_entropy: null pointer");
+    MOC_CHECK_ARG(n_slides >= 0 && n_classes >= 1, "moc_cross_entropy: bad sizes");
+    if (n_slides == 0) return MOC_OK;
+    cross_entropy_kernel<<<(n_slides + 127) / 128, 128, 0, (cudaStream_t)stream>>>(bag_logits, labels, n_slides,
+                                                                                  n_classes, grad_scale, loss, dlogits,
+                                                                                  pred);
+    MOC_LAUNCH_CHECK("cross_entropy_kernel");
+    return MOC_OK;
+}
+
+extern "C" size_t moc_head_backward_workspace_bytes(int n_slides, int n_classes, int topk) {
+    return (size_t)n_slides * n_classes * topk * sizeof(BwdScratch);
+}
+
+extern "C" int moc_head_backward(const float* feat, const float* keys, int64_t key_stride, int n_classes,
+                                 const int64_t* sel_base, const int32_t* sel_rows, const int32_t* sel_count,
+                                 int n_slides, const float* w1, const float* b1, const float* w2, const float* b2,
+                                 unsigned active_mask, int topk, const int32_t* pool_pos, const float* dlogits,
+                                 float* grads, void* workspace, size_t workspace_bytes, void* stream) {
+    MOC_CHECK_ARG(feat && keys && sel_base && sel_rows && sel_count && w1 && b1 && w2 && b2 && pool_pos && dlogits &&
+                      grads && workspace,
+                  "moc_head_backward: null pointer");
+    MOC_CHECK_ARG(n_slides >= 1 && topk >= 1, "moc_head_backward: bad sizes");
+    MOC_CHECK_SHAPE(n_classes >= 2 && n_classes < MOC_MAX_COLS, "moc_head_backward: bad class count %d", n_classes);
+    const size_t need = moc_head_backward_workspace_bytes(n_slides, n_classes, topk);
+    if (workspace_bytes < need) {
+        set_error("moc_head_backward: workspace %zu B < required %zu B", workspace_bytes, need);
+        return MOC_E_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n_virtual = n_slides * n_classes * topk;
+    BwdScratch* scratch = reinterpret_cast<BwdScratch*>(workspace);
+    head_bwd_rows_kernel<<<n_virtual, BW_THREADS, 0, st>>>(feat, keys, key_stride, n_classes, sel_base, sel_rows,
+                                                          sel_count, w1, b1, w2, b2, active_mask, topk, pool_pos,
+                                                          dlogits, scratch);
+    MOC_LAUNCH_CHECK("head_bwd_rows_kernel");
+    head_bwd_reduce_kernel<<<H + 1, 128, 0, st>>>(feat, scratch, n_virtual, grads);
+    MOC_LAUNCH_CHECK("head_bwd_reduce_kernel");
+    return MOC_OK;
+}
+
+extern "C" int moc_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                             int64_t step, float lr, float beta1, float beta2, float eps, float weight_decay,
+                             void* stream) {
+    MOC_CHECK_ARG(params && grads && exp_avg && exp_avg_sq, "moc_adam_step: null pointer");
+    MOC_CHECK_ARG(n >= 0 && step >= 1, "moc_adam_step: bad n / step");
+    if (n == 0) return MOC_OK;
+    const double bc1 = 1.0 - pow((double)beta1, (double)step);
+    const double bc2 = 1.0 - pow((double)beta2, (double)step);
+    adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, (float)((double)lr / bc1),
+        (float)sqrt(bc2));
+    MOC_LAUNCH_CHECK("adam_kernel");
+    return MOC_OK;
+}

@@ -1,0 +1,431 @@
+// Top-J patch selection, union and ascending compaction; sorted top-J; pooled top-K.
+//
+// Replaces utils/patch_selection_classifier_index.py:17-87 (the four selectors), the Python set union and
+// sort of main_moc.py:341-354, Tensor.topk in the selectors' return values, and topj_pooling /
+// delta_*_classifier_pooling (utils/patch_selection_classifier.py:18-78) for the zero-shot path.
+//
+// Selection is an exact radix select on the order-preserving uint32 image of the fp32 keys: four 8-bit
+// passes find the value of rank J, rows strictly beyond it are taken, and ties at the threshold are taken
+// in ascending row order until exactly J rows are chosen (torch leaves tie order unspecified).  The union of
+// the 2C+2 selections of a slide is a bitmap over its rows, so the ascending order of the reference's
+// sorted(set(...)) falls out of the compaction for free and nothing ever goes back to the host.
+#include "common.cuh"
+
+namespace moc {
+
+constexpr int SEL_THREADS = 512;
+constexpr int SEL_WARPS = SEL_THREADS / 32;
+
+struct SelShared {
+    unsigned int hist[256];
+    unsigned int warp_tot[SEL_WARPS];
+    unsigned int prefix;
+    unsigned int need;
+    unsigned int n_equal;
+    unsigned int taken;
+    unsigned int n_kept;
+};
+
+template <bool SMALLEST>
+__device__ __forceinline__ uint32_t sel_key(float v) {
+    const uint32_t u = f2ord(v);
+    return SMALLEST ? ~u : u;
+}
+
+// Block-wide: value (as ordered uint) of the element of rank j (1-based, largest first) among the kept
+// rows of v[i*ld], i<n.  Leaves sh.prefix = threshold, sh.need = how many threshold-equal rows to take,
+// sh.n_equal = how many exist.  Requires 1 <= j <= kept rows.
+template <bool SMALLEST, bool HAS_MASK>
+__device__ void radix_threshold(const float* __restrict__ v, int64_t ld, const uint8_t* __restrict__ mk, int n, int j,
+                                SelShared& sh) {
+    const int tid = threadIdx.x;
+    uint32_t prefix = 0, known = 0;
+    uint32_t need = (uint32_t)j;
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        if (tid < 256) sh.hist[tid] = 0;
+        __syncthreads();
+        int cur_bin = -1;
+        unsigned int cur_cnt = 0;
+        for (int i = tid; i < n; i += SEL_THREADS) {
+            if (HAS_MASK && !mk[i]) continue;
+            const uint32_t u = sel_key<SMALLEST>(v[(int64_t)i * ld]);
+            if ((u & known) != prefix) continue;
+            const int b = (u >> shift) & 255;
+            if (b == cur_bin) {
+                ++cur_cnt;
+            } else {
+                if (cur_cnt) atomicAdd(&sh.hist[cur_bin], cur_cnt);
+                cur_bin = b;
+                cur_cnt = 1;
+            }
+        }
+        if (cur_cnt) atomicAdd(&sh.hist[cur_bin], cur_cnt);
+        __syncthreads();
+        if (tid < 32) {
+            // lane l owns bins 255-8l .. 248-8l (descending); find where the running count reaches `need`
+            unsigned int loc[8], s = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                loc[k] = sh.hist[255 - (tid * 8 + k)];
+                s += loc[k];
+            }
+            unsigned int incl = s;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned int t = __shfl_up_sync(FULL, incl, o);
+                if (tid >= o) incl += t;
+            }
+            const unsigned int excl = incl - s;
+            if (excl < need && need <= incl) {
+                unsigned int run = excl;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    if (run < need && need <= run + loc[k]) {
+                        sh.prefix = prefix | ((uint32_t)(255 - (tid * 8 + k)) << shift);
+                        sh.need = need - run;
+                        sh.n_equal = loc[k];
+                    }
+                    run += loc[k];
+                }
+            }
+        }
+        __syncthreads();
+        prefix = sh.prefix;
+        need = sh.need;
+        known |= 255u << shift;
+        // (the next pass's hist reset is ordered after these reads by its own __syncthreads)
+        __syncthreads();
+    }
+}
+
+// Calls emit(i) for exactly the j selected rows (unordered, except that threshold ties are resolved towards
+// lower row indices).  Block-wide; all threads must call.
+template <bool SMALLEST, bool HAS_MASK, typename Emit>
+__device__ void select_rows(const float* __restrict__ v, int64_t ld, const uint8_t* __restrict__ mk, int n, int n_kept,
+                            int j, SelShared& sh, Emit emit) {
+    const int tid = threadIdx.x;
+    if (j <= 0) return;
+    if (j >= n_kept) {
+        for (int i = tid; i < n; i += SEL_THREADS)
+            if (!HAS_MASK || mk[i]) emit(i);
+        return;
+    }
+    radix_threshold<SMALLEST, HAS_MASK>(v, ld, mk, n, j, sh);
+    const uint32_t thr = sh.prefix;
+    const uint32_t need = sh.need;
+    const bool all_equal_taken = (sh.n_equal == need);
+    for (int i = tid; i < n; i += SEL_THREADS) {
+        if (HAS_MASK && !mk[i]) continue;
+        const uint32_t u = sel_key<SMALLEST>(v[(int64_t)i * ld]);
+        if (u > thr || (all_equal_taken && u == thr)) emit(i);
+    }
+    if (all_equal_taken) return;
+    // more rows sit exactly at the threshold than are needed: take the first `need` in row order
+    if (tid == 0) sh.taken = 0;
+    __syncthreads();
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int base = 0; base < n; base += SEL_THREADS) {
+        const int i = base + tid;
+        bool eq = false;
+        if (i < n && (!HAS_MASK || mk[i])) eq = sel_key<SMALLEST>(v[(int64_t)i * ld]) == thr;
+        const unsigned int bal = __ballot_sync(FULL, eq);
+        if (lane == 0) sh.warp_tot[warp] = __popc(bal);
+        __syncthreads();
+        unsigned int before = sh.taken, total = 0;
+        for (int w = 0; w < SEL_WARPS; ++w) {
+            const unsigned int t = sh.warp_tot[w];
+            if (w < warp) before += t;
+            total += t;
+        }
+        const unsigned int rank = before + __popc(bal & ((1u << lane) - 1u));
+        if (eq && rank < need) emit(i);
+        __syncthreads();
+        if (tid == 0) sh.taken += total;
+        __syncthreads();
+        if (sh.taken >= need) break;
+    }
+}
+
+template <bool HAS_MASK>
+__device__ int count_kept(const uint8_t* __restrict__ mk, int n, SelShared& sh) {
+    if (!HAS_MASK) return n;
+    if (threadIdx.x == 0) sh.n_kept = 0;
+    __syncthreads();
+    unsigned int c = 0;
+    for (int i = threadIdx.x; i < n; i += SEL_THREADS) c += mk[i] != 0;
+    c = (unsigned int)__reduce_add_sync(FULL, c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&sh.n_kept, c);
+    __syncthreads();
+    return (int)sh.n_kept;
+}
+
+// grid (n_slides, 2C+2): one selection of one slide per CTA; marks the chosen rows in the global bitmap.
+template <bool HAS_MASK>
+__global__ void __launch_bounds__(SEL_THREADS)
+select_mark_kernel(const float* __restrict__ keys, int64_t key_stride, const int64_t* __restrict__ offsets, int C,
+                   int topj, unsigned discard_mask, const uint8_t* __restrict__ row_mask,
+                   unsigned int* __restrict__ bitmap) {
+    __shared__ SelShared sh;
+    const int q = blockIdx.y, slide = blockIdx.x;
+    unsigned cls;
+    int plane;
+    bool smallest = false;
+    if (q < C) { cls = MOC_CLS_TOPK; plane = q; }
+    else if (q < 2 * C) { cls = MOC_CLS_DELTA_SOFTMAX; plane = q; }
+    else if (q == 2 * C) { cls = MOC_CLS_DELTA_DIFF; plane = 2 * C; }
+    else { cls = MOC_CLS_BOTTOMK; plane = 2 * C + 1; smallest = true; }
+    if (discard_mask & cls) return;
+    const int64_t row0 = offsets[slide];
+    const int n = (int)(offsets[slide + 1] - row0);
+    if (n <= 0) return;
+    const float* v = keys + (int64_t)plane * key_stride + row0;
+    const uint8_t* mk = HAS_MASK ? row_mask + row0 : nullptr;
+    const int n_kept = count_kept<HAS_MASK>(mk, n, sh);
+    const int j = topj < n_kept ? topj : n_kept;
+    auto mark = [&](int i) {
+        const int64_t r = row0 + i;
+        atomicOr(&bitmap[r >> 5], 1u << (r & 31));
+    };
+    if (smallest) select_rows<true, HAS_MASK>(v, 1, mk, n, n_kept, j, sh, mark);
+    else select_rows<false, HAS_MASK>(v, 1, mk, n, n_kept, j, sh, mark);
+}
+
+// grid n_slides: bitmap -> ascending row list (+ index inside the masked bag), count per slide.
+constexpr int CMP_THREADS = 256;
+template <bool HAS_MASK>
+__global__ void __launch_bounds__(CMP_THREADS)
+compact_kernel(const unsigned int* __restrict__ bitmap, const int64_t* __restrict__ offsets,
+               const uint8_t* __restrict__ row_mask, const int64_t* __restrict__ sel_base,
+               int32_t* __restrict__ sel_rows, int32_t* __restrict__ sel_local, int32_t* __restrict__ sel_count) {
+    __shared__ unsigned long long warp_tot[CMP_THREADS / 32];
+    __shared__ unsigned long long running;
+    const int slide = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t row0 = offsets[slide], row1 = offsets[slide + 1];
+    if (tid == 0) running = 0;
+    __syncthreads();
+    if (row1 > row0) {
+        const int64_t w0 = row0 >> 5, w1 = (row1 - 1) >> 5;
+        const int64_t out0 = sel_base[slide];
+        for (int64_t wb = w0; wb <= w1; wb += CMP_THREADS) {
+            const int64_t w = wb + tid;
+            unsigned int bits = 0, kept = 0;
+            if (w <= w1) {
+                unsigned int valid = 0xffffffffu;
+                const int64_t first = w << 5;
+                if (first < row0) valid &= 0xffffffffu << (row0 - first);
+                if (first + 32 > row1) valid &= 0xffffffffu >> (first + 32 - row1);
+                bits = bitmap[w] & valid;
+                if (HAS_MASK) {
+                    for (int b = 0; b < 32; ++b)
+                        if ((valid >> b) & 1u) kept |= (row_mask[first + b] != 0 ? 1u : 0u) << b;
+                } else {
+                    kept = valid;
+                }
+            }
+            // one scan for both counts: high word = kept rows, low word = selected rows
+            const unsigned long long mine = ((unsigned long long)__popc(kept) << 32) | (unsigned long long)__popc(bits);
+            unsigned long long incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long t = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (lane == 31) warp_tot[warp] = incl;
+            __syncthreads();
+            unsigned long long before = running, total = 0;
+            for (int k = 0; k < CMP_THREADS / 32; ++k) {
+                const unsigned long long t = warp_tot[k];
+                if (k < warp) before += t;
+                total += t;
+            }
+            const unsigned long long excl = before + incl - mine;
+            int64_t pos = out0 + (int64_t)(excl & 0xffffffffull);
+            const int kept_before = (int)(excl >> 32);
+            while (bits) {
+                const int b = __ffs(bits) - 1;
+                bits &= bits - 1;
+                sel_rows[pos] = (int32_t)((w << 5) + b);
+                sel_local[pos] = kept_before + __popc(kept & ((1u << b) - 1u));
+                ++pos;
+            }
+            __syncthreads();
+            if (tid == 0) running += total;
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    const int64_t count = (int64_t)(running & 0xffffffffull);
+    if (tid == 0) sel_count[slide] = (int32_t)count;
+    // unused tail of this slide's region: -1, so consumers can walk regions without the counts
+    for (int64_t p = sel_base[slide] + count + tid; p < sel_base[slide + 1]; p += CMP_THREADS) sel_rows[p] = -1;
+}
+
+// ---- stand-alone sorted top-J ------------------------------------------------------------------
+// grid n_cols; dynamic smem: P uint64 sort keys.
+__global__ void __launch_bounds__(SEL_THREADS)
+topj_sorted_kernel(const float* __restrict__ values, int n, int64_t ld, int64_t col_stride, int j, int largest,
+                   int sort_pow2, int64_t* __restrict__ idx_out, int64_t out_ld, float* __restrict__ val_out) {
+    extern __shared__ unsigned long long skeys[];
+    __shared__ SelShared sh;
+    __shared__ unsigned int n_out;
+    const int col = blockIdx.x, tid = threadIdx.x;
+    const float* v = values + (int64_t)col * col_stride;
+    if (tid == 0) n_out = 0;
+    for (int i = tid; i < sort_pow2; i += SEL_THREADS) skeys[i] = 0ull;
+    __syncthreads();
+    const bool small = !largest;
+    auto push = [&](int i) {
+        const uint32_t u = small ? ~f2ord(v[(int64_t)i * ld]) : f2ord(v[(int64_t)i * ld]);
+        const unsigned int slot = atomicAdd(&n_out, 1u);
+        // descending sort of (key, ~index): larger value first, lower index first among equals
+        skeys[slot] = (unsigned long long)u << 32 | (unsigned long long)(0xffffffffu - (uint32_t)i);
+    };
+    if (small) select_rows<true, false>(v, ld, nullptr, n, n, j, sh, push);
+    else select_rows<false, false>(v, ld, nullptr, n, n, j, sh, push);
+    __syncthreads();
+    // bitonic sort, descending
+    for (int k = 2; k <= sort_pow2; k <<= 1) {
+        for (int s = k >> 1; s > 0; s >>= 1) {
+            for (int i = tid; i < sort_pow2; i += SEL_THREADS) {
+                const int p = i ^ s;
+                if (p > i) {
+                    const unsigned long long a = skeys[i], b = skeys[p];
+                    const bool desc = (i & k) == 0;
+                    if (desc ? (a < b) : (a > b)) { skeys[i] = b; skeys[p] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int r = tid; r < j; r += SEL_THREADS) {
+        const unsigned long long kk = skeys[r];
+        const uint32_t i = 0xffffffffu - (uint32_t)(kk & 0xffffffffull);
+        idx_out[(int64_t)r * out_ld + col] = (int64_t)i;
+        if (val_out) val_out[(int64_t)r * out_ld + col] = v[(int64_t)i * ld];
+    }
+}
+
+// ---- pooled top-K over whole bags (zero-shot path) ---------------------------------------------
+// grid (n_slides, C): rows chosen by one key plane, the mean taken over another.
+constexpr int POOL_MAX_K = 64;
+__global__ void __launch_bounds__(SEL_THREADS)
+pool_topk_kernel(const float* __restrict__ keys, int64_t key_stride, const int64_t* __restrict__ offsets, int C,
+                 int topk, int sel_plane0, int sel_step, int sel_smallest, int val_plane0, int val_step,
+                 float* __restrict__ bag_logits) {
+    __shared__ SelShared sh;
+    __shared__ unsigned int n_out;
+    __shared__ unsigned long long win[POOL_MAX_K];
+    const int c = blockIdx.y, slide = blockIdx.x, tid = threadIdx.x;
+    const int64_t row0 = offsets[slide];
+    const int n = (int)(offsets[slide + 1] - row0);
+    const float* sv = keys + (int64_t)(sel_plane0 + c * sel_step) * key_stride + row0;
+    const float* vv = keys + (int64_t)(val_plane0 + c * val_step) * key_stride + row0;
+    if (tid == 0) n_out = 0;
+    __syncthreads();
+    const int k = topk < n ? topk : n;
+    const bool small = sel_smallest != 0;
+    auto push = [&](int i) {
+        const uint32_t u = small ? ~f2ord(sv[i]) : f2ord(sv[i]);
+        const unsigned int slot = atomicAdd(&n_out, 1u);
+        win[slot] = ((unsigned long long)u << 32) | (unsigned long long)(0xffffffffu - (uint32_t)i);
+    };
+    if (small) select_rows<true, false>(sv, 1, nullptr, n, n, k, sh, push);
+    else select_rows<false, false>(sv, 1, nullptr, n, n, k, sh, push);
+    __syncthreads();
+    if (tid == 0) {
+        // order the k winners (descending key, ascending row) so the fp32 sum has a fixed order
+        for (int a = 1; a < k; ++a) {
+            const unsigned long long x = win[a];
+            int b = a - 1;
+            while (b >= 0 && win[b] < x) { win[b + 1] = win[b]; --b; }
+            win[b + 1] = x;
+        }
+        float s = 0.f;
+        for (int a = 0; a < k; ++a) s += vv[0xffffffffu - (uint32_t)(win[a] & 0xffffffffull)];
+        bag_logits[(int64_t)slide * C + c] = k > 0 ? s / (float)k : 0.f;
+    }
+}
+
+}  // namespace moc
+
+using namespace moc;
+
+extern "C" int64_t moc_select_capacity(int64_t n_rows_of_slide, int n_classes, int topj) {
+    const int64_t bound = (int64_t)topj * (2 * n_classes + 2);
+    return n_rows_of_slide < bound ? n_rows_of_slide : bound;
+}
+
+extern "C" size_t moc_select_workspace_bytes(int64_t total_rows, int n_slides) {
+    (void)n_slides;
+    return (size_t)((total_rows + 31) / 32 + 1) * sizeof(unsigned int);
+}
+
+extern "C" int moc_select_union(const float* keys, int64_t key_stride, const int64_t* offsets, int n_slides,
+                                int64_t total_rows, int n_classes, int topj, unsigned discard_mask,
+                                const uint8_t* row_mask, const int64_t* sel_base, int32_t* sel_rows,
+                                int32_t* sel_local, int32_t* sel_count, void* workspace, size_t workspace_bytes,
+                                void* stream) {
+    MOC_CHECK_ARG(keys && offsets && sel_base && sel_rows && sel_local && sel_count && workspace,
+                  "moc_select_union: null pointer");
+    MOC_CHECK_ARG(n_slides >= 0 && total_rows >= 0 && topj >= 0, "moc_select_union: negative size");
+    MOC_CHECK_SHAPE(n_classes >= 2 && n_classes < MOC_MAX_COLS, "moc_select_union: bad class count %d", n_classes);
+    MOC_CHECK_SHAPE(total_rows < (1ll << 31), "moc_select_union: more than 2^31 rows in one store");
+    const size_t need = moc_select_workspace_bytes(total_rows, n_slides);
+    if (workspace_bytes < need) {
+        set_error("moc_select_union: workspace %zu B < required %zu B", workspace_bytes, need);
+        return MOC_E_WORKSPACE;
+    }
+    if (n_slides == 0) return MOC_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned int* bitmap = reinterpret_cast<unsigned int*>(workspace);
+    MOC_CUDA(cudaMemsetAsync(bitmap, 0, need, st));
+    const dim3 grid(n_slides, 2 * n_classes + 2);
+    if (row_mask) {
+        select_mark_kernel<true><<<grid, SEL_THREADS, 0, st>>>(keys, key_stride, offsets, n_classes, topj, discard_mask,
+                                                              row_mask, bitmap);
+        MOC_LAUNCH_CHECK("select_mark_kernel");
+        compact_kernel<true><<<n_slides, CMP_THREADS, 0, st>>>(bitmap, offsets, row_mask, sel_base, sel_rows, sel_local,
+                                                             sel_count);
+    } else {
+        select_mark_kernel<false><<<grid, SEL_THREADS, 0, st>>>(keys, key_stride, offsets, n_classes, topj,
+                                                               discard_mask, nullptr, bitmap);
+        MOC_LAUNCH_CHECK("select_mark_kernel");
+        compact_kernel<false><<<n_slides, CMP_THREADS, 0, st>>>(bitmap, offsets, nullptr, sel_base, sel_rows, sel_local,
+                                                              sel_count);
+    }
+    MOC_LAUNCH_CHECK("compact_kernel");
+    return MOC_OK;
+}
+
+extern "C" int moc_topj_sorted(const float* values, int64_t n, int64_t ld, int n_cols, int64_t col_stride, int j,
+                               int largest, int64_t* idx_out, int64_t out_ld, float* val_out, void* stream) {
+    MOC_CHECK_ARG(values && idx_out, "moc_topj_sorted: null pointer");
+    MOC_CHECK_ARG(n >= 0 && n < (1ll << 31) && ld >= 1 && n_cols >= 0 && j >= 0 && out_ld >= n_cols,
+                  "moc_topj_sorted: bad sizes");
+    if (j > n) j = (int)n;
+    if (n_cols == 0 || j == 0) return MOC_OK;
+    int p2 = 1;
+    while (p2 < j) p2 <<= 1;
+    MOC_CHECK_SHAPE(p2 <= 16384, "moc_topj_sorted: topj %d exceeds the 16384 rows this build sorts on chip", j);
+    const size_t smem = (size_t)p2 * sizeof(unsigned long long);
+    MOC_CUDA(cudaFuncSetAttribute(topj_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
+    topj_sorted_kernel<<<n_cols, SEL_THREADS, smem, (cudaStream_t)stream>>>(values, (int)n, ld, col_stride, j, largest,
+                                                                           p2, idx_out, out_ld, val_out);
+    MOC_LAUNCH_CHECK("topj_sorted_kernel");
+    return MOC_OK;
+}
+
+extern "C" int moc_pool_topk(const float* keys, int64_t key_stride, const int64_t* offsets, int n_slides,
+                             int n_classes, int topk, int sel_plane0, int sel_step, int sel_smallest, int val_plane0,
+                             int val_step, float* bag_logits, void* stream) {
+    MOC_CHECK_ARG(keys && offsets && bag_logits, "moc_pool_topk: null pointer");
+    MOC_CHECK_ARG(n_slides >= 0 && n_classes >= 1, "moc_pool_topk: bad sizes");
+    MOC_CHECK_SHAPE(topk >= 1 && topk <= POOL_MAX_K, "moc_pool_topk: topk must be in [1,%d], got %d", POOL_MAX_K, topk);
+    if (n_slides == 0) return MOC_OK;
+    pool_topk_kernel<<<dim3(n_slides, n_classes), SEL_THREADS, 0, (cudaStream_t)stream>>>(
+        keys, key_stride, offsets, n_classes, topk, sel_plane0, sel_step, sel_smallest, val_plane0, val_step,
+        bag_logits);
+    MOC_LAUNCH_CHECK("pool_topk_kernel");
+    return MOC_OK;
+}

@@ -1,0 +1,228 @@
+"""Tensor-level wrappers over the C ABI: torch tensors in, torch tensors out, current CUDA stream.
+
+torch is used here only for device memory, streams and (elsewhere) torch.distributed; every kernel that
+runs is one of ours from libmoc_b200.so.  Nothing in this module falls back to torch math.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import MocError, check
+
+D = 512
+HIDDEN = 64
+GATES = 4
+NUM_PARAMS = _lib.NUM_PARAMS
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dev_f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise MocError(_lib.E_ARG, "%s must be a CUDA tensor (moc_b200 has no CPU path)" % name)
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class Prompts:
+    """The two zero-shot classifier matrices in the packed layout the scoring kernel reads."""
+    packed: torch.Tensor      # [cols_pad, 512]
+    n_classes: int
+    n_ext: int
+
+    @staticmethod
+    def pack(w: torch.Tensor, w_ext: torch.Tensor) -> "Prompts":
+        w, w_ext = _dev_f32(w, "zeroshot_weights"), _dev_f32(w_ext, "zeroshot_weights_ext")
+        if w.dim() != 2 or w_ext.dim() != 2 or w.size(0) != D or w_ext.size(0) != D:
+            raise MocError(_lib.E_SHAPE, "prompt matrices must be [512,C] and [512,C_ext]")
+        c, ce = w.size(1), w_ext.size(1)
+        lib = _lib.load()
+        packed = torch.empty(lib.moc_packed_cols(c, ce), D, device=w.device, dtype=torch.float32)
+        check(lib.moc_pack_prompts(w.data_ptr(), c, w_ext.data_ptr(), ce, packed.data_ptr(), _stream()))
+        return Prompts(packed, c, ce)
+
+
+def num_key_planes(n_classes: int) -> int:
+    return 2 * n_classes + 3
+
+
+def score_keys(feat: torch.Tensor, prompts: Prompts, normalize: bool = False,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """keys [2C+3, R] (plane-major) for R rows of feat [R,512]."""
+    feat = _dev_f32(feat, "feat")
+    if feat.dim() != 2 or feat.size(1) != D:
+        raise MocError(_lib.E_SHAPE, "feat must be [rows,512], got %s" % (tuple(feat.shape),))
+    r = feat.size(0)
+    if out is None:
+        out = torch.empty(num_key_planes(prompts.n_classes), r, device=feat.device, dtype=torch.float32)
+    check(_lib.load().moc_score_keys(feat.data_ptr(), r, prompts.packed.data_ptr(), prompts.n_classes,
+                                     prompts.n_ext, int(bool(normalize)), out.data_ptr(), out.stride(0), _stream()))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class Selection:
+    """Union of the top-J selections of a batch of slides (device-resident, ragged)."""
+    sel_base: torch.Tensor     # int64 [n_slides+1], start of every slide's region
+    sel_base_h: List[int]
+    sel_rows: torch.Tensor     # int32 [capacity], absolute feat rows, ascending per slide, -1 padded
+    sel_local: torch.Tensor    # int32 [capacity], index inside the (masked) bag = the reference's selected_index
+    sel_count: torch.Tensor    # int32 [n_slides]
+    n_slides: int
+
+    @property
+    def capacity(self) -> int:
+        return self.sel_base_h[-1]
+
+
+def selection_layout(offsets_h: Sequence[int], n_classes: int, topj: int):
+    bound = topj * (2 * n_classes + 2)
+    base = [0]
+    for i in range(len(offsets_h) - 1):
+        base.append(base[-1] + min(offsets_h[i + 1] - offsets_h[i], bound))
+    return base
+
+
+def select_union(keys: torch.Tensor, offsets: torch.Tensor, offsets_h: Sequence[int], n_classes: int, topj: int,
+                 discard_mask: int = 0, row_mask: Optional[torch.Tensor] = None,
+                 sel_base: Optional[torch.Tensor] = None, sel_base_h: Optional[List[int]] = None) -> Selection:
+    n_slides = len(offsets_h) - 1
+    total_rows = int(offsets_h[-1])
+    dev = keys.device
+    if sel_base_h is None:
+        sel_base_h = selection_layout(offsets_h, n_classes, topj)
+        sel_base = torch.tensor(sel_base_h, dtype=torch.int64, device=dev)
+    cap = max(sel_base_h[-1], 1)
+    sel_rows = torch.empty(cap, dtype=torch.int32, device=dev)
+    sel_local = torch.empty(cap, dtype=torch.int32, device=dev)
+    sel_count = torch.empty(max(n_slides, 1), dtype=torch.int32, device=dev)
+    lib = _lib.load()
+    ws_bytes = lib.moc_select_workspace_bytes(total_rows, n_slides)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    if row_mask is not None:
+        if row_mask.dtype == torch.bool:
+            row_mask = row_mask.view(torch.uint8)
+        row_mask = row_mask.contiguous()
+        if not row_mask.is_cuda or row_mask.numel() != total_rows or row_mask.dtype != torch.uint8:
+            raise MocError(_lib.E_ARG, "row_mask must be a CUDA bool/uint8 tensor with one entry per row")
+    check(lib.moc_select_union(keys.data_ptr(), keys.stride(0), offsets.data_ptr(), n_slides, total_rows, n_classes,
+                               int(topj), int(discard_mask), _ptr(row_mask), sel_base.data_ptr(), sel_rows.data_ptr(),
+                               sel_local.data_ptr(), sel_count.data_ptr(), ws.data_ptr(), ws_bytes, _stream()))
+    return Selection(sel_base, list(sel_base_h), sel_rows, sel_local, sel_count, n_slides)
+
+
+def topj_sorted(values: torch.Tensor, j: int, largest: bool = True, want_values: bool = False):
+    """Column-wise Tensor.topk(j, dim=0, largest, sorted=True) of a [N,C] (or [N]) CUDA tensor -> int64 [j,C]."""
+    v = _dev_f32(values, "values")
+    squeeze = v.dim() == 1
+    if squeeze:
+        v = v.unsqueeze(1)
+    n, c = v.shape
+    j = min(int(j), n)
+    idx = torch.empty(j, c, dtype=torch.int64, device=v.device)
+    vals = torch.empty(j, c, dtype=torch.float32, device=v.device) if want_values else None
+    check(_lib.load().moc_topj_sorted(v.data_ptr(), n, v.stride(0), c, v.stride(1), j, int(bool(largest)),
+                                      idx.data_ptr(), c, _ptr(vals), _stream()))
+    if squeeze:
+        idx = idx[:, 0]
+        vals = vals[:, 0] if vals is not None else None
+    return (idx, vals) if want_values else idx
+
+
+def pool_topk(keys: torch.Tensor, offsets: torch.Tensor, n_slides: int, n_classes: int, topk: int,
+              sel_plane0: int, sel_step: int, val_plane0: int, val_step: int, smallest: bool = False) -> torch.Tensor:
+    out = torch.empty(n_slides, n_classes, dtype=torch.float32, device=keys.device)
+    check(_lib.load().moc_pool_topk(keys.data_ptr(), keys.stride(0), offsets.data_ptr(), n_slides, n_classes,
+                                    int(topk), sel_plane0, sel_step, int(smallest), val_plane0, val_step,
+                                    out.data_ptr(), _stream()))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class HeadParams:
+    """senet parameters as four contiguous fp32 CUDA tensors (views into one flat buffer when owned by
+    :class:`moc_b200.model.senet`)."""
+    w1: torch.Tensor
+    b1: torch.Tensor
+    w2: torch.Tensor
+    b2: torch.Tensor
+
+
+@dataclass
+class HeadOut:
+    final: torch.Tensor        # [capacity, C]  gated sum of the four planes per selected row
+    bag_logits: torch.Tensor   # [n_slides, C]
+    pool_pos: torch.Tensor     # int32 [n_slides, C, topk]
+    gate: Optional[torch.Tensor]  # [capacity, 4]
+
+
+def head_forward(feat: torch.Tensor, keys: torch.Tensor, n_classes: int, sel: Selection, params: HeadParams,
+                 active_mask: int, topk: int, want_gate: bool = False) -> HeadOut:
+    dev = feat.device
+    cap = max(sel.capacity, 1)
+    final = torch.empty(cap, n_classes, dtype=torch.float32, device=dev)
+    gate = torch.empty(cap, GATES, dtype=torch.float32, device=dev) if want_gate else None
+    bag = torch.empty(sel.n_slides, n_classes, dtype=torch.float32, device=dev)
+    pos = torch.empty(sel.n_slides, n_classes, topk, dtype=torch.int32, device=dev)
+    check(_lib.load().moc_head_forward(feat.data_ptr(), keys.data_ptr(), keys.stride(0), n_classes,
+                                       sel.sel_base.data_ptr(), sel.sel_rows.data_ptr(), sel.sel_count.data_ptr(),
+                                       sel.n_slides, sel.capacity, params.w1.data_ptr(), params.b1.data_ptr(),
+                                       params.w2.data_ptr(), params.b2.data_ptr(), int(active_mask), int(topk),
+                                       _ptr(gate), final.data_ptr(), bag.data_ptr(), pos.data_ptr(), _stream()))
+    return HeadOut(final, bag, pos, gate)
+
+
+def cross_entropy(bag_logits: torch.Tensor, labels: torch.Tensor, grad_scale: float = 1.0, want_grad: bool = False,
+                  want_pred: bool = False):
+    """Per-slide CE (no temperature).  Returns (loss [n], dlogits [n,C] | None, pred int32 [n] | None)."""
+    n, c = bag_logits.shape
+    dev = bag_logits.device
+    labels = labels.to(device=dev, dtype=torch.int64).contiguous()
+    loss = torch.empty(n, dtype=torch.float32, device=dev)
+    dl = torch.empty(n, c, dtype=torch.float32, device=dev) if want_grad else None
+    pred = torch.empty(n, dtype=torch.int32, device=dev) if want_pred else None
+    check(_lib.load().moc_cross_entropy(bag_logits.data_ptr(), labels.data_ptr(), n, c, float(grad_scale),
+                                        loss.data_ptr(), _ptr(dl), _ptr(pred), _stream()))
+    return loss, dl, pred
+
+
+def head_backward(feat: torch.Tensor, keys: torch.Tensor, n_classes: int, sel: Selection, params: HeadParams,
+                  active_mask: int, topk: int, pool_pos: torch.Tensor, dlogits: torch.Tensor,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Flat gradient [w1 | b1 | w2 | b2] (33 092 floats) of sum_i <dlogits_i, bag_logits_i>."""
+    dev = feat.device
+    lib = _lib.load()
+    if out is None:
+        out = torch.empty(NUM_PARAMS, dtype=torch.float32, device=dev)
+    ws_bytes = lib.moc_head_backward_workspace_bytes(sel.n_slides, n_classes, topk)
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+    dlogits = _dev_f32(dlogits, "dlogits")
+    check(lib.moc_head_backward(feat.data_ptr(), keys.data_ptr(), keys.stride(0), n_classes, sel.sel_base.data_ptr(),
+                                sel.sel_rows.data_ptr(), sel.sel_count.data_ptr(), sel.n_slides,
+                                params.w1.data_ptr(), params.b1.data_ptr(), params.w2.data_ptr(), params.b2.data_ptr(),
+                                int(active_mask), int(topk), pool_pos.data_ptr(), dlogits.data_ptr(), out.data_ptr(),
+                                ws.data_ptr(), ws_bytes, _stream()))
+    return out
+
+
+def adam_step(params: torch.Tensor, grads: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, step: int,
+              lr: float = 1e-3, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8,
+              weight_decay: float = 1e-4) -> None:
+    """In-place torch.optim.Adam update of a flat fp32 parameter buffer; ``step`` counts from 1."""
+    check(_lib.load().moc_adam_step(params.data_ptr(), grads.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
+                                    params.numel(), int(step), lr, beta1, beta2, eps, weight_decay, _stream()))

