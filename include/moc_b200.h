@@ -108,6 +108,17 @@ int moc_select_union(const float* keys, int64_t key_stride, const int64_t* offse
 int moc_topj_sorted(const float* values, int64_t n, int64_t ld, int n_cols, int64_t col_stride,
                     int j, int largest, int64_t* idx_out, int64_t out_ld, float* val_out, void* stream);
 
+/* ---- helpers behind the stand-alone selector / pooling functions ------------
+ * These take the [N,Ct] row-major logits the reference's functions are called
+ * with (columns < n_fg are classes, the rest background) instead of features. */
+int moc_row_keys(const float* logits, int64_t n, int64_t ld, int n_fg, int n_total, float* keys,
+                 int64_t key_stride, void* stream);
+/* dst[r][c] = src[idx[r]][c] for c < n_cols  (logits[indices] in the pooling functions) */
+int moc_take_rows(const float* src, int64_t ld, const int64_t* idx, int64_t n_idx, int n_cols, float* dst,
+                  void* stream);
+/* out[c] = mean of vals[0..j-1][c]  (values[:min(j,maxj)].mean(dim=0), patch_selection_classifier.py:27) */
+int moc_col_prefix_mean(const float* vals, int64_t ld, int n_cols, int j, float* out, void* stream);
+
 /* ---- a8..a11: head forward -------------------------------------------------
  * For every selected row: gather the 512-vector, senet gate
  * sigmoid(W2 relu(W1 x + b1) + b2) (main_moc.py:299-312,:390), the gated sum of
@@ -125,12 +136,36 @@ int moc_head_forward(const float* feat, const float* keys, int64_t key_stride, i
                      float* gate, float* final_scores, float* bag_logits, int32_t* pool_pos,
                      void* stream);
 
+/* ablation_evaluation (main_moc.py:523-582): un-gated avg (mode 0) / sum (1) / max (2) of the four planes
+ * of every selected row, then the same top-K pooling. */
+int moc_ablation_forward(const float* keys, int64_t key_stride, int n_classes, const int64_t* sel_base,
+                         const int32_t* sel_rows, const int32_t* sel_count, int n_slides,
+                         int64_t sel_capacity_total, int mode, int topk, float* final_scores,
+                         float* bag_logits, void* stream);
+
 /* per-(slide,class) top-K mean of one plane selected by another plane:
  * zs_evaluation's pooling (main_moc.py:427-432) with
  * select plane == value plane (topj_pooling) or softmax / delta planes. */
 int moc_pool_topk(const float* keys, int64_t key_stride, const int64_t* offsets, int n_slides,
                   int n_classes, int topk, int select_plane0, int select_plane_step, int select_smallest,
                   int value_plane0, int value_plane_step, float* bag_logits, void* stream);
+
+/* selected_feat = feat[selected_index] and the four [S,C] score planes as dense
+ * row-major tensors (main_moc.py:355-366), for callers that want the
+ * reference's slide_process() return value.  out_feat or the planes may be null. */
+int moc_gather_selected(const float* feat, const float* keys, int64_t key_stride, int n_classes,
+                        const int32_t* sel_rows, int64_t n_sel, float* out_feat, float* plane_top,
+                        float* plane_softmax, float* plane_diff, float* plane_bg, void* stream);
+
+/* senet as a stand-alone module on a dense [n_rows,512] input (main_moc.py:299-312):
+ * gate = sigmoid(W2 relu(W1 x + b1) + b2) and, for autograd, the parameter
+ * gradient given d(loss)/d(gate) [n_rows,4] (rows whose gradient is all-zero are skipped). */
+int moc_senet_forward(const float* x, int64_t n_rows, const float* w1, const float* b1, const float* w2,
+                      const float* b2, float* gate, void* stream);
+size_t moc_senet_backward_workspace_bytes(int64_t n_rows);
+int moc_senet_backward(const float* x, int64_t n_rows, const float* dgate, const float* w1, const float* b1,
+                       const float* w2, const float* b2, float* grads, void* workspace, size_t workspace_bytes,
+                       void* stream);
 
 /* ---- a12: loss, backward, optimiser ----------------------------------------
  * cross_entropy on [n,C] rows without temperature (main_moc.py:406,:494):

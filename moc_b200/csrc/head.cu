@@ -57,7 +57,7 @@ head_rows_kernel(const float* __restrict__ feat, const float* __restrict__ keys,
         const int64_t slot0 = tile * HR_TM;
         if (tid < HR_TM) {
             const int64_t s = slot0 + tid;
-            rows_s[tid] = s < n_slots ? sel_rows[s] : -1;
+            rows_s[tid] = s < n_slots ? (sel_rows ? sel_rows[s] : (int32_t)s) : -1;
         }
         __syncthreads();
         // gather: warp w loads rows w, w+8, w+16, w+24 (2 KB each, coalesced)
@@ -136,6 +136,7 @@ head_rows_kernel(const float* __restrict__ feat, const float* __restrict__ keys,
 #pragma unroll
                 for (int m = 0; m < G; ++m) g[m] = sigmoidf_exact(z[r][m] + b2s[m]);
                 if (gate != nullptr && tx < G) gate[slot * G + tx] = tx == 0 ? g[0] : tx == 1 ? g[1] : tx == 2 ? g[2] : g[3];
+                if (final_scores == nullptr) continue;
                 const float* kp = keys + row;
                 const float dlt = kp[(int64_t)(2 * C) * key_stride];
                 const float bgm = kp[(int64_t)(2 * C + 2) * key_stride];
@@ -244,19 +245,31 @@ head_bwd_rows_kernel(const float* __restrict__ feat, const float* __restrict__ k
                      const int32_t* __restrict__ sel_count, const float* __restrict__ w1,
                      const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
                      unsigned active_mask, int topk, const int32_t* __restrict__ pool_pos,
-                     const float* __restrict__ dlogits, BwdScratch* __restrict__ scratch) {
+                     const float* __restrict__ dlogits, const float* __restrict__ dgate_dense,
+                     BwdScratch* __restrict__ scratch) {
     __shared__ float z1s[H], dz2s[G];
-    const int v = blockIdx.x;  // virtual row = (slide*C + c)*topk + r
-    const int r = v % topk, c = (v / topk) % C, slide = v / (topk * C);
+    const int v = blockIdx.x;  // pooled mode: virtual row = (slide*C + c)*topk + r; dense mode: row of feat
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     BwdScratch& out = scratch[v];
-    const int32_t pos = pool_pos[v];
-    if (pos < 0) {
-        if (tid == 0) out.row = -1;
-        return;
+    int32_t row;
+    int c = 0, slide = 0;
+    if (dgate_dense != nullptr) {
+        const float4 dg = *reinterpret_cast<const float4*>(dgate_dense + (int64_t)v * G);
+        if (dg.x == 0.f && dg.y == 0.f && dg.z == 0.f && dg.w == 0.f) {
+            if (tid == 0) out.row = -1;
+            return;
+        }
+        row = v;
+    } else {
+        c = (v / topk) % C;
+        slide = v / (topk * C);
+        const int32_t pos = pool_pos[v];
+        if (pos < 0) {
+            if (tid == 0) out.row = -1;
+            return;
+        }
+        row = sel_rows[sel_base[slide] + pos];
     }
-    (void)r;
-    const int32_t row = sel_rows[sel_base[slide] + pos];
     const float4* xp = reinterpret_cast<const float4*>(feat + (int64_t)row * D);
     float4 x[4];
 #pragma unroll
@@ -285,17 +298,22 @@ head_bwd_rows_kernel(const float* __restrict__ feat, const float* __restrict__ k
         a = warp_sum(a);
         if (lane == 0) {
             const float g = sigmoidf_exact(a + b2[m]);
-            const int S = sel_count[slide];
-            const int k_eff = topk < S ? topk : S;
-            const float dF = dlogits[(int64_t)slide * C + c] / (float)k_eff;
-            const float* kp = keys + row;
-            float psi;
-            if (m == 0) psi = kp[(int64_t)c * key_stride];
-            else if (m == 1) psi = kp[(int64_t)(C + c) * key_stride];
-            else if (m == 2) psi = kp[(int64_t)(2 * C) * key_stride];
-            else psi = kp[(int64_t)(2 * C + 2) * key_stride];
-            const float act = ((active_mask >> m) & 1u) ? 1.f : 0.f;
-            dz2s[m] = act * dF * psi * g * (1.f - g);
+            float dg;
+            if (dgate_dense != nullptr) {
+                dg = dgate_dense[(int64_t)v * G + m];
+            } else {
+                const int S = sel_count[slide];
+                const int k_eff = topk < S ? topk : S;
+                const float dF = dlogits[(int64_t)slide * C + c] / (float)k_eff;
+                const float* kp = keys + row;
+                float psi;
+                if (m == 0) psi = kp[(int64_t)c * key_stride];
+                else if (m == 1) psi = kp[(int64_t)(C + c) * key_stride];
+                else if (m == 2) psi = kp[(int64_t)(2 * C) * key_stride];
+                else psi = kp[(int64_t)(2 * C + 2) * key_stride];
+                dg = ((active_mask >> m) & 1u) ? dF * psi : 0.f;
+            }
+            dz2s[m] = dg * g * (1.f - g);
         }
     }
     __syncthreads();
@@ -350,6 +368,61 @@ head_bwd_reduce_kernel(const float* __restrict__ feat, const BwdScratch* __restr
             for (int v = 0; v < n_virtual; ++v)
                 if (scratch[v].row >= 0) a += scratch[v].dz2[tid];
             db2[tid] = a;
+        }
+    }
+}
+
+
+// ablation_evaluation (main_moc.py:538-553): un-gated avg / sum / max of the four planes per selected row.
+// mode 0 = avg (0.25 each), 1 = sum, 2 = max.  One thread per (slot, class).
+__global__ void ablation_rows_kernel(const float* __restrict__ keys, int64_t key_stride, int C,
+                                     const int32_t* __restrict__ sel_rows, int64_t n_slots, int mode,
+                                     float* __restrict__ final_scores) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_slots * C) return;
+    const int64_t slot = t / C;
+    const int c = (int)(t % C);
+    const int32_t row = sel_rows[slot];
+    if (row < 0) return;
+    const float* kp = keys + row;
+    const float l = kp[(int64_t)c * key_stride], p = kp[(int64_t)(C + c) * key_stride];
+    const float d = kp[(int64_t)(2 * C) * key_stride], b = kp[(int64_t)(2 * C + 2) * key_stride];
+    float f;
+    if (mode == 2) {
+        f = fmaxf(fmaxf(l, p), fmaxf(d, b));
+    } else {
+        const float g = mode == 0 ? 0.25f : 1.0f;
+        f = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(g, l), __fmul_rn(g, p)), __fmul_rn(g, d)), __fmul_rn(g, b));
+    }
+    final_scores[t] = f;
+}
+
+// selected_feat = feat[selected_index] and the four [S,C] score planes (main_moc.py:355-366) for callers that
+// want the reference's dense tensors.  One warp per selected row.
+__global__ void __launch_bounds__(256)
+gather_selected_kernel(const float* __restrict__ feat, const float* __restrict__ keys, int64_t key_stride, int C,
+                       const int32_t* __restrict__ sel_rows, int64_t n_sel, float* __restrict__ out_feat,
+                       float* __restrict__ p_top, float* __restrict__ p_softmax, float* __restrict__ p_diff,
+                       float* __restrict__ p_bg) {
+    const int lane = threadIdx.x & 31;
+    const int64_t s = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (s >= n_sel) return;
+    const int32_t row = sel_rows[s];
+    if (row < 0) return;
+    if (out_feat) {
+        const float4* src = reinterpret_cast<const float4*>(feat + (int64_t)row * D);
+        float4* dst = reinterpret_cast<float4*>(out_feat + s * D);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dst[q * 32 + lane] = __ldg(src + q * 32 + lane);
+    }
+    if (p_top) {
+        const float* kp = keys + row;
+        const float dlt = kp[(int64_t)(2 * C) * key_stride], bgm = kp[(int64_t)(2 * C + 2) * key_stride];
+        for (int c = lane; c < C; c += 32) {
+            p_top[s * C + c] = kp[(int64_t)c * key_stride];
+            p_softmax[s * C + c] = kp[(int64_t)(C + c) * key_stride];
+            p_diff[s * C + c] = dlt;
+            p_bg[s * C + c] = bgm;
         }
     }
 }
@@ -440,7 +513,7 @@ extern "C" int moc_head_backward(const float* feat, const float* keys, int64_t k
     BwdScratch* scratch = reinterpret_cast<BwdScratch*>(workspace);
     head_bwd_rows_kernel<<<n_virtual, BW_THREADS, 0, st>>>(feat, keys, key_stride, n_classes, sel_base, sel_rows,
                                                           sel_count, w1, b1, w2, b2, active_mask, topk, pool_pos,
-                                                          dlogits, scratch);
+                                                          dlogits, nullptr, scratch);
     MOC_LAUNCH_CHECK("head_bwd_rows_kernel");
     head_bwd_reduce_kernel<<<H + 1, 128, 0, st>>>(feat, scratch, n_virtual, grads);
     MOC_LAUNCH_CHECK("head_bwd_reduce_kernel");
@@ -459,5 +532,77 @@ extern "C" int moc_adam_step(float* params, const float* grads, float* exp_avg, 
         params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, (float)((double)lr / bc1),
         (float)sqrt(bc2));
     MOC_LAUNCH_CHECK("adam_kernel");
+    return MOC_OK;
+}
+
+extern "C" int moc_gather_selected(const float* feat, const float* keys, int64_t key_stride, int n_classes,
+                                   const int32_t* sel_rows, int64_t n_sel, float* out_feat, float* plane_top,
+                                   float* plane_softmax, float* plane_diff, float* plane_bg, void* stream) {
+    MOC_CHECK_ARG(feat && sel_rows && n_sel >= 0, "moc_gather_selected: bad arguments");
+    MOC_CHECK_ARG(!plane_top || (keys && plane_softmax && plane_diff && plane_bg),
+                  "moc_gather_selected: the four planes come together");
+    if (n_sel == 0) return MOC_OK;
+    gather_selected_kernel<<<(unsigned)((n_sel + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+        feat, keys, key_stride, n_classes, sel_rows, n_sel, out_feat, plane_top, plane_softmax, plane_diff, plane_bg);
+    MOC_LAUNCH_CHECK("gather_selected_kernel");
+    return MOC_OK;
+}
+
+extern "C" int moc_senet_forward(const float* x, int64_t n_rows, const float* w1, const float* b1, const float* w2,
+                                 const float* b2, float* gate, void* stream) {
+    MOC_CHECK_ARG(x && w1 && b1 && w2 && b2 && gate && n_rows >= 0, "moc_senet_forward: bad arguments");
+    MOC_CHECK_SHAPE(n_rows < (1ll << 31), "moc_senet_forward: too many rows");
+    if (n_rows == 0) return MOC_OK;
+    const size_t smem = (size_t)(H + HR_TM) * HR_LD * sizeof(float);
+    MOC_CUDA(cudaFuncSetAttribute(head_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t n_tiles = (n_rows + HR_TM - 1) / HR_TM;
+    const int grid = (int)(n_tiles < sm_count() ? n_tiles : sm_count());
+    head_rows_kernel<<<grid, HR_THREADS, smem, (cudaStream_t)stream>>>(x, nullptr, 0, 0, nullptr, n_rows, w1, b1, w2, b2,
+                                                                      0u, gate, nullptr);
+    MOC_LAUNCH_CHECK("head_rows_kernel");
+    return MOC_OK;
+}
+
+extern "C" size_t moc_senet_backward_workspace_bytes(int64_t n_rows) { return (size_t)n_rows * sizeof(BwdScratch); }
+
+extern "C" int moc_senet_backward(const float* x, int64_t n_rows, const float* dgate, const float* w1, const float* b1,
+                                  const float* w2, const float* b2, float* grads, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
+    MOC_CHECK_ARG(x && dgate && w1 && b1 && w2 && b2 && grads && workspace && n_rows >= 1,
+                  "moc_senet_backward: bad arguments");
+    MOC_CHECK_SHAPE(n_rows < (1ll << 30), "moc_senet_backward: too many rows");
+    if (workspace_bytes < moc_senet_backward_workspace_bytes(n_rows)) {
+        set_error("moc_senet_backward: workspace too small");
+        return MOC_E_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    BwdScratch* scratch = reinterpret_cast<BwdScratch*>(workspace);
+    head_bwd_rows_kernel<<<(unsigned)n_rows, BW_THREADS, 0, st>>>(x, nullptr, 0, 0, nullptr, nullptr, nullptr, w1, b1, w2,
+                                                                 b2, 0u, 1, nullptr, nullptr, dgate, scratch);
+    MOC_LAUNCH_CHECK("head_bwd_rows_kernel");
+    head_bwd_reduce_kernel<<<H + 1, 128, 0, st>>>(x, scratch, (int)n_rows, grads);
+    MOC_LAUNCH_CHECK("head_bwd_reduce_kernel");
+    return MOC_OK;
+}
+
+extern "C" int moc_ablation_forward(const float* keys, int64_t key_stride, int n_classes, const int64_t* sel_base,
+                                    const int32_t* sel_rows, const int32_t* sel_count, int n_slides,
+                                    int64_t sel_capacity_total, int mode, int topk, float* final_scores,
+                                    float* bag_logits, void* stream) {
+    MOC_CHECK_ARG(keys && sel_base && sel_rows && sel_count && final_scores && bag_logits,
+                  "moc_ablation_forward: null pointer");
+    MOC_CHECK_ARG(mode >= 0 && mode <= 2 && topk >= 1 && n_slides >= 0, "moc_ablation_forward: bad arguments");
+    if (n_slides == 0) return MOC_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t items = sel_capacity_total * n_classes;
+    if (items > 0) {
+        ablation_rows_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(keys, key_stride, n_classes, sel_rows,
+                                                                            sel_capacity_total, mode, final_scores);
+        MOC_LAUNCH_CHECK("ablation_rows_kernel");
+    }
+    const int64_t pi = (int64_t)n_slides * n_classes;
+    pool_final_kernel<<<(unsigned)((pi + POOL_WARPS - 1) / POOL_WARPS), POOL_WARPS * 32, 0, st>>>(
+        final_scores, sel_base, sel_count, n_slides, n_classes, topk, bag_logits, nullptr);
+    MOC_LAUNCH_CHECK("pool_final_kernel");
     return MOC_OK;
 }

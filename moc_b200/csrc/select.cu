@@ -347,6 +347,54 @@ pool_topk_kernel(const float* __restrict__ keys, int64_t key_stride, const int64
     }
 }
 
+
+// ---- helpers for the stand-alone selector / pooling API (inputs are logits [N,Ct] row-major) -------------
+// key planes from already-computed logits: columns < n_fg are classes, the rest background.
+__global__ void row_keys_kernel(const float* __restrict__ logits, int64_t n, int64_t ld, int n_fg, int n_total,
+                                float* __restrict__ keys, int64_t key_stride) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* x = logits + i * ld;
+    float m1 = -INFINITY, m2 = -INFINITY;
+    for (int c = 0; c < n_fg; ++c) {
+        const float v = x[c];
+        if (v > m1) { m2 = m1; m1 = v; } else if (v > m2) { m2 = v; }
+    }
+    float es = 0.f;
+    for (int c = 0; c < n_fg; ++c) es += expf(x[c] - m1);
+    const float inv = 1.0f / es;
+    float* kp = keys + i;
+    for (int c = 0; c < n_fg; ++c) {
+        kp[(int64_t)c * key_stride] = x[c];
+        kp[(int64_t)(n_fg + c) * key_stride] = expf(x[c] - m1) * inv;
+    }
+    float bs = 0.f, bm = -INFINITY;
+    for (int c = n_fg; c < n_total; ++c) { bs += x[c]; bm = fmaxf(bm, x[c]); }
+    kp[(int64_t)(2 * n_fg) * key_stride] = fabsf(m1 - m2);
+    kp[(int64_t)(2 * n_fg + 1) * key_stride] = bs;
+    kp[(int64_t)(2 * n_fg + 2) * key_stride] = bm;
+}
+
+// dst[r][c] = src[idx[r]][c], c < n_cols
+__global__ void take_rows_kernel(const float* __restrict__ src, int64_t ld, const int64_t* __restrict__ idx,
+                                 int64_t n_idx, int n_cols, float* __restrict__ dst) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_idx * n_cols) return;
+    const int64_t r = t / n_cols;
+    const int c = (int)(t % n_cols);
+    dst[t] = src[idx[r] * ld + c];
+}
+
+// out[c] = mean(vals[0..j-1][c]) summed in row order (fixed order => reproducible)
+__global__ void col_prefix_mean_kernel(const float* __restrict__ vals, int64_t ld, int n_cols, int j,
+                                       float* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cols) return;
+    float s = 0.f;
+    for (int r = 0; r < j; ++r) s += vals[(int64_t)r * ld + c];
+    out[c] = s / (float)j;
+}
+
 }  // namespace moc
 
 using namespace moc;
@@ -427,5 +475,33 @@ extern "C" int moc_pool_topk(const float* keys, int64_t key_stride, const int64_
         keys, key_stride, offsets, n_classes, topk, sel_plane0, sel_step, sel_smallest, val_plane0, val_step,
         bag_logits);
     MOC_LAUNCH_CHECK("pool_topk_kernel");
+    return MOC_OK;
+}
+
+extern "C" int moc_row_keys(const float* logits, int64_t n, int64_t ld, int n_fg, int n_total, float* keys,
+                            int64_t key_stride, void* stream) {
+    MOC_CHECK_ARG(logits && keys && n >= 0 && ld >= n_total && key_stride >= n, "moc_row_keys: bad arguments");
+    MOC_CHECK_SHAPE(n_fg >= 1 && n_total >= n_fg, "moc_row_keys: bad column split %d/%d", n_fg, n_total);
+    if (n == 0) return MOC_OK;
+    row_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(logits, n, ld, n_fg, n_total, keys,
+                                                                                  key_stride);
+    MOC_LAUNCH_CHECK("row_keys_kernel");
+    return MOC_OK;
+}
+
+extern "C" int moc_take_rows(const float* src, int64_t ld, const int64_t* idx, int64_t n_idx, int n_cols, float* dst,
+                             void* stream) {
+    MOC_CHECK_ARG(src && idx && dst && n_idx >= 0 && n_cols >= 0 && ld >= n_cols, "moc_take_rows: bad arguments");
+    if (n_idx * n_cols == 0) return MOC_OK;
+    take_rows_kernel<<<(unsigned)((n_idx * n_cols + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, ld, idx, n_idx,
+                                                                                                n_cols, dst);
+    MOC_LAUNCH_CHECK("take_rows_kernel");
+    return MOC_OK;
+}
+
+extern "C" int moc_col_prefix_mean(const float* vals, int64_t ld, int n_cols, int j, float* out, void* stream) {
+    MOC_CHECK_ARG(vals && out && n_cols >= 1 && j >= 1 && ld >= n_cols, "moc_col_prefix_mean: bad arguments");
+    col_prefix_mean_kernel<<<(n_cols + 63) / 64, 64, 0, (cudaStream_t)stream>>>(vals, ld, n_cols, j, out);
+    MOC_LAUNCH_CHECK("col_prefix_mean_kernel");
     return MOC_OK;
 }

@@ -1,0 +1,158 @@
+"""Batched driver of the hot path over a :class:`RaggedBagStore`.
+
+One ``MocEngine`` holds the packed prompt matrices and the run's J / K / discard settings and exposes the
+three passes the MOC loops are made of, each as a handful of kernel launches over *all* slides at once:
+
+* ``zero_shot_logits``  - score + pooled top-K                      (zs_evaluation, main_moc.py:412-460)
+* ``eval_logits``       - score + select + gate/combine + pooling    (evaluation,    main_moc.py:462-520)
+* ``train_step``        - the same on one half-masked slide, then CE, backward, Adam (train, main_moc.py:378-410)
+
+Scores depend only on the bag and the frozen prompts, never on the trained gate, so with
+``cache_scores=True`` the key planes of a store are computed once and reused by every later pass; results are
+bit-identical either way.  The default is off: every pass streams the bags
+again, like the reference.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import _lib, ops
+from .bag_store import RaggedBagStore
+
+POOLINGS = {
+    # name -> (select plane0, select step, value plane0, value step, smallest) as functions of C
+    "topj": lambda c: (0, 1, 0, 1, False),
+    "delta_softmax": lambda c: (c, 1, 0, 1, False),
+    "delta_diff": lambda c: (2 * c, 0, 0, 1, False),
+    "bottomk_irrel": lambda c: (2 * c + 1, 0, 0, 1, True),
+}
+
+
+@dataclass
+class StepOut:
+    loss: torch.Tensor        # [1] device
+    bag_logits: torch.Tensor  # [1,C] device
+    n_selected: torch.Tensor  # int32 [1] device
+
+
+class MocEngine:
+    def __init__(self, zeroshot_weights: torch.Tensor, zeroshot_weights_ext: torch.Tensor, topj: int = 10,
+                 topk: int = 10, discard_classifiers: Sequence[str] = (), normalize: bool = False,
+                 cache_scores: bool = False, max_wave_rows: int = 48 * 1024 * 1024):
+        self.prompts = ops.Prompts.pack(zeroshot_weights, zeroshot_weights_ext)
+        self.n_classes = self.prompts.n_classes
+        self.topj, self.topk = int(topj), int(topk)
+        self.discard = tuple(discard_classifiers or ())
+        self.normalize = bool(normalize)
+        self.cache_scores = bool(cache_scores)
+        self.max_wave_rows = int(max_wave_rows)
+        self._key_cache: Dict[int, torch.Tensor] = {}
+        self._layout_cache: Dict[tuple, tuple] = {}
+        self.launches = 0  # kernels of ours launched (bench.py reports it)
+
+    # ---- scoring -------------------------------------------------------------------------------
+    def keys_for(self, store: RaggedBagStore, lo: int = 0, hi: Optional[int] = None) -> torch.Tensor:
+        """Key planes [2C+3, rows] for slides [lo, hi) of the store (whole store when cached)."""
+        hi = len(store) if hi is None else hi
+        if self.cache_scores:
+            k = self._key_cache.get(id(store))
+            if k is None:
+                k = ops.score_keys(store.feat, self.prompts, self.normalize)
+                self.launches += 1
+                self._key_cache[id(store)] = k
+            return k[:, store.offsets_h[lo]:store.offsets_h[hi]]
+        r0, r1 = store.offsets_h[lo], store.offsets_h[hi]
+        self.launches += 1
+        return ops.score_keys(store.feat[r0:r1], self.prompts, self.normalize)
+
+    def drop_cache(self, store: Optional[RaggedBagStore] = None) -> None:
+        if store is None:
+            self._key_cache.clear()
+        else:
+            self._key_cache.pop(id(store), None)
+
+    def _waves(self, store: RaggedBagStore):
+        """Split the store into runs of whole slides of at most max_wave_rows rows (key-plane memory bound)."""
+        lo, n = 0, len(store)
+        while lo < n:
+            hi = lo + 1
+            while hi < n and store.offsets_h[hi + 1] - store.offsets_h[lo] <= self.max_wave_rows:
+                hi += 1
+            yield lo, hi
+            lo = hi
+
+    def _layout(self, store: RaggedBagStore, lo: int, hi: int):
+        key = (id(store), lo, hi, self.topj)
+        hit = self._layout_cache.get(key)
+        if hit is None:
+            r0 = store.offsets_h[lo]
+            offs_h = [v - r0 for v in store.offsets_h[lo:hi + 1]]
+            offs = (store.offsets[lo:hi + 1] - r0).contiguous()
+            base_h = ops.selection_layout(offs_h, self.n_classes, self.topj)
+            base = torch.tensor(base_h, dtype=torch.int64, device=store.device)
+            hit = (offs, offs_h, base, base_h)
+            self._layout_cache[key] = hit
+        return hit
+
+    # ---- zero-shot -----------------------------------------------------------------------------
+    def zero_shot_logits(self, store: RaggedBagStore, pooling: str = "topj") -> torch.Tensor:
+        c = self.n_classes
+        sp0, ss, vp0, vs, small = POOLINGS[pooling](c)
+        out = torch.empty(len(store), c, dtype=torch.float32, device=store.device)
+        for lo, hi in self._waves(store):
+            keys = self.keys_for(store, lo, hi)
+            offs, _, _, _ = self._layout(store, lo, hi)
+            out[lo:hi] = ops.pool_topk(keys, offs, hi - lo, c, self.topk, sp0, ss, vp0, vs, small)
+            self.launches += 1
+        return out
+
+    # ---- evaluation ----------------------------------------------------------------------------
+    def eval_logits(self, store: RaggedBagStore, params: ops.HeadParams, mode: str = "eval",
+                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Bag logits [n_slides, C] of every slide in the store under the current gate parameters."""
+        c = self.n_classes
+        if out is None:
+            out = torch.empty(len(store), c, dtype=torch.float32, device=store.device)
+        disc = _lib.discard_bits(self.discard)
+        act = _lib.active_bits(self.discard, mode)
+        for lo, hi in self._waves(store):
+            keys = self.keys_for(store, lo, hi)
+            offs, offs_h, base, base_h = self._layout(store, lo, hi)
+            feat = store.feat[store.offsets_h[lo]:store.offsets_h[hi]]
+            sel = ops.select_union(keys, offs, offs_h, c, self.topj, disc, None, base, base_h)
+            ho = ops.head_forward(feat, keys, c, sel, params, act, self.topk)
+            out[lo:hi] = ho.bag_logits
+            self.launches += 5  # memset-free: select_mark, compact, head_rows, pool_final (+ the bitmap clear)
+        return out
+
+    def ablation_logits(self, store: RaggedBagStore, how: str) -> torch.Tensor:
+        """Un-gated avg / sum / max of the four planes (ablation_evaluation, main_moc.py:523-582)."""
+        c = self.n_classes
+        out = torch.empty(len(store), c, dtype=torch.float32, device=store.device)
+        for lo, hi in self._waves(store):
+            keys = self.keys_for(store, lo, hi)
+            offs, offs_h, base, base_h = self._layout(store, lo, hi)
+            feat = store.feat[store.offsets_h[lo]:store.offsets_h[hi]]
+            sel = ops.select_union(keys, offs, offs_h, c, self.topj, 0, None, base, base_h)
+            out[lo:hi] = ops.ablation_pool(keys, c, sel, how, self.topk)
+            del feat
+        return out
+
+    # ---- training ------------------------------------------------------------------------------
+    def train_step(self, store: RaggedBagStore, slide: int, label_dev: torch.Tensor, params: ops.HeadParams,
+                   row_mask: Optional[torch.Tensor], grads_out: torch.Tensor) -> StepOut:
+        """Forward + CE + backward of one (masked) slide; fills ``grads_out`` (flat, 33 092 floats)."""
+        c = self.n_classes
+        keys = self.keys_for(store, slide, slide + 1)
+        offs, offs_h, base, base_h = self._layout(store, slide, slide + 1)
+        feat = store.bag(slide)
+        sel = ops.select_union(keys, offs, offs_h, c, self.topj, _lib.discard_bits(self.discard), row_mask, base, base_h)
+        act = _lib.active_bits(self.discard, "train")
+        ho = ops.head_forward(feat, keys, c, sel, params, act, self.topk)
+        loss, dl, _ = ops.cross_entropy(ho.bag_logits, label_dev, want_grad=True)
+        ops.head_backward(feat, keys, c, sel, params, act, self.topk, ho.pool_pos, dl, out=grads_out)
+        self.launches += 8
+        return StepOut(loss, ho.bag_logits, sel.sel_count)

@@ -127,7 +127,11 @@ def select_union(keys: torch.Tensor, offsets: torch.Tensor, offsets_h: Sequence[
 
 def topj_sorted(values: torch.Tensor, j: int, largest: bool = True, want_values: bool = False):
     """Column-wise Tensor.topk(j, dim=0, largest, sorted=True) of a [N,C] (or [N]) CUDA tensor -> int64 [j,C]."""
-    v = _dev_f32(values, "values")
+    v = values
+    if not v.is_cuda:
+        raise MocError(_lib.E_ARG, "values must be a CUDA tensor (moc_b200 has no CPU path)")
+    if v.dtype != torch.float32:
+        v = v.float()
     squeeze = v.dim() == 1
     if squeeze:
         v = v.unsqueeze(1)
@@ -226,3 +230,92 @@ def adam_step(params: torch.Tensor, grads: torch.Tensor, exp_avg: torch.Tensor, 
     """In-place torch.optim.Adam update of a flat fp32 parameter buffer; ``step`` counts from 1."""
     check(_lib.load().moc_adam_step(params.data_ptr(), grads.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
                                     params.numel(), int(step), lr, beta1, beta2, eps, weight_decay, _stream()))
+
+
+def gather_selected(feat: torch.Tensor, keys: torch.Tensor, n_classes: int, sel_rows: torch.Tensor, n_sel: int,
+                    want_feat: bool = True, want_planes: bool = True):
+    """Dense selected_feat [S,512] and the four [S,C] score planes of main_moc.py:355-366."""
+    dev = feat.device
+    sf = torch.empty(n_sel, D, dtype=torch.float32, device=dev) if want_feat else None
+    planes = [torch.empty(n_sel, n_classes, dtype=torch.float32, device=dev) for _ in range(4)] if want_planes else [None] * 4
+    check(_lib.load().moc_gather_selected(feat.data_ptr(), _ptr(keys), keys.stride(0) if keys is not None else 0,
+                                          n_classes, sel_rows.data_ptr(), n_sel, _ptr(sf), _ptr(planes[0]),
+                                          _ptr(planes[1]), _ptr(planes[2]), _ptr(planes[3]), _stream()))
+    return sf, planes
+
+
+def senet_forward(x: torch.Tensor, params: HeadParams) -> torch.Tensor:
+    x = _dev_f32(x, "x")
+    if x.dim() != 2 or x.size(1) != D:
+        raise MocError(_lib.E_SHAPE, "senet input must be [rows,512], got %s" % (tuple(x.shape),))
+    gate = torch.empty(x.size(0), GATES, dtype=torch.float32, device=x.device)
+    check(_lib.load().moc_senet_forward(x.data_ptr(), x.size(0), params.w1.data_ptr(), params.b1.data_ptr(),
+                                        params.w2.data_ptr(), params.b2.data_ptr(), gate.data_ptr(), _stream()))
+    return gate
+
+
+def senet_backward(x: torch.Tensor, dgate: torch.Tensor, params: HeadParams) -> torch.Tensor:
+    x, dgate = _dev_f32(x, "x"), _dev_f32(dgate, "dgate")
+    lib = _lib.load()
+    n = x.size(0)
+    out = torch.empty(NUM_PARAMS, dtype=torch.float32, device=x.device)
+    if n == 0:
+        return out.zero_()
+    ws_bytes = lib.moc_senet_backward_workspace_bytes(n)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+    check(lib.moc_senet_backward(x.data_ptr(), n, dgate.data_ptr(), params.w1.data_ptr(), params.b1.data_ptr(),
+                                 params.w2.data_ptr(), params.b2.data_ptr(), out.data_ptr(), ws.data_ptr(), ws_bytes,
+                                 _stream()))
+    return out
+
+
+def split_grads(flat: torch.Tensor):
+    """Views of the flat gradient in state_dict order: model.0.weight, model.0.bias, model.2.weight, model.2.bias."""
+    o1 = HIDDEN * D
+    o2 = o1 + HIDDEN
+    o3 = o2 + GATES * HIDDEN
+    return (flat[:o1].view(HIDDEN, D), flat[o1:o2], flat[o2:o3].view(GATES, HIDDEN), flat[o3:o3 + GATES])
+
+
+def row_keys(logits: torch.Tensor, n_fg: int) -> torch.Tensor:
+    """Key planes [2*n_fg+3, N] from logits [N, Ct] (first n_fg columns are classes, the rest background)."""
+    x = _dev_f32(logits, "logits")
+    n, ct = x.shape
+    keys = torch.empty(num_key_planes(n_fg), n, dtype=torch.float32, device=x.device)
+    check(_lib.load().moc_row_keys(x.data_ptr(), n, x.stride(0), n_fg, ct, keys.data_ptr(), keys.stride(0), _stream()))
+    return keys
+
+
+def take_rows(src: torch.Tensor, idx: torch.Tensor, n_cols: int) -> torch.Tensor:
+    """src[idx, :n_cols] for an int64 index vector."""
+    src = _dev_f32(src, "src")
+    idx = idx.to(device=src.device, dtype=torch.int64).contiguous()
+    out = torch.empty(idx.numel(), n_cols, dtype=torch.float32, device=src.device)
+    check(_lib.load().moc_take_rows(src.data_ptr(), src.stride(0), idx.data_ptr(), idx.numel(), n_cols,
+                                    out.data_ptr(), _stream()))
+    return out
+
+
+def col_prefix_mean(vals: torch.Tensor, j: int) -> torch.Tensor:
+    """vals[:j].mean(dim=0, keepdim=True) for a [J,C] tensor, summed in row order."""
+    vals = _dev_f32(vals, "vals")
+    out = torch.empty(1, vals.size(1), dtype=torch.float32, device=vals.device)
+    check(_lib.load().moc_col_prefix_mean(vals.data_ptr(), vals.stride(0), vals.size(1), int(j), out.data_ptr(), _stream()))
+    return out
+
+
+_ABLATION_MODES = {"avg": 0, "sum": 1, "max": 2}
+
+
+def ablation_pool(keys: torch.Tensor, n_classes: int, sel: Selection, how: str, topk: int) -> torch.Tensor:
+    """Bag logits [n_slides,C] of the un-gated avg / sum / max combination (main_moc.py:538-555)."""
+    if how not in _ABLATION_MODES:
+        raise MocError(_lib.E_ARG, "ablation_study must be one of avg, sum, max")
+    dev = keys.device
+    final = torch.empty(max(sel.capacity, 1), n_classes, dtype=torch.float32, device=dev)
+    bag = torch.empty(sel.n_slides, n_classes, dtype=torch.float32, device=dev)
+    check(_lib.load().moc_ablation_forward(keys.data_ptr(), keys.stride(0), n_classes, sel.sel_base.data_ptr(),
+                                           sel.sel_rows.data_ptr(), sel.sel_count.data_ptr(), sel.n_slides,
+                                           sel.capacity, _ABLATION_MODES[how], int(topk), final.data_ptr(),
+                                           bag.data_ptr(), _stream()))
+    return bag

@@ -1,0 +1,200 @@
+"""The reference-shaped Python API (slide_process, selectors, poolers, senet, loops) on the GPU against the
+golden fixtures written by the reference's own code."""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import assert_topj_set, close
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def T(a):
+    return torch.from_numpy(np.ascontiguousarray(a))
+
+
+def _args(c, j, k, discard=()):
+    return types.SimpleNamespace(disable_tqdm=True, n_classes=c, topj=j, topk=k, discard_classifiers=list(discard),
+                                 pretrain="conch", ablation_study="none", cache_scores=False)
+
+
+@pytest.mark.parametrize("name", ["slide_c2", "slide_c2_j64", "slide_c3", "slide_c30"])
+def test_slide_process_golden(golden, name):
+    from moc_b200 import senet, slide_process, topj_pooling
+    g = golden(name)
+    c, j, k = int(g["C"]), int(g["J"]), int(g["K"])
+    w, we = T(g["W"]).to(DEV), T(g["W_ext"]).to(DEV)
+    model = senet(512, 4)
+    model.load_state_dict({kk[3:].replace("model_0_", "model.0.").replace("model_2_", "model.2."): T(v)
+                           for kk, v in g.items() if kk.startswith("sd_")})
+    model.to(DEV).eval()
+    for i in range(int(g["n_slides"])):
+        x = T(g["s%d_feat" % i]).float()  # host tensor: slide_process moves it, like the reference
+        for di, disc in enumerate(g["discards"]):
+            disc = [d for d in str(disc).split("|") if d]
+            q = "s%d_d%d_" % (i, di)
+            r = slide_process(x, w, we, n_classes=c, topj=j, discard_classifiers=disc)
+            assert isinstance(r["selected_index"], list)
+            if r["selected_index"] != g[q + "selected_index"].tolist():
+                assert len(set(r["selected_index"]) ^ set(g[q + "selected_index"].tolist())) <= 4
+                continue
+            assert torch.equal(r["selected_feat"].cpu(), x[r["selected_index"]])
+            close(r["logits_top_classifier"], g[q + "plane_top"])
+            close(r["logits_delta_softmax_classifier"], g[q + "plane_dsoftmax"])
+            close(r["logits_delta_diff_classifier"], g[q + "plane_ddiff"])
+            close(r["logits_bottomk_irrel_classifier"], g[q + "plane_bottomk"])
+            with torch.no_grad():
+                gate = model(r["selected_feat"])
+            close(gate, g[q + "gate"], rtol=1e-4, atol=1e-6)
+            # the reference's own eval-time combination written with torch ops on our tensors
+            f = gate[:, 0:1] * r["logits_top_classifier"]
+            if "delta_softmax" not in disc:
+                f = f + gate[:, 1:2] * r["logits_delta_softmax_classifier"]
+            if "delta_diff" not in disc:
+                f = f + gate[:, 2:3] * r["logits_delta_diff_classifier"]
+            f = f + gate[:, 3:4] * r["logits_bottomk_irrel_classifier"]
+            close(topj_pooling(f, [k])[1][k], g[q + "bag_logits"])
+
+
+@pytest.mark.parametrize("name", ["slide_c2", "slide_c3", "slide_c30"])
+def test_selectors_and_poolers_golden(golden, name):
+    import moc_b200 as M
+    g = golden(name)
+    c, j, k = int(g["C"]), int(g["J"]), int(g["K"])
+    for i in range(int(g["n_slides"])):
+        lo, le = T(g["s%d_L" % i]), T(g["s%d_Le" % i])
+        lod, led = lo.to(DEV), le.to(DEV)
+        n = lo.size(0)
+        sm = torch.softmax(lo, dim=1).numpy()
+        srt = np.sort(lo.numpy().astype(np.float64), axis=1)
+        delta = np.abs(srt[:, -1] - srt[:, -2])
+        bg = le[:, c:].sum(dim=1).numpy()
+        i1 = M.index_topj_classifier(lod, [j]).cpu().numpy()
+        i2 = M.index_delta_softmax_classifier(lod, [j]).cpu().numpy()
+        i3 = M.index_delta_diff_classifier(lod, [j]).cpu().numpy()
+        i4 = M.index_bottomk_irrel_classifier(led, [j], c).cpu().numpy()
+        for arr, key in ((i1, "idx_topj"), (i2, "idx_dsoftmax"), (i3, "idx_ddiff"), (i4, "idx_bottomk")):
+            assert arr.shape == g["s%d_%s" % (i, key)].shape and arr.dtype == np.int64
+        for cc in range(c):
+            assert_topj_set(i1[:, cc], g["s%d_idx_topj" % i][:, cc], lo[:, cc].numpy(), j)
+            assert_topj_set(i2[:, cc], g["s%d_idx_dsoftmax" % i][:, cc], sm[:, cc], j)
+            assert_topj_set(i3[:, cc], g["s%d_idx_ddiff" % i][:, cc], delta, j)
+            assert_topj_set(i4[:, cc], g["s%d_idx_bottomk" % i][:, cc], bg, j, largest=False)
+        for fn, key, arg in ((M.topj_pooling, "pool_topj", lod), (M.delta_softmax_classifier_pooling, "pool_dsoftmax", lod),
+                             (M.delta_diff_classifier_pooling, "pool_ddiff", lod)):
+            preds, pooled = fn(arg, [k])
+            close(pooled[k], g["s%d_%s" % (i, key)])
+            assert int(preds[k]) == int(np.argmax(g["s%d_%s" % (i, key)]))
+        preds, pooled, idx = M.bottomk_irrel_classifier_pooling(led, [k], return_indices=True, coords_list=c)
+        close(pooled[k], g["s%d_pool_bottomk" % i])
+        assert idx.shape == (min(k, n), c)
+        # several pooling sizes in one call, as the reference's dict-of-j API allows
+        preds, pooled = M.topj_pooling(lod, [1, 5, 50])
+        for jj in (1, 5, 50):
+            ref = lo.topk(min(50, n), 0)[0][:min(jj, n)].mean(dim=0, keepdim=True)
+            close(pooled[jj], ref)
+
+
+def test_senet_autograd_matches_torch():
+    """senet.forward through the CUDA kernels is differentiable w.r.t. its parameters like the nn.Sequential."""
+    from moc_b200 import senet
+    torch.manual_seed(0)
+    m = senet(512, 4).to(DEV)
+    ref = torch.nn.Sequential(torch.nn.Linear(512, 64), torch.nn.ReLU(), torch.nn.Linear(64, 4), torch.nn.Sigmoid())
+    ref.load_state_dict({k.replace("model.", ""): v.cpu() for k, v in m.state_dict().items()})
+    assert sorted(m.state_dict().keys()) == ["model.0.bias", "model.0.weight", "model.2.bias", "model.2.weight"]
+    x = torch.randn(300, 512) / 22.6
+    coef = torch.randn(300, 4)
+    coef[torch.rand(300) > 0.1] = 0  # sparse upstream gradient, like top-K pooling produces
+    out = m(x.to(DEV))
+    (out * coef.to(DEV)).sum().backward()
+    out_ref = ref(x)
+    (out_ref * coef).sum().backward()
+    close(out, out_ref, rtol=1e-5, atol=1e-6)
+    for (n1, p1), (n2, p2) in zip(m.named_parameters(), ref.named_parameters()):
+        scale = float(p2.grad.abs().max())
+        assert float((p1.grad.cpu() - p2.grad).abs().max()) <= 1e-4 * scale + 1e-9, n1
+
+
+@pytest.mark.parametrize("name", ["loop_c2", "loop_c3_discard"])
+def test_loops_golden(golden, name):
+    """zs_evaluation / ablation_evaluation / train / evaluation against the reference's own loop outputs."""
+    import moc_b200 as M
+    from moc_b200 import loops
+    g = golden(name)
+    c, j, k = int(g["C"]), int(g["J"]), int(g["K"])
+    disc = [d for d in str(g["discard"]).split("|") if d]
+    loops.set_prompts(T(g["W"]).to(DEV), T(g["W_ext"]).to(DEV))
+    args = _args(c, j, k, disc)
+    tr_store = M.RaggedBagStore.from_bags([T(g["train_feat_%d" % i]).float() for i in range(int(g["n_train"]))],
+                                          g["train_labels"].tolist(), DEV)
+    va_store = M.RaggedBagStore.from_bags([T(g["val_feat_%d" % i]).float() for i in range(int(g["n_val"]))],
+                                          g["val_labels"].tolist(), DEV)
+    tr = M.BagLoader(M.BagDataset(tr_store, repeat_num=int(g["repeat_num"])))
+    va = M.BagLoader(M.BagDataset(va_store))
+
+    def ev(d):
+        return np.asarray([d["loss"], d["acc"], d["auc"]])
+
+    def same(d, key, rtol=2e-5):
+        got, ref = ev(d), g[key]
+        np.testing.assert_allclose(got[0], ref[0], rtol=rtol, err_msg=key + " loss")
+        assert got[1] == ref[1], key + " acc"
+        assert got[2] == ref[2], key + " auc"
+
+    same(M.zs_evaluation(tr, DEV, args), "zs_train")
+    same(M.zs_evaluation(va, DEV, args), "zs_val")
+    same(M.zs_evaluation(va, DEV, args, pooling_func=M.delta_softmax_classifier_pooling), "zs_val_dsoftmax")
+    same(M.zs_evaluation(va, DEV, args, pooling_func=M.delta_diff_classifier_pooling), "zs_val_ddiff")
+    same(M.zs_evaluation(va, DEV, args, pooling_func=M.bottomk_irrel_classifier_pooling), "zs_val_bottomk")
+    for how in ("avg", "sum", "max"):
+        args.ablation_study = how
+        same(M.ablation_evaluation(va, DEV, args), "ablation_val_" + how)
+    args.ablation_study = "none"
+    # reference quirk kept: ablation_evaluation/evaluation restore repeat_num = len(dataset), so None becomes n
+    assert tr.dataset.repeat_num == int(g["repeat_num"]) and va.dataset.repeat_num == int(g["n_val"])
+
+    model = M.senet(512, 4)
+    model.load_state_dict({kk[4:].replace("model_0_", "model.0.").replace("model_2_", "model.2."): T(v)
+                           for kk, v in g.items() if kk.startswith("sd0_")})
+    model.to(DEV)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4)
+    masks = [T(g["mask_%d" % i]) for i in range(int(g["n_masks"]))]
+    per = int(g["repeat_num"])
+    for e in range(int(g["epochs"])):
+        losses = M.train(model, tr, opt, DEV, args, masks=masks[e * per:(e + 1) * per])
+        np.testing.assert_allclose(losses.cpu().numpy(), g["train_losses_e%d" % e], rtol=5e-5)
+        for key, t in model.state_dict().items():
+            ref = g["sd_e%d_" % e + key.replace(".", "_")]
+            assert np.abs(t.cpu().numpy() - ref).max() < 2e-5, key  # lr = 1e-3: well under one Adam step
+        same(M.evaluation(model, tr, DEV, args), "eval_train_e%d" % e, rtol=5e-5)
+        same(M.evaluation(model, va, DEV, args), "eval_val_e%d" % e, rtol=5e-5)
+    # the torch optimizer's own state was advanced by our kernel and stays a valid torch state
+    p0 = model.model[0].weight
+    assert int(opt.state[p0]["step"]) == int(g["adam_step"])
+    np.testing.assert_allclose(opt.state[p0]["exp_avg"].cpu().numpy(), g["adam_m_0"], rtol=1e-3, atol=1e-8)
+    opt.state_dict()
+
+
+def test_cached_scores_are_bit_identical(golden):
+    import moc_b200 as M
+    from moc_b200 import loops
+    g = golden("loop_c2")
+    c, j, k = int(g["C"]), int(g["J"]), int(g["K"])
+    loops.set_prompts(T(g["W"]).to(DEV), T(g["W_ext"]).to(DEV))
+    store = M.RaggedBagStore.from_bags([T(g["val_feat_%d" % i]).float() for i in range(int(g["n_val"]))],
+                                       g["val_labels"].tolist(), DEV)
+    torch.manual_seed(1)
+    model = M.senet(512, 4).to(DEV)
+    a = M.MocEngine(loops.zeroshot_weights, loops.zeroshot_weights_ext, j, k, cache_scores=False)
+    b = M.MocEngine(loops.zeroshot_weights, loops.zeroshot_weights_ext, j, k, cache_scores=True)
+    la = a.eval_logits(store, model.head_params())
+    lb1 = b.eval_logits(store, model.head_params())
+    lb2 = b.eval_logits(store, model.head_params())
+    assert torch.equal(la, lb1) and torch.equal(la, lb2)
+    # waves: force several small waves and compare with the single-wave result
+    s = M.MocEngine(loops.zeroshot_weights, loops.zeroshot_weights_ext, j, k, max_wave_rows=300)
+    assert torch.equal(la, s.eval_logits(store, model.head_params()))
