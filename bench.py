@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""Benchmark of the MOC per-slide hot path (score + top-J selection + gate/pooling) on B200.
+
+    python bench.py --gpus 1 --steps 20 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference            # the reference algorithm on the host cores
+
+Metric (BASELINE.json): slides/s - with patches/s and the streaming kernel's HBM GB/s beside it - on
+configs[1]: NSCLC-shaped (C=2, 4 normal-tissue prompts), 1000 slides x 20 000 patches per GPU, J=400, K=10.
+One *step* is one evaluation pass of the hot path over every slide of the split: score all patches, make the
+four top-J selections and their union, gate + combine the selected patches, pool to bag logits, cross-entropy.
+Per-GPU work is fixed as N grows (slides are sharded, "weak" scaling); with N>1 every step ends with the
+all-gather of the bag logits, the one exchange the evaluation loop has.
+
+`value`  : bags resident in HBM when the timed region starts (CUDA events, max over ranks).
+`e2e`    : the same pass through MocEngine.eval_logits_host with the bags in pinned HOST memory - every
+           step copies all its features host->device (double-buffered on a copy stream) and reads the logits
+           back device->host.
+`roofline`: the streaming score+keys kernel; algorithmic bytes = 2048 B per patch, timed live with CUDA events
+           on its stream inside the timed region, against the measured HBM copy bandwidth.
+`cpu_baseline`: the oracle port of the reference (torch fp32 on all host cores) on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+N_CLASSES, TOPJ, TOPK = 2, 400, 10
+WORKLOAD = "NSCLC 16-shot eval split: 1000 synthetic slides x 20000 CONCH-shaped patches (C=2, C_ext=6, J=400, K=10)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--slides", type=int, default=1000, help="slides per GPU")
+    ap.add_argument("--patches", type=int, default=20000)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-host-slides", type=int, default=128, help="distinct slides kept in pinned host memory")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic_bytes(rows_per_launch):
+    """dram bytes per launch of the streaming kernel from the committed ncu capture, scaled per row."""
+    p = os.path.join(ROOT, "profiles", "score_keys_traffic.json")
+    if not os.path.exists(p):
+        return None
+    try:
+        d = json.load(open(p))
+        return float(d["dram_bytes_per_row"]) * rows_per_launch
+    except Exception:
+        return None
+
+
+class ClockSampler(threading.Thread):
+    """SM clock / throttle reasons sampled through NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag, self.active = index, [], False, False
+        self.max_mhz, self.ok = None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                if self.active:
+                    self.samples.append((mhz, reasons))
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unsampled"]}
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        mhz = sorted(s[0] for s in self.samples)
+        seen = set()
+        for _, r in self.samples:
+            for bit, nm in names.items():
+                if r & bit:
+                    seen.add(nm)
+        return {"sm_mhz": mhz[len(mhz) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(seen),
+                "samples": len(mhz)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_pass(n_slides, n_patches, seconds, threads):
+    """The oracle port of the reference's evaluation() on host cores: returns (slides/s, slides timed, passes)."""
+    from moc_b200 import synthetic
+    from oracle import moc_oracle as O
+    torch.set_num_threads(threads)
+    w, we = synthetic.prompt_matrices(N_CLASSES)
+    bags, labels = synthetic.make_cohort(n_slides, n_patches, N_CLASSES, cohort_seed=99)
+    prm = O.SenetParams.init(0)
+    with torch.no_grad():
+        for x in bags[:2]:  # warm-up
+            O.slide_eval_logits(prm, x, w, we, N_CLASSES, TOPJ, TOPK)
+        done, passes, t0 = 0, 0, time.perf_counter()
+        while True:
+            for x, y in zip(bags, labels):
+                lg = O.slide_eval_logits(prm, x, w, we, N_CLASSES, TOPJ, TOPK)
+                float(O.cross_entropy(lg, y))
+                done += 1
+            passes += 1
+            dt = time.perf_counter() - t0
+            if dt >= seconds:
+                break
+    return done / dt, done, passes, dt
+
+
+def run_reference(a):
+    """--impl reference: the reference's CPU algorithm (oracle port, kind "port") on this box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n_slides = 32
+    per_step = []
+    total = a.steps + a.warmup
+    budget = max(1.0, min(150.0, 150.0) / max(total, 1))
+    from moc_b200 import synthetic
+    from oracle import moc_oracle as O
+    torch.set_num_threads(threads)
+    w, we = synthetic.prompt_matrices(N_CLASSES)
+    bags, labels = synthetic.make_cohort(n_slides, a.patches, N_CLASSES, cohort_seed=99)
+    prm = O.SenetParams.init(0)
+
+    def step():
+        t0 = time.perf_counter()
+        n = 0
+        with torch.no_grad():
+            while True:
+                for x, y in zip(bags, labels):
+                    lg = O.slide_eval_logits(prm, x, w, we, N_CLASSES, TOPJ, TOPK)
+                    float(O.cross_entropy(lg, y))
+                    n += 1
+                if time.perf_counter() - t0 >= min(budget, 2.0):
+                    break
+        return n, time.perf_counter() - t0
+
+    for _ in range(a.warmup):
+        step()
+    n_tot, t_tot = 0, 0.0
+    for _ in range(a.steps):
+        n, dt = step()
+        n_tot += n
+        t_tot += dt
+        per_step.append(dt / n)
+    value = n_tot / t_tot
+    sample = "%d distinct slides x %d patches in host RAM, looped; %d slides timed over %d steps" % (
+        n_slides, a.patches, n_tot, a.steps)
+    line = {
+        "impl": "reference", "metric": "slides_per_sec", "value": value, "unit": "slides/s", "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * t_tot / max(a.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "reference algorithm (oracle port) on host cores; bounded sample"},
+        "patches_per_sec": value * a.patches,
+        "cpu_baseline": {"value": value, "unit": "slides/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "slides/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(a):
+    from moc_b200 import ops, synthetic
+    from moc_b200.bag_store import HostBags, HostChunk, RaggedBagStore
+    from moc_b200.dist import barrier_max_ms, init_from_env
+    from moc_b200.engine import MocEngine
+    import torch.distributed as dist
+
+    rank, local, world = init_from_env()
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world != a.gpus and rank == 0:
+        print("warning: --gpus %d but WORLD_SIZE=%d" % (a.gpus, world), file=sys.stderr)
+
+    w, we = synthetic.prompt_matrices(N_CLASSES, device=dev)
+    store = RaggedBagStore.synthetic([a.patches] * a.slides, N_CLASSES, we, cohort_seed=1000 + rank, device=dev)
+    eng = MocEngine(w, we, TOPJ, TOPK)
+    g = torch.Generator().manual_seed(0)
+    prm = ops.HeadParams(((torch.rand(64, 512, generator=g) * 2 - 1) * 512 ** -0.5).to(dev),
+                         ((torch.rand(64, generator=g) * 2 - 1) * 512 ** -0.5).to(dev),
+                         ((torch.rand(4, 64, generator=g) * 2 - 1) * 0.125).to(dev),
+                         ((torch.rand(4, generator=g) * 2 - 1) * 0.125).to(dev))
+    gathered = [torch.empty(a.slides, N_CLASSES + 1, device=dev) for _ in range(world)] if world > 1 else None
+
+    def step():
+        logits = eng.eval_logits(store, prm)
+        loss, _, pred = ops.cross_entropy(logits, store.labels, want_pred=True)
+        if world > 1:  # the evaluation loop's one exchange: every rank gets every shard's logits + labels
+            buf = torch.cat([logits, store.labels.unsqueeze(1).float()], dim=1)
+            dist.all_gather(gathered, buf)
+        return logits, loss
+
+    for _ in range(max(a.warmup, 3)):
+        step()
+    sampler = ClockSampler(local)
+    sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    eng.score_events = []
+    launches0 = ops.LAUNCHES
+    sampler.active = True
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        logits, loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler.active = False
+    launches = ops.LAUNCHES - launches0
+    ms_total = barrier_max_ms(e0.elapsed_time(e1), dev)
+    score_ms = [x.elapsed_time(y) for x, y, _ in eng.score_events]
+    score_rows = [r for _, _, r in eng.score_events]
+    eng.score_events = None
+    ms_step = ms_total / a.steps
+    slides_total = a.slides * world
+    value = slides_total / (ms_step * 1e-3)
+
+    # ---- roofline of the streaming kernel (rank 0's launches) ----------------------------------------
+    peak, peak_src = measured_peak()
+    avg_ms = sum(score_ms) / len(score_ms)
+    rows_per_launch = sum(score_rows) / len(score_rows)
+    achieved = rows_per_launch * 2048 / (avg_ms * 1e-3) / 1e9
+    traffic = ncu_traffic_bytes(rows_per_launch)
+    roofline = {"bound": "hbm", "kernel": "score_keys_regw_kernel<6>", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": rows_per_launch * 2048, "avg_launch_ms": avg_ms,
+                "launches_timed": len(score_ms), "share_of_step": avg_ms * len(score_ms) / a.steps / ms_step,
+                "frac_of_8TBps_nominal": achieved / 8000.0}
+
+    # ---- end to end from pinned host memory -------------------------------------------------------------
+    e2e = None
+    if not a.no_e2e:
+        n_host = min(a.e2e_host_slides, a.slides)
+        per_chunk = 32
+        chunks = []
+        for lo in range(0, n_host, per_chunk):
+            n = min(per_chunk, n_host - lo)
+            pinned = torch.empty(n * a.patches, 512, dtype=torch.float32, pin_memory=True)
+            pinned.copy_(store.feat[lo * a.patches:(lo + n) * a.patches])
+            chunks.append(HostChunk(pinned, [i * a.patches for i in range(n + 1)], store.labels_h[lo:lo + n], dev))
+        seq, k = [], 0
+        remaining = a.slides
+        while remaining > 0:  # the step's cohort: cycle through the pinned chunks until every slide is covered
+            ch = chunks[k % len(chunks)]
+            n = len(ch.labels_h)
+            if n > remaining:
+                ch = HostChunk(ch.feat[:remaining * a.patches], ch.offsets_h[:remaining + 1], ch.labels_h[:remaining], dev)
+            seq.append(ch)
+            remaining -= len(ch.labels_h)
+            k += 1
+        host = HostBags(seq, dev)
+        out_h = torch.empty(a.slides, N_CLASSES, dtype=torch.float32, pin_memory=True)
+
+        def e2e_step():
+            lg = eng.eval_logits_host(host, prm)
+            out_h.copy_(lg, non_blocking=True)
+            torch.cuda.current_stream().synchronize()  # the caller holds the logits on the host
+
+        e2e_step()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(a.e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        dt = barrier_max_ms(dt * 1e3, dev) / 1e3
+        e2e = {"value": slides_total / (dt / a.e2e_steps), "unit": "slides/s", "steps": a.e2e_steps,
+               "h2d_bytes_per_step": host.h2d_bytes(), "d2h_bytes_per_step": a.slides * N_CLASSES * 4,
+               "ms_per_step": 1e3 * dt / a.e2e_steps, "h2d_GBps": host.h2d_bytes() / (dt / a.e2e_steps) / 1e9,
+               "host_pool": "%d distinct slides pinned, cycled to %d per step" % (n_host, a.slides),
+               "api": "MocEngine.eval_logits_host"}
+        del host, seq, chunks
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        v, done, passes, dt = cpu_reference_pass(32, a.patches, a.cpu_seconds, threads)
+        cpu = {"value": v, "unit": "slides/s", "cores": threads, "kind": "port",
+               "sample": "32 distinct slides x %d patches in host RAM, looped %d times (%d slides, %.1f s); "
+                         "oracle port of evaluation(), torch fp32" % (a.patches, passes, done, dt)}
+
+    if rank == 0:
+        line = {
+            "metric": "slides_per_sec", "value": value, "unit": "slides/s", "n_gpus": world, "steps": a.steps,
+            "warmup": max(a.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "slides_per_gpu": a.slides, "patches_per_slide": a.patches,
+                       "n_classes": N_CLASSES, "n_ext": N_CLASSES + 4, "topj": TOPJ, "topk": TOPK,
+                       "step": "one evaluation pass over every slide: score + select + gate/combine + pool + CE",
+                       "l2": "inputs are %.1f GB per GPU, far larger than the 126 MB L2: no flush needed"
+                             % (store.nbytes() / 1e9),
+                       "sharding": "slides sharded over GPUs, logits all-gathered per step" if world > 1 else "single GPU"},
+            "patches_per_sec": value * a.patches,
+            "algorithmic_GBps_whole_step": slides_total * a.patches * 2048 / (ms_step * 1e-3) / 1e9,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+            "clocks": sampler.summary(),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

@@ -153,3 +153,48 @@ class BagLoader:
         for k in range(len(d)):
             feats, lbl, coords, path = d[k]
             yield feats.unsqueeze(0), torch.tensor([lbl], device=feats.device), torch.from_numpy(coords).unsqueeze(0), (path,)
+
+
+class HostChunk:
+    def __init__(self, feat: torch.Tensor, offsets_h: Sequence[int], labels_h: Sequence[int], device):
+        self.feat = feat                      # pinned [rows,512]
+        self.rows = feat.size(0)
+        self.offsets_h = [int(v) for v in offsets_h]
+        self.labels_h = [int(v) for v in labels_h]
+        self.offsets = torch.tensor(self.offsets_h, dtype=torch.int64, device=device)
+
+
+class HostBags:
+    """Bags held in pinned host memory in chunks of whole slides, plus the two device staging buffers the
+    engine streams them through (MocEngine.eval_logits_host).  ``chunks`` may repeat the same pinned chunk
+    object to model a cohort larger than host RAM should hold."""
+
+    def __init__(self, chunks: Sequence[HostChunk], device="cuda"):
+        self.chunks = list(chunks)
+        self.device = torch.device(device)
+        self.n_slides = sum(len(c.labels_h) for c in self.chunks)
+        self.total_rows = sum(c.rows for c in self.chunks)
+        max_rows = max(c.rows for c in self.chunks)
+        self.staging = [torch.empty(max_rows, D, dtype=torch.float32, device=device) for _ in range(2)]
+        self.copy_stream = torch.cuda.Stream(device=device)
+        self.ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self.free = [None, None]
+        self.labels = torch.tensor([v for c in self.chunks for v in c.labels_h], dtype=torch.int64, device=device)
+
+    @staticmethod
+    def from_bags(bags: Sequence[torch.Tensor], labels: Sequence[int], slides_per_chunk: int = 64, device="cuda"
+                  ) -> "HostBags":
+        chunks = []
+        for lo in range(0, len(bags), slides_per_chunk):
+            part = bags[lo:lo + slides_per_chunk]
+            offs = [0]
+            for b in part:
+                offs.append(offs[-1] + b.size(0))
+            pinned = torch.empty(offs[-1], D, dtype=torch.float32, pin_memory=True)
+            for i, b in enumerate(part):
+                pinned[offs[i]:offs[i + 1]].copy_(b)
+            chunks.append(HostChunk(pinned, offs, labels[lo:lo + slides_per_chunk], device))
+        return HostBags(chunks, device)
+
+    def h2d_bytes(self) -> int:
+        return self.total_rows * D * 4

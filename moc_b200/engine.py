@@ -51,7 +51,7 @@ class MocEngine:
         self.max_wave_rows = int(max_wave_rows)
         self._key_cache: Dict[int, torch.Tensor] = {}
         self._layout_cache: Dict[tuple, tuple] = {}
-        self.launches = 0  # kernels of ours launched (bench.py reports it)
+        self.score_events = None  # when a list: (start, stop) CUDA events around every scoring launch
 
     # ---- scoring -------------------------------------------------------------------------------
     def keys_for(self, store: RaggedBagStore, lo: int = 0, hi: Optional[int] = None) -> torch.Tensor:
@@ -60,13 +60,21 @@ class MocEngine:
         if self.cache_scores:
             k = self._key_cache.get(id(store))
             if k is None:
-                k = ops.score_keys(store.feat, self.prompts, self.normalize)
-                self.launches += 1
+                k = self._score(store.feat)
                 self._key_cache[id(store)] = k
             return k[:, store.offsets_h[lo]:store.offsets_h[hi]]
         r0, r1 = store.offsets_h[lo], store.offsets_h[hi]
-        self.launches += 1
-        return ops.score_keys(store.feat[r0:r1], self.prompts, self.normalize)
+        return self._score(store.feat[r0:r1])
+
+    def _score(self, feat: torch.Tensor) -> torch.Tensor:
+        if self.score_events is None:
+            return ops.score_keys(feat, self.prompts, self.normalize)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        k = ops.score_keys(feat, self.prompts, self.normalize)
+        b.record()
+        self.score_events.append((a, b, feat.size(0)))
+        return k
 
     def drop_cache(self, store: Optional[RaggedBagStore] = None) -> None:
         if store is None:
@@ -106,7 +114,6 @@ class MocEngine:
             keys = self.keys_for(store, lo, hi)
             offs, _, _, _ = self._layout(store, lo, hi)
             out[lo:hi] = ops.pool_topk(keys, offs, hi - lo, c, self.topk, sp0, ss, vp0, vs, small)
-            self.launches += 1
         return out
 
     # ---- evaluation ----------------------------------------------------------------------------
@@ -125,7 +132,6 @@ class MocEngine:
             sel = ops.select_union(keys, offs, offs_h, c, self.topj, disc, None, base, base_h)
             ho = ops.head_forward(feat, keys, c, sel, params, act, self.topk)
             out[lo:hi] = ho.bag_logits
-            self.launches += 5  # memset-free: select_mark, compact, head_rows, pool_final (+ the bitmap clear)
         return out
 
     def ablation_logits(self, store: RaggedBagStore, how: str) -> torch.Tensor:
@@ -154,5 +160,45 @@ class MocEngine:
         ho = ops.head_forward(feat, keys, c, sel, params, act, self.topk)
         loss, dl, _ = ops.cross_entropy(ho.bag_logits, label_dev, want_grad=True)
         ops.head_backward(feat, keys, c, sel, params, act, self.topk, ho.pool_pos, dl, out=grads_out)
-        self.launches += 8
         return StepOut(loss, ho.bag_logits, sel.sel_count)
+
+    # ---- host-resident bags (end-to-end path) ---------------------------------------------------
+    def eval_logits_host(self, host: "HostBags", params: ops.HeadParams, out: Optional[torch.Tensor] = None
+                         ) -> torch.Tensor:
+        """evaluation over bags that live in pinned HOST memory: chunks are copied to the GPU on a copy stream
+        into two staging buffers while the previous chunk is scored (what a caller holding numpy / h5 data
+        pays end to end).  Returns device logits [n_slides, C]."""
+        c = self.n_classes
+        dev = host.device
+        if out is None:
+            out = torch.empty(host.n_slides, c, dtype=torch.float32, device=dev)
+        disc = _lib.discard_bits(self.discard)
+        act = _lib.active_bits(self.discard, "eval")
+        cur = torch.cuda.current_stream()
+        copy = host.copy_stream
+        copy.wait_stream(cur)
+        lo = 0
+        for ci, ch in enumerate(host.chunks):
+            b = ci % 2
+            buf = host.staging[b][:ch.rows]
+            with torch.cuda.stream(copy):
+                if host.free[b] is not None:
+                    copy.wait_event(host.free[b])
+                buf.copy_(ch.feat, non_blocking=True)
+                host.ready[b].record(copy)
+            cur.wait_event(host.ready[b])
+            key = ("host", id(host), ci, self.topj)
+            lay = self._layout_cache.get(key)
+            if lay is None:
+                base_h = ops.selection_layout(ch.offsets_h, c, self.topj)
+                lay = (torch.tensor(base_h, dtype=torch.int64, device=dev), base_h)
+                self._layout_cache[key] = lay
+            keys = self._score(buf)
+            sel = ops.select_union(keys, ch.offsets, ch.offsets_h, c, self.topj, disc, None, lay[0], lay[1])
+            ho = ops.head_forward(buf, keys, c, sel, params, act, self.topk)
+            n = len(ch.offsets_h) - 1
+            out[lo:lo + n] = ho.bag_logits
+            lo += n
+            host.free[b] = torch.cuda.Event()
+            host.free[b].record(cur)
+        return out

@@ -13,6 +13,14 @@ import torch
 from . import _lib
 from ._lib import MocError, check
 
+LAUNCHES = 0  # kernels of ours launched through this module (bench.py reports the count of its timed region)
+
+
+def _count(n: int) -> None:
+    global LAUNCHES
+    LAUNCHES += n
+
+
 D = 512
 HIDDEN = 64
 GATES = 4
@@ -68,6 +76,7 @@ def score_keys(feat: torch.Tensor, prompts: Prompts, normalize: bool = False,
     r = feat.size(0)
     if out is None:
         out = torch.empty(num_key_planes(prompts.n_classes), r, device=feat.device, dtype=torch.float32)
+    _count(1)
     check(_lib.load().moc_score_keys(feat.data_ptr(), r, prompts.packed.data_ptr(), prompts.n_classes,
                                      prompts.n_ext, int(bool(normalize)), out.data_ptr(), out.stride(0), _stream()))
     return out
@@ -119,6 +128,7 @@ def select_union(keys: torch.Tensor, offsets: torch.Tensor, offsets_h: Sequence[
         row_mask = row_mask.contiguous()
         if not row_mask.is_cuda or row_mask.numel() != total_rows or row_mask.dtype != torch.uint8:
             raise MocError(_lib.E_ARG, "row_mask must be a CUDA bool/uint8 tensor with one entry per row")
+    _count(2)
     check(lib.moc_select_union(keys.data_ptr(), keys.stride(0), offsets.data_ptr(), n_slides, total_rows, n_classes,
                                int(topj), int(discard_mask), _ptr(row_mask), sel_base.data_ptr(), sel_rows.data_ptr(),
                                sel_local.data_ptr(), sel_count.data_ptr(), ws.data_ptr(), ws_bytes, _stream()))
@@ -139,6 +149,7 @@ def topj_sorted(values: torch.Tensor, j: int, largest: bool = True, want_values:
     j = min(int(j), n)
     idx = torch.empty(j, c, dtype=torch.int64, device=v.device)
     vals = torch.empty(j, c, dtype=torch.float32, device=v.device) if want_values else None
+    _count(1)
     check(_lib.load().moc_topj_sorted(v.data_ptr(), n, v.stride(0), c, v.stride(1), j, int(bool(largest)),
                                       idx.data_ptr(), c, _ptr(vals), _stream()))
     if squeeze:
@@ -150,6 +161,7 @@ def topj_sorted(values: torch.Tensor, j: int, largest: bool = True, want_values:
 def pool_topk(keys: torch.Tensor, offsets: torch.Tensor, n_slides: int, n_classes: int, topk: int,
               sel_plane0: int, sel_step: int, val_plane0: int, val_step: int, smallest: bool = False) -> torch.Tensor:
     out = torch.empty(n_slides, n_classes, dtype=torch.float32, device=keys.device)
+    _count(1)
     check(_lib.load().moc_pool_topk(keys.data_ptr(), keys.stride(0), offsets.data_ptr(), n_slides, n_classes,
                                     int(topk), sel_plane0, sel_step, int(smallest), val_plane0, val_step,
                                     out.data_ptr(), _stream()))
@@ -183,6 +195,7 @@ def head_forward(feat: torch.Tensor, keys: torch.Tensor, n_classes: int, sel: Se
     gate = torch.empty(cap, GATES, dtype=torch.float32, device=dev) if want_gate else None
     bag = torch.empty(sel.n_slides, n_classes, dtype=torch.float32, device=dev)
     pos = torch.empty(sel.n_slides, n_classes, topk, dtype=torch.int32, device=dev)
+    _count(2)
     check(_lib.load().moc_head_forward(feat.data_ptr(), keys.data_ptr(), keys.stride(0), n_classes,
                                        sel.sel_base.data_ptr(), sel.sel_rows.data_ptr(), sel.sel_count.data_ptr(),
                                        sel.n_slides, sel.capacity, params.w1.data_ptr(), params.b1.data_ptr(),
@@ -200,6 +213,7 @@ def cross_entropy(bag_logits: torch.Tensor, labels: torch.Tensor, grad_scale: fl
     loss = torch.empty(n, dtype=torch.float32, device=dev)
     dl = torch.empty(n, c, dtype=torch.float32, device=dev) if want_grad else None
     pred = torch.empty(n, dtype=torch.int32, device=dev) if want_pred else None
+    _count(1)
     check(_lib.load().moc_cross_entropy(bag_logits.data_ptr(), labels.data_ptr(), n, c, float(grad_scale),
                                         loss.data_ptr(), _ptr(dl), _ptr(pred), _stream()))
     return loss, dl, pred
@@ -216,6 +230,7 @@ def head_backward(feat: torch.Tensor, keys: torch.Tensor, n_classes: int, sel: S
     ws_bytes = lib.moc_head_backward_workspace_bytes(sel.n_slides, n_classes, topk)
     ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
     dlogits = _dev_f32(dlogits, "dlogits")
+    _count(2)
     check(lib.moc_head_backward(feat.data_ptr(), keys.data_ptr(), keys.stride(0), n_classes, sel.sel_base.data_ptr(),
                                 sel.sel_rows.data_ptr(), sel.sel_count.data_ptr(), sel.n_slides,
                                 params.w1.data_ptr(), params.b1.data_ptr(), params.w2.data_ptr(), params.b2.data_ptr(),
@@ -228,6 +243,7 @@ def adam_step(params: torch.Tensor, grads: torch.Tensor, exp_avg: torch.Tensor, 
               lr: float = 1e-3, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8,
               weight_decay: float = 1e-4) -> None:
     """In-place torch.optim.Adam update of a flat fp32 parameter buffer; ``step`` counts from 1."""
+    _count(1)
     check(_lib.load().moc_adam_step(params.data_ptr(), grads.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
                                     params.numel(), int(step), lr, beta1, beta2, eps, weight_decay, _stream()))
 
@@ -238,6 +254,7 @@ def gather_selected(feat: torch.Tensor, keys: torch.Tensor, n_classes: int, sel_
     dev = feat.device
     sf = torch.empty(n_sel, D, dtype=torch.float32, device=dev) if want_feat else None
     planes = [torch.empty(n_sel, n_classes, dtype=torch.float32, device=dev) for _ in range(4)] if want_planes else [None] * 4
+    _count(1)
     check(_lib.load().moc_gather_selected(feat.data_ptr(), _ptr(keys), keys.stride(0) if keys is not None else 0,
                                           n_classes, sel_rows.data_ptr(), n_sel, _ptr(sf), _ptr(planes[0]),
                                           _ptr(planes[1]), _ptr(planes[2]), _ptr(planes[3]), _stream()))
@@ -249,6 +266,7 @@ def senet_forward(x: torch.Tensor, params: HeadParams) -> torch.Tensor:
     if x.dim() != 2 or x.size(1) != D:
         raise MocError(_lib.E_SHAPE, "senet input must be [rows,512], got %s" % (tuple(x.shape),))
     gate = torch.empty(x.size(0), GATES, dtype=torch.float32, device=x.device)
+    _count(1)
     check(_lib.load().moc_senet_forward(x.data_ptr(), x.size(0), params.w1.data_ptr(), params.b1.data_ptr(),
                                         params.w2.data_ptr(), params.b2.data_ptr(), gate.data_ptr(), _stream()))
     return gate
@@ -263,6 +281,7 @@ def senet_backward(x: torch.Tensor, dgate: torch.Tensor, params: HeadParams) -> 
         return out.zero_()
     ws_bytes = lib.moc_senet_backward_workspace_bytes(n)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+    _count(2)
     check(lib.moc_senet_backward(x.data_ptr(), n, dgate.data_ptr(), params.w1.data_ptr(), params.b1.data_ptr(),
                                  params.w2.data_ptr(), params.b2.data_ptr(), out.data_ptr(), ws.data_ptr(), ws_bytes,
                                  _stream()))
@@ -282,6 +301,7 @@ def row_keys(logits: torch.Tensor, n_fg: int) -> torch.Tensor:
     x = _dev_f32(logits, "logits")
     n, ct = x.shape
     keys = torch.empty(num_key_planes(n_fg), n, dtype=torch.float32, device=x.device)
+    _count(1)
     check(_lib.load().moc_row_keys(x.data_ptr(), n, x.stride(0), n_fg, ct, keys.data_ptr(), keys.stride(0), _stream()))
     return keys
 
@@ -291,6 +311,7 @@ def take_rows(src: torch.Tensor, idx: torch.Tensor, n_cols: int) -> torch.Tensor
     src = _dev_f32(src, "src")
     idx = idx.to(device=src.device, dtype=torch.int64).contiguous()
     out = torch.empty(idx.numel(), n_cols, dtype=torch.float32, device=src.device)
+    _count(1)
     check(_lib.load().moc_take_rows(src.data_ptr(), src.stride(0), idx.data_ptr(), idx.numel(), n_cols,
                                     out.data_ptr(), _stream()))
     return out
@@ -300,6 +321,7 @@ def col_prefix_mean(vals: torch.Tensor, j: int) -> torch.Tensor:
     """vals[:j].mean(dim=0, keepdim=True) for a [J,C] tensor, summed in row order."""
     vals = _dev_f32(vals, "vals")
     out = torch.empty(1, vals.size(1), dtype=torch.float32, device=vals.device)
+    _count(1)
     check(_lib.load().moc_col_prefix_mean(vals.data_ptr(), vals.stride(0), vals.size(1), int(j), out.data_ptr(), _stream()))
     return out
 
@@ -314,6 +336,7 @@ def ablation_pool(keys: torch.Tensor, n_classes: int, sel: Selection, how: str, 
     dev = keys.device
     final = torch.empty(max(sel.capacity, 1), n_classes, dtype=torch.float32, device=dev)
     bag = torch.empty(sel.n_slides, n_classes, dtype=torch.float32, device=dev)
+    _count(2)
     check(_lib.load().moc_ablation_forward(keys.data_ptr(), keys.stride(0), n_classes, sel.sel_base.data_ptr(),
                                            sel.sel_rows.data_ptr(), sel.sel_count.data_ptr(), sel.n_slides,
                                            sel.capacity, _ABLATION_MODES[how], int(topk), final.data_ptr(),

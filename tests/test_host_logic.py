@@ -1,0 +1,149 @@
+"""CPU-side checks: the C ABI loads and exports every declared symbol, host logic, sharding, gloo collectives."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    from moc_b200 import _lib, build
+    build.build()
+    lib = _lib.load()
+    hdr = open(os.path.join(ROOT, "include", "moc_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(moc_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), "libmoc_b200.so does not export %s" % name
+    assert declared == set(_lib.SIGNATURES), "ctypes table and header disagree: %s" % (declared ^ set(_lib.SIGNATURES))
+    assert lib.moc_version() >= 100
+    assert lib.moc_num_key_planes(3) == 9
+    assert lib.moc_select_capacity(100000, 2, 400) == 2400 and lib.moc_select_capacity(50, 2, 400) == 50
+    assert lib.moc_packed_cols(2, 6) == 8 and lib.moc_packed_cols(30, 34) == 36
+
+
+def test_sass_uses_bulk_copy_engine():
+    """The streaming kernel must move patches with the bulk-copy engine (UBLKCP) and wait on mbarriers."""
+    from moc_b200 import _lib, build
+    build.build()
+    out = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    assert "UBLKCP" in out and "SYNCS" in out
+
+
+def test_ops_fail_loudly_without_cuda():
+    from moc_b200 import MocError, slide_process
+    from moc_b200 import ops
+    with pytest.raises(MocError):
+        ops.score_keys(torch.zeros(8, 512), None)
+    with pytest.raises(MocError):
+        slide_process(torch.zeros(8, 512), torch.zeros(512, 2), torch.zeros(512, 6), 2)
+    if not torch.cuda.is_available():
+        from moc_b200 import senet
+        with pytest.raises(MocError):
+            senet(512, 4)(torch.zeros(3, 512))
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "moc_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
+                assert "moc_oracle" not in src, f
+
+
+def test_flag_masks_follow_reference_quirks():
+    from moc_b200 import _lib
+    assert _lib.discard_bits(["topk", "bottomk"]) == 9
+    assert _lib.discard_bits(["nonsense"]) == 0
+    assert _lib.active_bits([], "train") == 15
+    assert _lib.active_bits(["topk", "delta_diff"], "train") == 2 | 8
+    # evaluation keeps top-k and bottom-k whatever is discarded (main_moc.py:486-492)
+    assert _lib.active_bits(["topk", "bottomk", "delta_diff"], "eval") == 1 | 2 | 8
+
+
+def test_selection_layout_and_synthetic_are_deterministic():
+    from moc_b200 import ops, synthetic
+    assert ops.selection_layout([0, 50, 20050], 2, 400) == [0, 50, 2450]
+    w, we = synthetic.prompt_matrices(3)
+    assert w.shape == (512, 3) and we.shape == (512, 7) and torch.equal(we[:, :3], w)
+    assert torch.allclose(we.norm(dim=0), torch.ones(7), atol=1e-6)
+    a = synthetic.make_bag(257, 1, we, 3, seed=5)
+    b = synthetic.make_bag(257, 1, we, 3, seed=5)
+    assert torch.equal(a, b) and a.shape == (257, 512)
+    assert torch.allclose(a.norm(dim=1), torch.ones(257), atol=1e-5)
+    bank, collapsed = synthetic.prompt_bank(3, 64)
+    assert bank.shape == (512, 192) and collapsed.shape == (512, 3)
+    sizes = synthetic.log_uniform_sizes(1000)
+    assert min(sizes) >= 1000 and max(sizes) <= 100000 and 15000 < np.mean(sizes) < 30000
+
+
+def test_bag_dataset_surface_on_cpu():
+    from moc_b200.bag_store import BagDataset, BagLoader, RaggedBagStore
+    bags = [torch.randn(n, 512) for n in (3, 5, 2)]
+    st = RaggedBagStore.from_bags(bags, [0, 1, 0], device="cpu")
+    assert st.total_rows == 10 and st.offsets_h == [0, 3, 8, 10] and torch.equal(st.bag(1), bags[1])
+    ds = BagDataset(st, repeat_num=7)
+    assert len(ds) == 7 and ds.real_len() == 3
+    assert torch.equal(ds[4][0], bags[1]) and ds[4][1] == 1
+    with pytest.raises(IndexError):
+        ds[7]
+    ds.repeat_num = None
+    assert len(ds) == 3
+    items = list(BagLoader(ds))
+    assert len(items) == 3 and items[0][0].shape == (1, 3, 512) and items[2][1].tolist() == [0]
+
+
+def test_lpt_shards_balance_and_cover():
+    from moc_b200 import synthetic
+    from moc_b200.dist import lpt_shards
+    sizes = synthetic.log_uniform_sizes(500)
+    for world in (1, 2, 4, 8):
+        shards = lpt_shards(sizes, world)
+        flat = sorted(i for s in shards for i in s)
+        assert flat == list(range(500))
+        loads = [sum(sizes[i] for i in s) for s in shards]
+        assert max(loads) - min(loads) <= max(sizes)
+        assert lpt_shards(sizes, world) == shards
+
+
+_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %(root)r)
+from moc_b200.dist import Shard, allreduce_sum, init_from_env, barrier_max_ms
+rank, local, world = init_from_env("gloo")
+sizes = [1000 + 37 * ((i * 7919) %% 101) for i in range(23)]
+sh = Shard(sizes, rank, world)
+g = torch.Generator().manual_seed(0)
+full = torch.randn(23, 3, generator=g)
+labels = torch.arange(23) %% 3
+ids = torch.tensor(sh.ids, dtype=torch.int64)
+out, lab = sh.gather(full[ids], labels[ids])
+assert torch.equal(out, full) and torch.equal(lab, labels), "gather mismatch on rank %%d" %% rank
+flat = torch.full((33092,), float(rank + 1))
+allreduce_sum(flat)
+assert float(flat[0]) == sum(range(1, world + 1))
+assert barrier_max_ms(float(rank), "cpu") == float(world - 1)
+dist.barrier()
+dist.destroy_process_group()
+print("rank %%d ok" %% rank)
+'''
+
+
+def test_gloo_world2_gather_and_allreduce(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(_WORKER % {"root": ROOT})
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29731", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r), LOCAL_RANK=str(r)),
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, o
+        assert "rank %d ok" % r in o
