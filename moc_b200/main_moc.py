@@ -1,0 +1,141 @@
+"""Command line of the MOC few-shot run on B200 - the reference's flags (main_moc.py:29-46) plus the options
+needed to run without a CONCH checkpoint or slide data:
+
+    python -m moc_b200.main_moc --fold 0 --shot 4 --topj 400 --topk 10 --dataset nsclc --synthetic
+    torchrun --nproc-per-node 8 -m moc_b200.main_moc --dataset ebrains30 --shot 16 --synthetic --n_patches 50000
+
+Real data: ``--data_dir`` with CLAM-style ``pt_files/<slide_id>.pt`` bags, ``--csv`` (slide_id,label) and
+``--splits_csv`` (train,val,test columns, as ``splits/*_fewshot/*shots/splits_*.csv``), and ``--weights`` /
+``--weights_ext`` pointing at the cached prompt matrices the reference writes to ``models/classifier_weights``.
+Outputs keep the reference's names and JSON schema (zs_results_*, best_results_*, best_model_*.pt).
+"""
+from __future__ import annotations
+
+import argparse
+import os
+
+import torch
+
+DATASETS = {
+    # name: (classes, label names, synthetic val/test sizes following the shipped 4-shot splits where they exist)
+    "nsclc": (2, ["LUAD", "LUSC"], 49, 209),
+    "rcc": (3, ["KICH", "KIRC", "KIRP"], 65, 222),
+    "ebrains30": (30, None, 120, 400),
+}
+
+
+def get_args(argv=None):
+    p = argparse.ArgumentParser(description="Configurations for WSI Training")
+    p.add_argument("--fold", type=int, default=0, help="fold number")
+    p.add_argument("--shot", type=int, default=1, help="split number")
+    p.add_argument("--topj", type=int, default=10, help="topj for classifier selection")
+    p.add_argument("--topk", type=int, default=10, help="topk for final pooling")
+    p.add_argument("--result_dir", type=str, default="results/moc_train", help="result directory")
+    p.add_argument("--dataset", type=str, default="nsclc", choices=sorted(DATASETS), help="dataset name")
+    p.add_argument("--pretrain", type=str, default="conch", choices=["conch"], help="pretrain model")
+    p.add_argument("--disable_tqdm", action="store_true", help="accepted for compatibility (no progress bars here)")
+    p.add_argument("--discard_classifiers", nargs="+", default=[], help="topk, delta_softmax, delta_diff, bottomk")
+    p.add_argument("--load_weight", type=bool, default=True, help="load stored classifier weight")
+    p.add_argument("--check_zeroshot", type=bool, default=True, help="get zero-shot results")
+    p.add_argument("--ablation_study", type=str, default="none", choices=["none", "avg", "sum", "max"])
+    # additions
+    p.add_argument("--synthetic", action="store_true", help="synthetic CONCH-shaped bags and random prompt matrices")
+    p.add_argument("--n_patches", type=int, default=8000)
+    p.add_argument("--n_val", type=int, default=None)
+    p.add_argument("--n_test", type=int, default=None)
+    p.add_argument("--epochs", type=int, default=25, help="the reference hard-codes 25 (main_moc.py:611)")
+    p.add_argument("--seed", type=int, default=None, help="torch.manual_seed before model init (reference: unseeded)")
+    p.add_argument("--cache_scores", action="store_true", help="score every bag once per run (bit-identical results)")
+    p.add_argument("--data_dir", type=str, default=None)
+    p.add_argument("--csv", type=str, default=None)
+    p.add_argument("--splits_csv", type=str, default=None)
+    p.add_argument("--weights", type=str, default=None)
+    p.add_argument("--weights_ext", type=str, default=None)
+    return p.parse_args(argv)
+
+
+def _real_stores(args, device):
+    import pandas as pd
+    from .bag_store import RaggedBagStore
+    n_classes, names, _, _ = DATASETS[args.dataset]
+    df = pd.read_csv(args.csv, dtype={"slide_id": str})
+    lab = {n: i for i, n in enumerate(names)} if names else None
+    df["y"] = df["label"].map(lab) if lab else df["label"].astype("category").cat.codes
+    splits = pd.read_csv(args.splits_csv, dtype=str)
+    out = []
+    for key in ("train", "val", "test"):
+        ids = set(splits[key].dropna().tolist())
+        part = df[df["slide_id"].isin(ids)]  # dataset-csv order, as get_split_from_df (dataset_generic.py:206-207)
+        out.append(RaggedBagStore.from_pt_dir(args.data_dir, part["slide_id"].tolist(), part["y"].tolist(), device))
+    return out
+
+
+def run(args):
+    from . import loops, synthetic
+    from .bag_store import BagDataset, BagLoader, RaggedBagStore
+    from .dist import Shard, init_from_env
+    from .model import senet
+
+    rank, local, world = init_from_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("moc_b200 needs a CUDA device: there is no CPU path")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    n_classes, _, n_val, n_test = DATASETS[args.dataset]
+    args.n_classes = n_classes
+    n_val = args.n_val or n_val
+    n_test = args.n_test or n_test
+
+    if args.synthetic:
+        w, w_ext = synthetic.prompt_matrices(n_classes, device=device)
+        n_train = args.shot * n_classes
+        sizes = {"train": [args.n_patches] * n_train, "val": [args.n_patches] * n_val, "test": [args.n_patches] * n_test}
+        seeds = {"train": 11 + args.fold, "val": 22 + args.fold, "test": 33 + args.fold}
+        stores, shards = {}, {}
+        for key in ("train", "val", "test"):
+            labels = [i % n_classes for i in range(len(sizes[key]))]
+            ids = list(range(len(sizes[key])))
+            if world > 1 and key != "train":  # eval splits are slide-sharded; few-shot bags are replicated
+                shards[key] = Shard(sizes[key], rank, world)
+                ids = shards[key].ids
+            st = RaggedBagStore.synthetic([sizes[key][i] for i in ids], n_classes, w_ext, device=device,
+                                          labels=[labels[i] for i in ids], cohort_seed=seeds[key])
+            # slide i of the cohort must be the same bag whichever rank holds it
+            if world > 1 and key != "train":
+                for k, i in enumerate(ids):
+                    synthetic.make_bag(sizes[key][i], labels[i], w_ext, n_classes, synthetic.slide_seed(seeds[key], i),
+                                       device=device, out=st.bag(k))
+            stores[key] = st
+    else:
+        if not (args.data_dir and args.csv and args.splits_csv and args.weights and args.weights_ext):
+            raise SystemExit("real data needs --data_dir --csv --splits_csv --weights --weights_ext (or use --synthetic)")
+        w = torch.load(args.weights, map_location=device).float()
+        w_ext = torch.load(args.weights_ext, map_location=device).float()
+        tr, va, te = _real_stores(args, device)
+        stores, shards = {"train": tr, "val": va, "test": te}, {}
+
+    loops.set_prompts(w, w_ext)
+    loaders = {}
+    for key, st in stores.items():
+        ds = BagDataset(st, repeat_num=int(args.shot) * n_classes if key == "train" else None)
+        if key in shards:
+            ds.shard = shards[key]
+        loaders[key] = BagLoader(ds)
+
+    if args.seed is not None:
+        torch.manual_seed(args.seed)
+    model = senet(512, 4).to(device)
+    optimizer = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4)
+    res = loops.main(args, model, optimizer, loaders["train"], loaders["val"], loaders["test"], device,
+                     num_epoch=args.epochs, is_main=(rank == 0))
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+    return res
+
+
+if __name__ == "__main__":
+    a = get_args()
+    os.makedirs(a.result_dir, exist_ok=True)
+    run(a)

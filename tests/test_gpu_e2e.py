@@ -1,0 +1,97 @@
+"""BASELINE.json configs[0]: NSCLC 4-shot MOC train+eval - the CPU oracle end to end against the CUDA path.
+
+Same seeded synthetic cohort (8 train / 49 val / 209 test slides, shapes of splits/nsclc_fewshot/4shots), same
+initial gate weights, same half masks; per-epoch loss/acc/auc and the final best_results must agree."""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import moc_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _run_case(c, shot, n_patches, n_val, n_test, topj, topk, epochs, seed):
+    import moc_b200 as M
+    from moc_b200 import loops, synthetic
+    w, we = synthetic.prompt_matrices(c)
+    n_train = shot * c
+    tr_b, tr_y = synthetic.make_cohort(n_train, n_patches, c, cohort_seed=seed)
+    va_b, va_y = synthetic.make_cohort(n_val, n_patches, c, cohort_seed=seed + 1)
+    te_b, te_y = synthetic.make_cohort(n_test, n_patches, c, cohort_seed=seed + 2)
+    gen = torch.Generator().manual_seed(seed + 3)
+    masks = [[torch.rand(tr_b[k % n_train].size(0), generator=gen) > 0.5 for k in range(n_train)] for _ in range(epochs)]
+
+    # ---- oracle (CPU) -----------------------------------------------------------------------------
+    torch.set_num_threads(torch.get_num_threads())
+    prm = O.SenetParams.init(seed + 4)
+    init = prm.clone()
+    st = O.AdamState()
+    tr = O.BagList(tr_b, tr_y, repeat_num=n_train)
+    va, te = O.BagList(va_b, va_y), O.BagList(te_b, te_y)
+    ref = {"zs": [O.zs_evaluation(d, w, we, c, topk) for d in (tr, va, te)], "epochs": []}
+    best_val, best = 0, None
+    for e in range(epochs):
+        O.train_epoch(prm, st, tr, w, we, c, topj, topk, (), masks[e])
+        row = {"train": O.evaluation(prm, tr, w, we, c, topj, topk), "val": O.evaluation(prm, va, w, we, c, topj, topk)}
+        if row["val"]["auc"] > best_val:
+            row["test"] = O.evaluation(prm, te, w, we, c, topj, topk)
+            best_val, best = row["val"]["auc"], (e, row["test"]["auc"], row["test"]["acc"])
+        ref["epochs"].append(row)
+
+    # ---- CUDA path through the reference-shaped loops ------------------------------------------------
+    loops.set_prompts(w.to(DEV), we.to(DEV))
+    args = types.SimpleNamespace(n_classes=c, topj=topj, topk=topk, discard_classifiers=[], pretrain="conch",
+                                 ablation_study="none", cache_scores=True, disable_tqdm=True)
+    mk = lambda b, y, rep=None: M.BagLoader(M.BagDataset(M.RaggedBagStore.from_bags(b, y, DEV), repeat_num=rep))
+    trl, val, tel = mk(tr_b, tr_y, n_train), mk(va_b, va_y), mk(te_b, te_y)
+    model = M.senet(512, 4)
+    model.load_state_dict(init.state_dict())
+    model.to(DEV)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4)
+    got = {"zs": [M.zs_evaluation(l, DEV, args) for l in (trl, val, tel)], "epochs": []}
+    g_best_val, g_best = 0, None
+    for e in range(epochs):
+        M.train(model, trl, opt, DEV, args, masks=masks[e])
+        row = {"train": M.evaluation(model, trl, DEV, args), "val": M.evaluation(model, val, DEV, args)}
+        if row["val"]["auc"] > g_best_val:
+            row["test"] = M.evaluation(model, tel, DEV, args)
+            g_best_val, g_best = row["val"]["auc"], (e, row["test"]["auc"], row["test"]["acc"])
+        got["epochs"].append(row)
+    return ref, got, best, g_best, prm, model
+
+
+def _same(a, b, what):
+    assert a["acc"] == b["acc"], "%s acc %r vs %r" % (what, a["acc"], b["acc"])
+    assert a["auc"] == b["auc"], "%s auc %r vs %r" % (what, a["auc"], b["auc"])
+    assert abs(a["loss"] - b["loss"]) <= 1e-4 * abs(b["loss"]) + 1e-7, "%s loss %r vs %r" % (what, a["loss"], b["loss"])
+
+
+def test_config1_nsclc_4shot_train_eval():
+    ref, got, best, g_best, prm, model = _run_case(c=2, shot=4, n_patches=8000, n_val=49, n_test=209, topj=400,
+                                                   topk=10, epochs=25, seed=50)
+    for r, g, name in zip(ref["zs"], got["zs"], ("zs_train", "zs_val", "zs_test")):
+        _same(g, r, name)
+    assert 0.6 < ref["zs"][2]["auc"] < 1.0  # the synthetic cohort is informative, so AUC equality means something
+    for e, (r, g) in enumerate(zip(ref["epochs"], got["epochs"])):
+        assert set(r) == set(g), "epoch %d: test evaluated on different epochs" % e
+        for k in r:
+            _same(g[k], r[k], "epoch %d %s" % (e, k))
+    assert best == g_best
+    for key, t in model.state_dict().items():
+        assert (t.cpu() - prm.state_dict()[key]).abs().max().item() < 1e-4, key
+
+
+def test_config3_rcc_shapes_short():
+    """RCC-shaped (C=3, C_ext=7): 3 epochs are enough to cover the three-class AUC path (ovo / macro)."""
+    ref, got, best, g_best, _, _ = _run_case(c=3, shot=2, n_patches=3000, n_val=30, n_test=45, topj=400, topk=10,
+                                             epochs=3, seed=60)
+    for r, g, name in zip(ref["zs"], got["zs"], ("zs_train", "zs_val", "zs_test")):
+        _same(g, r, name)
+    for e, (r, g) in enumerate(zip(ref["epochs"], got["epochs"])):
+        for k in r:
+            _same(g[k], r[k], "epoch %d %s" % (e, k))
+    assert best == g_best
