@@ -125,16 +125,21 @@ int moc_col_prefix_mean(const float* vals, int64_t ld, int n_cols, int j, float*
  * the four score planes (main_moc.py:391-403 / :482-492, planes chosen by
  * active_mask), then per (slide, class) the mean of the min(topk, S) largest
  * (topj_pooling, utils/patch_selection_classifier.py:18-32).
+ * The first layer runs on the tensor cores (tcgen05, 3xTF32 = fp32-accurate);
+ * the workspace (moc_head_forward_workspace_bytes(), 16-byte aligned) holds W1
+ * split and swizzled for them.  MOC_HEAD_IMPL=simt in the environment selects
+ * the CUDA-core kernel instead.
  * gate [S_total,4], final [S_total,C], bag_logits [n_slides,C],
  * pool_pos [n_slides,C,topk] (positions inside the slide's selected list,
  * -1 padded), all indexed through sel_base/sel_count. gate may be null. */
+size_t moc_head_forward_workspace_bytes(void);
 int moc_head_forward(const float* feat, const float* keys, int64_t key_stride, int n_classes,
                      const int64_t* sel_base, const int32_t* sel_rows, const int32_t* sel_count,
                      int n_slides, int64_t sel_capacity_total,
                      const float* w1, const float* b1, const float* w2, const float* b2,
                      unsigned active_mask, int topk,
                      float* gate, float* final_scores, float* bag_logits, int32_t* pool_pos,
-                     void* stream);
+                     void* workspace, size_t workspace_bytes, void* stream);
 
 /* ablation_evaluation (main_moc.py:523-582): un-gated avg (mode 0) / sum (1) / max (2) of the four planes
  * of every selected row, then the same top-K pooling. */
@@ -161,7 +166,7 @@ int moc_gather_selected(const float* feat, const float* keys, int64_t key_stride
  * gate = sigmoid(W2 relu(W1 x + b1) + b2) and, for autograd, the parameter
  * gradient given d(loss)/d(gate) [n_rows,4] (rows whose gradient is all-zero are skipped). */
 int moc_senet_forward(const float* x, int64_t n_rows, const float* w1, const float* b1, const float* w2,
-                      const float* b2, float* gate, void* stream);
+                      const float* b2, float* gate, void* workspace, size_t workspace_bytes, void* stream);
 size_t moc_senet_backward_workspace_bytes(int64_t n_rows);
 int moc_senet_backward(const float* x, int64_t n_rows, const float* dgate, const float* w1, const float* b1,
                        const float* w2, const float* b2, float* grads, void* workspace, size_t workspace_bytes,

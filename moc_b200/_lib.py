@@ -43,14 +43,15 @@ SIGNATURES = {
     "moc_row_keys": (i32, [p, i64, i64, i32, i32, p, i64, p]),
     "moc_take_rows": (i32, [p, i64, p, i64, i32, p, p]),
     "moc_col_prefix_mean": (i32, [p, i64, i32, i32, p, p]),
-    "moc_head_forward": (i32, [p, p, i64, i32, p, p, p, i32, i64, p, p, p, p, u32, i32, p, p, p, p, p]),
+    "moc_head_forward_workspace_bytes": (sz, []),
+    "moc_head_forward": (i32, [p, p, i64, i32, p, p, p, i32, i64, p, p, p, p, u32, i32, p, p, p, p, p, sz, p]),
     "moc_ablation_forward": (i32, [p, i64, i32, p, p, p, i32, i64, i32, i32, p, p, p]),
     "moc_pool_topk": (i32, [p, i64, p, i32, i32, i32, i32, i32, i32, i32, i32, p, p]),
     "moc_cross_entropy": (i32, [p, p, i32, i32, f32, p, p, p, p]),
     "moc_head_backward_workspace_bytes": (sz, [i32, i32, i32]),
     "moc_head_backward": (i32, [p, p, i64, i32, p, p, p, i32, p, p, p, p, u32, i32, p, p, p, p, sz, p]),
     "moc_gather_selected": (i32, [p, p, i64, i32, p, i64, p, p, p, p, p, p]),
-    "moc_senet_forward": (i32, [p, i64, p, p, p, p, p, p]),
+    "moc_senet_forward": (i32, [p, i64, p, p, p, p, p, p, sz, p]),
     "moc_senet_backward_workspace_bytes": (sz, [i64]),
     "moc_senet_backward": (i32, [p, i64, p, p, p, p, p, p, p, sz, p]),
     "moc_adam_step": (i32, [p, p, p, p, i64, i64, f32, f32, f32, f32, f32, p]),

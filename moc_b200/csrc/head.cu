@@ -9,10 +9,27 @@
 // All arithmetic is fp32 with fp32 accumulation.  Reductions that decide results (pooling order, gradient
 // sums) run in a fixed order, so repeated runs are bit-identical.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
 namespace moc {
+
+// head_tc.cu: the tcgen05 (3xTF32) implementation of the gate MLP
+size_t head_tc_workspace_bytes();
+int launch_head_rows_tc(const float* feat, const float* keys, int64_t key_stride, int C, const int32_t* sel_rows,
+                        int64_t n_slots, const float* w1, const float* b1, const float* w2, const float* b2,
+                        unsigned active_mask, float* gate, float* final_scores, void* workspace, cudaStream_t st);
+
+// MOC_HEAD_IMPL=simt selects the CUDA-core kernel (kept as the in-tree cross-check of the tensor-core path)
+static bool use_simt_head() {
+    static int cached = -1;
+    if (cached < 0) {
+        const char* e = getenv("MOC_HEAD_IMPL");
+        cached = (e && e[0] == 's') ? 1 : 0;
+    }
+    return cached == 1;
+}
 
 constexpr int H = MOC_HIDDEN;  // 64
 constexpr int G = MOC_GATES;   // 4
@@ -452,7 +469,8 @@ extern "C" int moc_head_forward(const float* feat, const float* keys, int64_t ke
                                 const int64_t* sel_base, const int32_t* sel_rows, const int32_t* sel_count,
                                 int n_slides, int64_t sel_capacity_total, const float* w1, const float* b1,
                                 const float* w2, const float* b2, unsigned active_mask, int topk, float* gate,
-                                float* final_scores, float* bag_logits, int32_t* pool_pos, void* stream) {
+                                float* final_scores, float* bag_logits, int32_t* pool_pos, void* workspace,
+                                size_t workspace_bytes, void* stream) {
     MOC_CHECK_ARG(feat && keys && sel_base && sel_rows && sel_count && w1 && b1 && w2 && b2 && final_scores &&
                       bag_logits,
                   "moc_head_forward: null pointer");
@@ -461,14 +479,24 @@ extern "C" int moc_head_forward(const float* feat, const float* keys, int64_t ke
     if (n_slides == 0) return MOC_OK;
     cudaStream_t st = (cudaStream_t)stream;
     if (sel_capacity_total > 0) {
-        const size_t smem = (size_t)(H + HR_TM) * HR_LD * sizeof(float);
-        MOC_CUDA(cudaFuncSetAttribute(head_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const int64_t n_tiles = (sel_capacity_total + HR_TM - 1) / HR_TM;
-        const int grid = (int)(n_tiles < sm_count() ? n_tiles : sm_count());
-        head_rows_kernel<<<grid, HR_THREADS, smem, st>>>(feat, keys, key_stride, n_classes, sel_rows,
-                                                         sel_capacity_total, w1, b1, w2, b2, active_mask, gate,
-                                                         final_scores);
-        MOC_LAUNCH_CHECK("head_rows_kernel");
+        if (use_simt_head()) {
+            const size_t smem = (size_t)(H + HR_TM) * HR_LD * sizeof(float);
+            MOC_CUDA(cudaFuncSetAttribute(head_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const int64_t n_tiles = (sel_capacity_total + HR_TM - 1) / HR_TM;
+            const int grid = (int)(n_tiles < sm_count() ? n_tiles : sm_count());
+            head_rows_kernel<<<grid, HR_THREADS, smem, st>>>(feat, keys, key_stride, n_classes, sel_rows,
+                                                             sel_capacity_total, w1, b1, w2, b2, active_mask, gate,
+                                                             final_scores);
+            MOC_LAUNCH_CHECK("head_rows_kernel");
+        } else {
+            if (workspace == nullptr || workspace_bytes < head_tc_workspace_bytes()) {
+                set_error("moc_head_forward: workspace %zu B < required %zu B", workspace_bytes, head_tc_workspace_bytes());
+                return MOC_E_WORKSPACE;
+            }
+            const int rc = launch_head_rows_tc(feat, keys, key_stride, n_classes, sel_rows, sel_capacity_total, w1, b1,
+                                               w2, b2, active_mask, gate, final_scores, workspace, st);
+            if (rc != MOC_OK) return rc;
+        }
     }
     const int64_t items = (int64_t)n_slides * n_classes;
     pool_final_kernel<<<(unsigned)((items + POOL_WARPS - 1) / POOL_WARPS), POOL_WARPS * 32, 0, st>>>(
@@ -548,11 +576,21 @@ extern "C" int moc_gather_selected(const float* feat, const float* keys, int64_t
     return MOC_OK;
 }
 
+extern "C" size_t moc_head_forward_workspace_bytes(void) { return head_tc_workspace_bytes(); }
+
 extern "C" int moc_senet_forward(const float* x, int64_t n_rows, const float* w1, const float* b1, const float* w2,
-                                 const float* b2, float* gate, void* stream) {
+                                 const float* b2, float* gate, void* workspace, size_t workspace_bytes, void* stream) {
     MOC_CHECK_ARG(x && w1 && b1 && w2 && b2 && gate && n_rows >= 0, "moc_senet_forward: bad arguments");
     MOC_CHECK_SHAPE(n_rows < (1ll << 31), "moc_senet_forward: too many rows");
     if (n_rows == 0) return MOC_OK;
+    if (!use_simt_head()) {
+        if (workspace == nullptr || workspace_bytes < head_tc_workspace_bytes()) {
+            set_error("moc_senet_forward: workspace %zu B < required %zu B", workspace_bytes, head_tc_workspace_bytes());
+            return MOC_E_WORKSPACE;
+        }
+        return launch_head_rows_tc(x, nullptr, 0, 0, nullptr, n_rows, w1, b1, w2, b2, 0u, gate, nullptr, workspace,
+                                   (cudaStream_t)stream);
+    }
     const size_t smem = (size_t)(H + HR_TM) * HR_LD * sizeof(float);
     MOC_CUDA(cudaFuncSetAttribute(head_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t n_tiles = (n_rows + HR_TM - 1) / HR_TM;

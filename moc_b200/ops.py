@@ -195,12 +195,16 @@ def head_forward(feat: torch.Tensor, keys: torch.Tensor, n_classes: int, sel: Se
     gate = torch.empty(cap, GATES, dtype=torch.float32, device=dev) if want_gate else None
     bag = torch.empty(sel.n_slides, n_classes, dtype=torch.float32, device=dev)
     pos = torch.empty(sel.n_slides, n_classes, topk, dtype=torch.int32, device=dev)
-    _count(2)
-    check(_lib.load().moc_head_forward(feat.data_ptr(), keys.data_ptr(), keys.stride(0), n_classes,
+    lib = _lib.load()
+    ws_bytes = lib.moc_head_forward_workspace_bytes()
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    _count(3)
+    check(lib.moc_head_forward(feat.data_ptr(), keys.data_ptr(), keys.stride(0), n_classes,
                                        sel.sel_base.data_ptr(), sel.sel_rows.data_ptr(), sel.sel_count.data_ptr(),
                                        sel.n_slides, sel.capacity, params.w1.data_ptr(), params.b1.data_ptr(),
                                        params.w2.data_ptr(), params.b2.data_ptr(), int(active_mask), int(topk),
-                                       _ptr(gate), final.data_ptr(), bag.data_ptr(), pos.data_ptr(), _stream()))
+                                       _ptr(gate), final.data_ptr(), bag.data_ptr(), pos.data_ptr(), ws.data_ptr(),
+                                       ws_bytes, _stream()))
     return HeadOut(final, bag, pos, gate)
 
 
@@ -266,9 +270,13 @@ def senet_forward(x: torch.Tensor, params: HeadParams) -> torch.Tensor:
     if x.dim() != 2 or x.size(1) != D:
         raise MocError(_lib.E_SHAPE, "senet input must be [rows,512], got %s" % (tuple(x.shape),))
     gate = torch.empty(x.size(0), GATES, dtype=torch.float32, device=x.device)
-    _count(1)
-    check(_lib.load().moc_senet_forward(x.data_ptr(), x.size(0), params.w1.data_ptr(), params.b1.data_ptr(),
-                                        params.w2.data_ptr(), params.b2.data_ptr(), gate.data_ptr(), _stream()))
+    lib = _lib.load()
+    ws_bytes = lib.moc_head_forward_workspace_bytes()
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+    _count(2)
+    check(lib.moc_senet_forward(x.data_ptr(), x.size(0), params.w1.data_ptr(), params.b1.data_ptr(),
+                                params.w2.data_ptr(), params.b2.data_ptr(), gate.data_ptr(), ws.data_ptr(), ws_bytes,
+                                _stream()))
     return gate
 
 

@@ -295,3 +295,29 @@ def test_errors_are_loud():
         ops.Prompts.pack(w, torch.zeros(512, 2, device=DEV))  # needs background columns
     with pytest.raises(MocError):
         ops.Prompts.pack(w, torch.zeros(512, 80, device=DEV))  # wider than this build supports
+
+
+def test_tensor_core_head_matches_cuda_core_head():
+    """The tcgen05 (3xTF32) gate kernel against the fp32 CUDA-core kernel on the same rows, dense senet mode."""
+    import os
+    import subprocess
+    import sys
+    from moc_b200 import ops
+    gen = torch.Generator().manual_seed(3)
+    x = torch.randn(1000, 512, generator=gen) * 0.3
+    x[5] = 0
+    x[17] *= 40.0  # large rows: TF32 splitting must stay accurate across magnitudes
+    oprm = O.SenetParams.init(11)
+    prm = ops.HeadParams(oprm.w1.to(DEV), oprm.b1.to(DEV), oprm.w2.to(DEV), oprm.b2.to(DEV))
+    g_tc = ops.senet_forward(x.to(DEV), prm).cpu()
+    g_ref, _ = O.senet_forward(oprm, x)
+    assert (g_tc - g_ref).abs().max().item() < 2e-6
+    # the CUDA-core implementation is selected per process through the environment
+    code = ("import torch,sys;sys.path.insert(0,%r);from moc_b200 import ops;from oracle import moc_oracle as O;"
+            "g=torch.Generator().manual_seed(3);x=torch.randn(1000,512,generator=g)*0.3;x[5]=0;x[17]*=40.0;"
+            "p=O.SenetParams.init(11);q=ops.HeadParams(p.w1.cuda(),p.b1.cuda(),p.w2.cuda(),p.b2.cuda());"
+            "torch.save(ops.senet_forward(x.cuda(),q).cpu(),sys.argv[1])") % os.path.dirname(os.path.dirname(__file__))
+    out = "/tmp/moc_simt_gate.pt"
+    subprocess.run([sys.executable, "-c", code, out], check=True, env=dict(os.environ, MOC_HEAD_IMPL="simt"), timeout=120)
+    g_simt = torch.load(out)
+    assert (g_tc - g_simt).abs().max().item() < 2e-6
