@@ -1,0 +1,55 @@
+"""torchrun worker: slide-sharded evaluation over NCCL must reproduce the single-GPU metrics exactly."""
+import json
+import os
+import sys
+import types
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import moc_b200 as M  # noqa: E402
+from moc_b200 import loops, synthetic  # noqa: E402
+from moc_b200.dist import Shard, init_from_env  # noqa: E402
+
+
+def main():
+    rank, local, world = init_from_env("nccl")
+    dev = torch.device("cuda", local)
+    c, j, k = 3, 200, 10
+    w, we = synthetic.prompt_matrices(c, device=dev)
+    loops.set_prompts(w, we)
+    sizes = synthetic.log_uniform_sizes(37, lo=300, hi=6000, seed=3)
+    labels = [i % c for i in range(len(sizes))]
+    args = types.SimpleNamespace(n_classes=c, topj=j, topk=k, discard_classifiers=[], pretrain="conch",
+                                 ablation_study="none", cache_scores=False)
+    torch.manual_seed(5)
+    model = M.senet(512, 4).to(dev)
+
+    def store_for(ids):
+        st = M.RaggedBagStore.synthetic([sizes[i] for i in ids], c, we, device=dev, labels=[labels[i] for i in ids])
+        for kk, i in enumerate(ids):
+            synthetic.make_bag(sizes[i], labels[i], we, c, synthetic.slide_seed(77, i), device=dev, out=st.bag(kk))
+        return st
+
+    full = M.BagLoader(M.BagDataset(store_for(list(range(len(sizes))))))
+    ref_eval = M.evaluation(model, full, dev, args)
+    ref_zs = M.zs_evaluation(full, dev, args)
+
+    sh = Shard(sizes, rank, world)
+    ds = M.BagDataset(store_for(sh.ids))
+    ds.shard = sh
+    part = M.BagLoader(ds)
+    got_eval = M.evaluation(model, part, dev, args)
+    got_zs = M.zs_evaluation(part, dev, args)
+    assert got_eval == ref_eval, (rank, got_eval, ref_eval)
+    assert got_zs == ref_zs, (rank, got_zs, ref_zs)
+    import torch.distributed as dist
+    dist.barrier()
+    if rank == 0:
+        print("DIST_OK " + json.dumps({"world": world, "eval": got_eval, "shard_sizes": [len(v) for v in sh.all_ids]}))
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
