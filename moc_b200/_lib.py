@@ -9,7 +9,7 @@ import os
 import threading
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libmoc_b200.so")
+LIB_PATH = os.environ.get("MOC_B200_LIB", os.path.join(PKG, "libmoc_b200.so"))  # override: developer experiments only
 
 OK, E_ARG, E_SHAPE, E_WORKSPACE, E_CUDA = 0, -1, -2, -3, -4
 CLS_TOPK, CLS_DELTA_SOFTMAX, CLS_DELTA_DIFF, CLS_BOTTOMK, CLS_ALL = 1, 2, 4, 8, 15

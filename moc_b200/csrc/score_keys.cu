@@ -6,20 +6,29 @@
 // Roofline: HBM.  One fp32 512-vector (2048 B) is read per patch, exactly once; the outputs are 2C+3 floats.
 // Design (B200): persistent grid of one CTA per SM; every warp owns a private ring of STAGES x 8 KB shared
 // memory stages that it fills itself with 1-D bulk copies (cp.async.bulk -> UBLKCP, completion on an mbarrier),
-// so there is no CTA-wide synchronisation anywhere in the steady state and 128-192 KB are in flight per SM.
+// so there is no CTA-wide synchronisation anywhere in the steady state and ~128 KB are in flight per SM.
 // A stage holds RP=4 consecutive patches.  The 32 lanes split the 512-long dot products (16 elements each,
 // conflict-free LDS.128); with few prompt columns the lane's slice of every column lives in registers, so
-// the inner loop is pure FFMA.  Partial sums are combined with a two-level transposing butterfly (rows are
-// scattered over lane groups while they are reduced) followed by a three-level all-reduce inside each group
-// of 8 lanes, which leaves every group holding all column sums of "its" row for the per-row epilogue.
+// the inner loop is pure (two-wide) FMA.  Partial sums are combined with a two-level transposing butterfly
+// (rows are scattered over lane groups while they are reduced) followed by a three-level all-reduce inside
+// each group of 8 lanes.
+// Measured on B200 (16.4 GB, C=2): 6.2-6.3 TB/s; the same ring with no compute and no stores reads 7.45 TB/s,
+// dropping only the 28 B/patch key stores gives 6.65 TB/s (any DRAM write mixed into the read stream costs
+// ~5 %, independent of store cache policy, locality or wave size), dropping 3/4 of the FMAs gives 6.55 TB/s.
 #include "common.cuh"
 
 namespace moc {
 
 constexpr int RP = 4;                       // patches per stage
 constexpr int STAGE_BYTES = RP * ROW_BYTES; // 8 KB
-constexpr int SK_WARPS = 8;
-constexpr int SK_STAGES = 3;
+#ifndef MOC_SK_WARPS
+#define MOC_SK_WARPS 8
+#endif
+#ifndef MOC_SK_STAGES
+#define MOC_SK_STAGES 2
+#endif
+constexpr int SK_WARPS = MOC_SK_WARPS;
+constexpr int SK_STAGES = MOC_SK_STAGES;
 
 __device__ __forceinline__ float dot4(const float4& a, const float4& b, float acc) {
     acc = fmaf(a.x, b.x, acc);
@@ -73,7 +82,21 @@ struct WarpRing {
 
 // ------------------------------------------------------------------------------------------------
 // Few prompt columns (NC = C + n_bg <= 8): prompt slices in registers.
+//
+// Work unit of a warp = a super-group of 32 consecutive patches (8 stages of 4).  Per stage the lane holds
+// its 16-element slice of 4 patches; slot s of lane L holds patch (s ^ p(L)), p = 2*bit4(L) + bit3(L), so the
+// two transposing butterfly levels need no selects: a lane always keeps slots {0,1} (then {0}) and sends
+// {2,3} (then {1}).  FMAs are issued two-wide (FFMA2).  The reduced sums of a stage are parked in a per-warp
+// smem scratch; after 8 stages every lane finishes one patch (softmax, top-2, background sum/max) and the key
+// planes are written with full 128-byte stores.
 // ------------------------------------------------------------------------------------------------
+constexpr int SG_STAGES = 8;               // stages (of RP patches) per super-group
+constexpr int SG_ROWS = SG_STAGES * RP;    // 32
+
+__device__ __forceinline__ float2 ffma2(float a0, float a1, float b0, float b1, float2 c) {
+    return __ffma2_rn(make_float2(a0, a1), make_float2(b0, b1), c);
+}
+
 template <int NC, bool NORM>
 __global__ void __launch_bounds__(SK_WARPS * 32, 1)
 score_keys_regw_kernel(const float* __restrict__ feat, int64_t n_rows, const float* __restrict__ packed,
@@ -81,10 +104,13 @@ score_keys_regw_kernel(const float* __restrict__ feat, int64_t n_rows, const flo
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int NV = NC + (NORM ? 1 : 0);
+    constexpr int SLD = (NV % 2 == 0) ? NV + 1 : NV;  // odd scratch stride: conflict-free row-per-lane reads
 
     WarpRing ring;
     ring.stage0 = reinterpret_cast<float*>(smem + (size_t)warp * SK_STAGES * STAGE_BYTES);
-    ring.bars = reinterpret_cast<uint64_t*>(smem + (size_t)SK_WARPS * SK_STAGES * STAGE_BYTES) + warp * SK_STAGES;
+    unsigned char* tail = smem + (size_t)SK_WARPS * SK_STAGES * STAGE_BYTES;
+    ring.bars = reinterpret_cast<uint64_t*>(tail) + warp * SK_STAGES;
+    float* scratch = reinterpret_cast<float*>(tail + SK_WARPS * SK_STAGES * 8) + warp * (SG_ROWS * SLD);
     ring.policy = l2_policy_evict_first();
 
     if (lane == 0) {
@@ -95,13 +121,19 @@ score_keys_regw_kernel(const float* __restrict__ feat, int64_t n_rows, const flo
     }
     __syncwarp();
 
+    // groups (stages) are enumerated super-group by super-group: local index t -> group of 4 patches
     const int64_t n_groups = (n_rows + RP - 1) / RP;
-    const int64_t gstride = (int64_t)gridDim.x * SK_WARPS;
-    int64_t g = (int64_t)blockIdx.x * SK_WARPS + warp;
+    const int64_t n_sg = (n_rows + SG_ROWS - 1) / SG_ROWS;
+    const int64_t sg_stride = (int64_t)gridDim.x * SK_WARPS;
+    const int64_t sg0 = (int64_t)blockIdx.x * SK_WARPS + warp;
+    auto group_of = [&](int64_t t) -> int64_t {  // t-th stage this warp processes
+        const int64_t sg = sg0 + (t / SG_STAGES) * sg_stride;
+        return sg < n_sg ? sg * SG_STAGES + (t % SG_STAGES) : n_groups;
+    };
     if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < SK_STAGES; ++s) {
-            const int64_t gg = g + s * gstride;
+            const int64_t gg = group_of(s);
             if (gg < n_groups) ring.issue(feat, n_rows, gg, s);
         }
     }
@@ -115,59 +147,94 @@ score_keys_regw_kernel(const float* __restrict__ feat, int64_t n_rows, const flo
             w[c][q] = __ldg(reinterpret_cast<const float4*>(packed + c * D + q * 128 + lane * 4));
 
     const int C = n_classes;
+    const int perm = ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);  // slot s holds patch s ^ perm; reduced row = perm
     int stage = 0;
     uint32_t parity = 0;
-    for (; g < n_groups; g += gstride) {
+    for (int64_t t = 0;; ++t) {
+        const int64_t g = group_of(t);
+        if (g >= n_groups) break;
+        const int j = (int)(t % SG_STAGES);
         mbar_wait(&ring.bars[stage], parity);
         const float4* xs = reinterpret_cast<const float4*>(ring.stage0 + stage * (RP * D));
-        float acc[RP][NV];
+        float2 acc[RP][NV];
 #pragma unroll
         for (int r = 0; r < RP; ++r)
 #pragma unroll
-            for (int c = 0; c < NV; ++c) acc[r][c] = 0.f;
+            for (int c = 0; c < NV; ++c) acc[r][c] = make_float2(0.f, 0.f);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             float4 xv[RP];
 #pragma unroll
-            for (int r = 0; r < RP; ++r) xv[r] = xs[r * (D / 4) + q * 32 + lane];
+            for (int r = 0; r < RP; ++r) xv[r] = xs[(r ^ perm) * (D / 4) + q * 32 + lane];
 #pragma unroll
             for (int r = 0; r < RP; ++r) {
 #pragma unroll
-                for (int c = 0; c < NC; ++c) acc[r][c] = dot4(xv[r], w[c][q], acc[r][c]);
-                if (NORM) acc[r][NV - 1] = dot4(xv[r], xv[r], acc[r][NV - 1]);
+                for (int c = 0; c < NC; ++c) {
+                    acc[r][c] = ffma2(xv[r].x, xv[r].y, w[c][q].x, w[c][q].y, acc[r][c]);
+                    acc[r][c] = ffma2(xv[r].z, xv[r].w, w[c][q].z, w[c][q].w, acc[r][c]);
+                }
+                if (NORM) {
+                    acc[r][NV - 1] = ffma2(xv[r].x, xv[r].y, xv[r].x, xv[r].y, acc[r][NV - 1]);
+                    acc[r][NV - 1] = ffma2(xv[r].z, xv[r].w, xv[r].z, xv[r].w, acc[r][NV - 1]);
+                }
             }
         }
         __syncwarp();  // every lane has consumed the stage: hand it back to the copy engine
         if (lane == 0) {
-            const int64_t gn = g + (int64_t)SK_STAGES * gstride;
+            const int64_t gn = group_of(t + SK_STAGES);
             if (gn < n_groups) ring.issue(feat, n_rows, gn, stage);
         }
-
+        // select-free transposing butterfly: keep slots {0,1}, send {2,3}; then keep {0}, send {1}
         float u[NV];
-        butterfly_rows<NV>(acc, u, lane);
-        const int64_t row = g * RP + row_of_lane(lane);
-        if ((lane & 7) == 0 && row < n_rows) {
-            if (NORM) {
-                const float inv = 1.0f / fmaxf(sqrtf(u[NV - 1]), 1e-12f);
 #pragma unroll
-                for (int c = 0; c < NC; ++c) u[c] *= inv;
+        for (int c = 0; c < NV; ++c) {
+            const float a0 = acc[0][c].x + acc[0][c].y, a1 = acc[1][c].x + acc[1][c].y;
+            const float a2 = acc[2][c].x + acc[2][c].y, a3 = acc[3][c].x + acc[3][c].y;
+            const float t0 = a0 + __shfl_xor_sync(FULL, a2, 16);
+            const float t1 = a1 + __shfl_xor_sync(FULL, a3, 16);
+            float v = t0 + __shfl_xor_sync(FULL, t1, 8);
+            v += __shfl_xor_sync(FULL, v, 4);
+            v += __shfl_xor_sync(FULL, v, 2);
+            v += __shfl_xor_sync(FULL, v, 1);
+            u[c] = v;
+        }
+        if ((lane & 7) == 0) {
+            float* dst = scratch + (j * RP + perm) * SLD;
+#pragma unroll
+            for (int c = 0; c < NV; ++c) dst[c] = u[c];
+        }
+        if (++stage == SK_STAGES) { stage = 0; parity ^= 1u; }
+
+        const bool last_of_sg = (j == SG_STAGES - 1) || (g == n_groups - 1);
+        if (!last_of_sg) continue;
+        __syncwarp();
+        // one patch per lane
+        const int64_t row = (g / SG_STAGES) * SG_ROWS + lane;
+        if (row < n_rows) {
+            const float* sr = scratch + lane * SLD;
+            float v[NV];
+#pragma unroll
+            for (int c = 0; c < NV; ++c) v[c] = sr[c];
+            if (NORM) {
+                const float inv = 1.0f / fmaxf(sqrtf(v[NV - 1]), 1e-12f);
+#pragma unroll
+                for (int c = 0; c < NC; ++c) v[c] *= inv;
             }
             float m1 = -INFINITY, m2 = -INFINITY, bsum = 0.f, bmax = -INFINITY;
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
                 if (c < C) {
-                    const float v = u[c];
-                    if (v > m1) { m2 = m1; m1 = v; } else if (v > m2) { m2 = v; }
+                    if (v[c] > m1) { m2 = m1; m1 = v[c]; } else if (v[c] > m2) { m2 = v[c]; }
                 } else {
-                    bsum += u[c];
-                    bmax = fmaxf(bmax, u[c]);
+                    bsum += v[c];
+                    bmax = fmaxf(bmax, v[c]);
                 }
             }
             float e[NC];
             float esum = 0.f;
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
-                e[c] = (c < C) ? expf(u[c] - m1) : 0.f;
+                e[c] = (c < C) ? expf(v[c] - m1) : 0.f;
                 esum += e[c];
             }
             const float inv_sum = 1.0f / esum;
@@ -175,7 +242,7 @@ score_keys_regw_kernel(const float* __restrict__ feat, int64_t n_rows, const flo
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
                 if (c < C) {
-                    kp[(int64_t)c * key_stride] = u[c];
+                    kp[(int64_t)c * key_stride] = v[c];
                     kp[(int64_t)(C + c) * key_stride] = e[c] * inv_sum;
                 }
             }
@@ -183,7 +250,7 @@ score_keys_regw_kernel(const float* __restrict__ feat, int64_t n_rows, const flo
             kp[(int64_t)(2 * C + 1) * key_stride] = bsum;
             kp[(int64_t)(2 * C + 2) * key_stride] = bmax;
         }
-        if (++stage == SK_STAGES) { stage = 0; parity ^= 1u; }
+        __syncwarp();  // scratch is reused by the next super-group
     }
 }
 
@@ -342,15 +409,14 @@ __global__ void pack_prompts_kernel(const float* __restrict__ w, int C, const fl
 template <int NC, bool NORM>
 static int launch_regw(const float* feat, int64_t n_rows, const float* packed, int C, float* keys,
                        int64_t key_stride, cudaStream_t st) {
-    constexpr size_t smem = (size_t)SK_WARPS * SK_STAGES * STAGE_BYTES + SK_WARPS * SK_STAGES * 8;
-    static bool configured = false;  // per instantiation
-    if (!configured) {
-        MOC_CUDA(cudaFuncSetAttribute(score_keys_regw_kernel<NC, NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)smem));
-        configured = true;
-    }
-    const int64_t n_groups = (n_rows + RP - 1) / RP;
-    int64_t ctas = (n_groups + SK_WARPS - 1) / SK_WARPS;
+    constexpr int NV = NC + (NORM ? 1 : 0);
+    constexpr int SLD = (NV % 2 == 0) ? NV + 1 : NV;
+    constexpr size_t smem = (size_t)SK_WARPS * SK_STAGES * STAGE_BYTES + SK_WARPS * SK_STAGES * 8 +
+                            (size_t)SK_WARPS * SG_ROWS * SLD * 4;
+    MOC_CUDA(cudaFuncSetAttribute(score_keys_regw_kernel<NC, NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+    const int64_t n_sg = (n_rows + SG_ROWS - 1) / SG_ROWS;
+    int64_t ctas = (n_sg + SK_WARPS - 1) / SK_WARPS;
     if (ctas > sm_count()) ctas = sm_count();
     score_keys_regw_kernel<NC, NORM><<<(unsigned)ctas, SK_WARPS * 32, smem, st>>>(feat, n_rows, packed, C, keys,
                                                                                 key_stride);
