@@ -82,6 +82,25 @@ int moc_pack_prompts(const float* w, int n_classes, const float* w_ext, int n_ex
 int moc_score_keys(const float* feat, int64_t n_rows, const float* packed, int n_classes, int n_ext,
                    int normalize, float* keys, int64_t key_stride, void* stream);
 
+/* ---- a2 for wide prompt sets: the same contract on the tensor cores ---------
+ * With more than ~10 prompt columns (EBRAINS-30: 30 classes + 4 background)
+ * main_moc.py:336-337 is a dense contraction that CUDA-core FMAs cannot keep
+ * HBM-bound.  moc_score_keys_tc streams the patches through tcgen05.mma
+ * (FP16 x 3-product split with fp32 accumulation in TMEM: fp32-level accuracy,
+ * |x| < 65504 required) against a resident image of the prompts that
+ * moc_prepare_prompts_tc builds once from the packed matrix (no host
+ * synchronisation: the prompt scale is chosen on the device).  Works for any
+ * C_ext <= MOC_MAX_COLS; moc_score_keys (CUDA cores, prompts in registers) is
+ * the faster one for C_ext <= 8.  If a score comes out non-finite (non-finite
+ * or out-of-range input) the int at moc_prompts_tc_flag_offset() inside the
+ * image is set to 1; the caller may read it back whenever it synchronises. */
+size_t moc_prompts_tc_bytes(int n_classes, int n_ext);
+size_t moc_prompts_tc_flag_offset(int n_classes, int n_ext);
+int moc_prepare_prompts_tc(const float* packed, int n_classes, int n_ext, void* prompts_tc,
+                           size_t prompts_tc_bytes, void* stream);
+int moc_score_keys_tc(const float* feat, int64_t n_rows, const void* prompts_tc, int n_classes, int n_ext,
+                      int normalize, float* keys, int64_t key_stride, void* stream);
+
 /* ---- a3..a7: four top-J selections, union, ascending compaction -----------
  * Replaces index_{topj,delta_softmax,delta_diff,bottomk_irrel}_classifier
  * (_index.py:17-87) plus the set union / sort of main_moc.py:341-354, for

@@ -36,6 +36,10 @@ SIGNATURES = {
     "moc_packed_cols": (i32, [i32, i32]),
     "moc_pack_prompts": (i32, [p, i32, p, i32, p, p]),
     "moc_score_keys": (i32, [p, i64, p, i32, i32, i32, p, i64, p]),
+    "moc_prompts_tc_bytes": (sz, [i32, i32]),
+    "moc_prompts_tc_flag_offset": (sz, [i32, i32]),
+    "moc_prepare_prompts_tc": (i32, [p, i32, i32, p, sz, p]),
+    "moc_score_keys_tc": (i32, [p, i64, p, i32, i32, i32, p, i64, p]),
     "moc_select_capacity": (i64, [i64, i32, i32]),
     "moc_select_workspace_bytes": (sz, [i64, i32]),
     "moc_select_union": (i32, [p, i64, p, i32, i64, i32, i32, u32, p, p, p, p, p, p, sz, p]),

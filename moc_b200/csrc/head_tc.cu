@@ -11,8 +11,9 @@
 // Structure (persistent, one CTA per SM, 14 warps):
 //   warps 0-3   epilogue: tcgen05.ld the 128x64 accumulator (thread = row), +b1, ReLU, 4x64 second layer,
 //               sigmoid, gated combination with the row's key planes, stores
-//   warps 4-11  A producers: gather 128 B of 16 rows each per K-block straight from HBM/L2, split hi/lo in
-//               registers, store into the 128B-swizzled K-major smem tiles the UMMA descriptor describes
+//   warps 4-11  A producers: gather 128 B of 16 rows each per K-block straight from HBM/L2 (TC_PF K-blocks of
+//               loads in flight per thread, across tile boundaries), split hi/lo in registers, store into the
+//               128B-swizzled K-major smem tiles the UMMA descriptor describes
 //   warp 12     MMA issuer (one elected lane): 4 k-steps x 3 products of tcgen05.mma.kind::tf32 M128 N64 K8
 //   warp 13     B copier: one 16 KB bulk copy per K-block of the pre-split, pre-swizzled W1 (hi|lo)
 // Four smem stages of {A_hi 16K, A_lo 16K, B_hi 8K, B_lo 8K}; full/empty mbarriers; two TMEM accumulators so
@@ -27,6 +28,7 @@ constexpr int TC_M = 128;          // rows per tile (UMMA M)
 constexpr int TC_KB = 32;          // K elements per stage (one 128-byte swizzle row)
 constexpr int TC_NKB = D / TC_KB;  // 16 K-blocks
 constexpr int TC_STAGES = 4;
+constexpr int TC_PF = 5;            // K-block register sets each producer thread keeps in flight (5 x 16 KB per CTA; the register file of an SM sub-partition caps 4 resident warps at 128 registers)
 constexpr int TC_A_BYTES = TC_M * 128;            // 16 KB per component
 constexpr int TC_B_BYTES = TC_H * 128;            // 8 KB per component
 constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;  // 48 KB
@@ -151,54 +153,75 @@ head_rows_tc_kernel(const float* __restrict__ feat, const float* __restrict__ ke
 
     if (warp >= TC_EPI_WARPS && warp < TC_WARP_MMA) {
         // =============================== A producers ===============================================
+        // The CTA's non-empty tiles form one flat stream of (tile, K-block) steps.  A thread owns 16 bytes of 4
+        // rows in every step and keeps TC_PF steps of gather loads in flight (a ring of register sets that
+        // runs across tile boundaries): the gather is latency-bound, so bytes in flight are what buys bandwidth.
         const int pw = warp - TC_EPI_WARPS;      // 0..7 : rows 16*pw .. 16*pw+15 of the tile
         const int rsub = lane >> 3, chunk = lane & 7;
-        int stage = 0;
-        uint32_t parity = 0;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int64_t slot0 = tile * TC_M;
-            if (!tile_has_rows(sel_rows, slot0, n_slots, lane)) continue;
-            const float4* src[4];
-            int roff[4];
+        int roff[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = pw * 16 + i * 4 + rsub;
+            roff[i] = r * 128 + ((chunk ^ (r & 7)) << 4);
+        }
+        // load cursor
+        int64_t ltile = blockIdx.x;
+        int lkb = 0;
+        const float4* lsrc[4];
+        auto seek = [&]() {  // move ltile to the next tile with rows and fetch its row pointers
+            while (ltile < n_tiles && !tile_has_rows(sel_rows, ltile * TC_M, n_slots, lane)) ltile += gridDim.x;
+            if (ltile >= n_tiles) return;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int r = pw * 16 + i * 4 + rsub;
-                const int64_t s = slot0 + r;
+                const int64_t sl = ltile * TC_M + pw * 16 + i * 4 + rsub;
                 int64_t row = -1;
-                if (s < n_slots) row = sel_rows ? (int64_t)sel_rows[s] : s;
-                src[i] = row >= 0 ? reinterpret_cast<const float4*>(feat + row * D) + chunk : nullptr;
-                roff[i] = r * 128 + ((chunk ^ (r & 7)) << 4);
+                if (sl < n_slots) row = sel_rows ? (int64_t)sel_rows[sl] : sl;
+                lsrc[i] = row >= 0 ? reinterpret_cast<const float4*>(feat + row * D) + chunk : nullptr;
             }
-            float4 nxt[4];
+        };
+        auto issue = [&](float4 (&b)[4]) -> bool {  // load the cursor's step into b and advance; false when done
+            if (ltile >= n_tiles) return false;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) nxt[i] = src[i] ? __ldg(src[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int kb = 0; kb < TC_NKB; ++kb) {
-                float4 cur[4];
+            for (int i = 0; i < 4; ++i) b[i] = lsrc[i] ? __ldg(lsrc[i] + lkb * 8) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (++lkb == TC_NKB) {
+                lkb = 0;
+                ltile += gridDim.x;
+                seek();
+            }
+            return true;
+        };
+        float4 buf[TC_PF][4];
+        bool pending[TC_PF];
+        seek();
 #pragma unroll
-                for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
-                if (kb + 1 < TC_NKB) {
+        for (int s = 0; s < TC_PF; ++s) pending[s] = issue(buf[s]);
+        int stage = 0;
+        uint32_t parity = 0;
+        while (pending[0]) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        nxt[i] = src[i] ? __ldg(src[i] + (kb + 1) * 8) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int s = 0; s < TC_PF; ++s) {
+                if (pending[s]) {
+                    mbar_wait(&empty_bar[stage], parity ^ 1u);
+                    unsigned char* a_hi = smem + (size_t)stage * TC_STAGE_BYTES;
+                    unsigned char* a_lo = a_hi + TC_A_BYTES;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 cur = buf[s][i];
+                        float4 hi, lo;
+                        hi.x = __uint_as_float(__float_as_uint(cur.x) & 0xffffe000u);
+                        hi.y = __uint_as_float(__float_as_uint(cur.y) & 0xffffe000u);
+                        hi.z = __uint_as_float(__float_as_uint(cur.z) & 0xffffe000u);
+                        hi.w = __uint_as_float(__float_as_uint(cur.w) & 0xffffe000u);
+                        lo = make_float4(cur.x - hi.x, cur.y - hi.y, cur.z - hi.z, cur.w - hi.w);
+                        *reinterpret_cast<float4*>(a_hi + roff[i]) = hi;
+                        *reinterpret_cast<float4*>(a_lo + roff[i]) = lo;
+                    }
+                    fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async proxy
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&full_bar[stage]);
+                    if (++stage == TC_STAGES) { stage = 0; parity ^= 1u; }
+                    pending[s] = issue(buf[s]);
                 }
-                mbar_wait(&empty_bar[stage], parity ^ 1u);
-                unsigned char* a_hi = smem + (size_t)stage * TC_STAGE_BYTES;
-                unsigned char* a_lo = a_hi + TC_A_BYTES;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    float4 hi, lo;
-                    hi.x = __uint_as_float(__float_as_uint(cur[i].x) & 0xffffe000u);
-                    hi.y = __uint_as_float(__float_as_uint(cur[i].y) & 0xffffe000u);
-                    hi.z = __uint_as_float(__float_as_uint(cur[i].z) & 0xffffe000u);
-                    hi.w = __uint_as_float(__float_as_uint(cur[i].w) & 0xffffe000u);
-                    lo = make_float4(cur[i].x - hi.x, cur[i].y - hi.y, cur[i].z - hi.z, cur[i].w - hi.w);
-                    *reinterpret_cast<float4*>(a_hi + roff[i]) = hi;
-                    *reinterpret_cast<float4*>(a_lo + roff[i]) = lo;
-                }
-                fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async proxy
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&full_bar[stage]);
-                if (++stage == TC_STAGES) { stage = 0; parity ^= 1u; }
             }
         }
     } else if (warp == TC_WARP_B) {

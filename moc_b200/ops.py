@@ -8,6 +8,8 @@ from __future__ import annotations
 from dataclasses import dataclass
 from typing import List, Optional, Sequence
 
+import os
+
 import torch
 
 from . import _lib
@@ -20,6 +22,10 @@ def _count(n: int) -> None:
     global LAUNCHES
     LAUNCHES += n
 
+
+REGW_MAX_COLS = 8   # up to here moc_score_keys keeps the prompts in registers and is HBM-bound on CUDA cores
+# developer switch: "simt" forces the CUDA-core kernel for wide prompt sets, "tc" forces tensor cores for all
+SCORE_IMPL = os.environ.get("MOC_SCORE_IMPL", "auto")
 
 D = 512
 HIDDEN = 64
@@ -50,6 +56,8 @@ class Prompts:
     packed: torch.Tensor      # [cols_pad, 512]
     n_classes: int
     n_ext: int
+    tc: Optional[torch.Tensor] = None   # uint8 image for the tensor-core scoring kernel (wide prompt sets)
+    tc_flag: Optional[torch.Tensor] = None  # int32 [1] view into ``tc``: set when a score came out non-finite
 
     @staticmethod
     def pack(w: torch.Tensor, w_ext: torch.Tensor) -> "Prompts":
@@ -60,7 +68,20 @@ class Prompts:
         lib = _lib.load()
         packed = torch.empty(lib.moc_packed_cols(c, ce), D, device=w.device, dtype=torch.float32)
         check(lib.moc_pack_prompts(w.data_ptr(), c, w_ext.data_ptr(), ce, packed.data_ptr(), _stream()))
-        return Prompts(packed, c, ce)
+        pr = Prompts(packed, c, ce)
+        if ce > REGW_MAX_COLS or SCORE_IMPL == "tc":
+            nb = lib.moc_prompts_tc_bytes(c, ce)
+            pr.tc = torch.empty(nb, dtype=torch.uint8, device=w.device)
+            check(lib.moc_prepare_prompts_tc(packed.data_ptr(), c, ce, pr.tc.data_ptr(), nb, _stream()))
+            off = lib.moc_prompts_tc_flag_offset(c, ce)
+            pr.tc_flag = pr.tc[off:off + 4].view(torch.int32)
+        return pr
+
+    def check_finite(self) -> None:
+        """Raise if the tensor-core scoring kernel produced a non-finite score since the image was built
+        (non-finite features, or |x| >= 65504).  Synchronises; call it where the results are read anyway."""
+        if self.tc_flag is not None and int(self.tc_flag.item()) != 0:
+            raise MocError(_lib.E_ARG, "scoring produced non-finite values (non-finite features or |x| >= 65504)")
 
 
 def num_key_planes(n_classes: int) -> int:
@@ -77,8 +98,14 @@ def score_keys(feat: torch.Tensor, prompts: Prompts, normalize: bool = False,
     if out is None:
         out = torch.empty(num_key_planes(prompts.n_classes), r, device=feat.device, dtype=torch.float32)
     _count(1)
-    check(_lib.load().moc_score_keys(feat.data_ptr(), r, prompts.packed.data_ptr(), prompts.n_classes,
-                                     prompts.n_ext, int(bool(normalize)), out.data_ptr(), out.stride(0), _stream()))
+    if prompts.tc is not None and SCORE_IMPL != "simt":
+        check(_lib.load().moc_score_keys_tc(feat.data_ptr(), r, prompts.tc.data_ptr(), prompts.n_classes,
+                                            prompts.n_ext, int(bool(normalize)), out.data_ptr(), out.stride(0),
+                                            _stream()))
+    else:
+        check(_lib.load().moc_score_keys(feat.data_ptr(), r, prompts.packed.data_ptr(), prompts.n_classes,
+                                         prompts.n_ext, int(bool(normalize)), out.data_ptr(), out.stride(0),
+                                         _stream()))
     return out
 
 

@@ -64,6 +64,47 @@ def test_score_keys_shapes(n_rows, c, n_ext):
     close(keys.cpu().numpy(), oracle_keys(x, w, we, c), rtol=1e-3, atol=2e-6)
 
 
+@pytest.mark.parametrize("impl", ["tc", "simt"])
+@pytest.mark.parametrize("n_rows", [1, 127, 128, 129, 4099, 60001])
+@pytest.mark.parametrize("c,n_ext", [(2, 6), (12, 16), (20, 33), (30, 34), (59, 64)])
+def test_score_keys_both_impls(monkeypatch, impl, n_rows, c, n_ext):
+    """The tensor-core (tcgen05, FP16 x3 split) and CUDA-core scoring kernels compute the same fp32-level keys;
+    60001 rows = several 128-patch tiles per CTA, a ragged last tile and the cross-tile load ring."""
+    from moc_b200 import ops
+    monkeypatch.setattr(ops, "SCORE_IMPL", impl)
+    gen = torch.Generator().manual_seed(n_rows * 7 + n_ext)
+    x = torch.randn(n_rows, 512, generator=gen)
+    x = x / x.norm(dim=1, keepdim=True) * (0.25 + 4 * torch.rand(n_rows, 1, generator=gen))  # norms 0.25 .. 4.25
+    wa = torch.randn(n_ext, 512, generator=gen)
+    wa = wa / wa.norm(dim=1, keepdim=True)
+    w, we = wa[:c].t().contiguous(), wa.t().contiguous()
+    pr = ops.Prompts.pack(w.to(DEV), we.to(DEV))
+    assert (pr.tc is not None) == (impl == "tc" or n_ext > 8)
+    keys = ops.score_keys(x.to(DEV), pr).cpu().numpy()
+    close(keys, oracle_keys(x, w, we, c), rtol=1e-3, atol=2e-6)
+    exact = (x.double() @ w.double()).numpy().T  # fp32-level accuracy of the raw similarities
+    assert np.abs(keys[:c] - exact).max() < 4e-6
+    pr.check_finite()
+
+
+def test_score_keys_tc_flags_nonfinite():
+    """Out-of-range / non-finite features give non-finite scores (as they do in the reference) and raise the flag."""
+    from moc_b200 import ops
+    from moc_b200._lib import MocError
+    gen = torch.Generator().manual_seed(3)
+    wa = torch.randn(34, 512, generator=gen)
+    wa = wa / wa.norm(dim=1, keepdim=True)
+    pr = ops.Prompts.pack(wa[:30].t().contiguous().to(DEV), wa.t().contiguous().to(DEV))
+    x = torch.randn(300, 512, generator=gen)
+    ops.score_keys(x.to(DEV), pr)
+    pr.check_finite()
+    x[17, 5] = float("inf")
+    keys = ops.score_keys(x.to(DEV), pr)
+    assert not torch.isfinite(keys[:30, 17]).all() and torch.isfinite(keys[:, :17]).all()
+    with pytest.raises(MocError):
+        pr.check_finite()
+
+
 def test_score_keys_normalize_flag():
     """normalize=1 == scoring F.normalize(x) (models/model_adapters.py:188); off by default as in MOC."""
     from moc_b200 import ops

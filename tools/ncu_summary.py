@@ -64,7 +64,9 @@ if __name__ == "__main__":
     os.makedirs(out_dir, exist_ok=True)
     go = os.path.join(ROOT, "gpurun_out")
     lines = []
-    lp = os.path.join(go, "launches.csv")
+    lp = os.path.join(go, tag + "_launches.csv")
+    if not os.path.exists(lp):
+        lp = os.path.join(go, "launches.csv")
     if os.path.exists(lp):
         order, agg = launches(lp)
         tot = sum(sum(v) / len(v) for v in agg.values())
