@@ -4,9 +4,12 @@
 // sort of main_moc.py:341-354, Tensor.topk in the selectors' return values, and topj_pooling /
 // delta_*_classifier_pooling (utils/patch_selection_classifier.py:18-78) for the zero-shot path.
 //
-// Selection is an exact radix select on the order-preserving uint32 image of the fp32 keys: four 8-bit
-// passes find the value of rank J, rows strictly beyond it are taken, and ties at the threshold are taken
-// in ascending row order until exactly J rows are chosen (torch leaves tie order unspecified).  The union of
+// Selection is an exact radix select on the order-preserving uint32 image of the fp32 keys: the value of rank
+// J is found digit by digit, rows strictly beyond it are taken, and ties at the threshold are taken in
+// ascending row order until exactly J rows are chosen (torch leaves tie order unspecified).  The batched
+// selection kernel scans a column three times with 16-byte loads (range, a 4096-bin histogram of the occupied
+// range, then marking + on-chip resolution of the threshold bin; see select_rows_fast).  The generic four-pass
+// version serves the stand-alone top-J / pooling kernels and degenerate columns.  The union of
 // the 2C+2 selections of a slide is a bitmap over its rows, so the ascending order of the reference's
 // sorted(set(...)) falls out of the compaction for free and nothing ever goes back to the host.
 #include "common.cuh"
@@ -147,6 +150,186 @@ __device__ void select_rows(const float* __restrict__ v, int64_t ld, const uint8
     }
 }
 
+// ---- fast path of the batched selection: 12-bit first digit + in-shared-memory candidates -----------------------
+constexpr int FS_BITS = 12;
+constexpr int FS_BINS = 1 << FS_BITS;       // 4096
+constexpr int FS_CAND = 4096;               // candidates (keys inside the threshold bin) kept on chip
+constexpr int FS_TIES = 512;                // threshold-value ties resolved on chip
+struct FastShared {
+    unsigned int hist[FS_BINS];
+    uint2 cand[FS_CAND];                    // (ordered key, row)
+};
+
+// f(i, u) for every kept key of a contiguous column; 16-byte loads, two in flight per thread.
+template <bool SMALLEST, bool HAS_MASK, typename F>
+__device__ __forceinline__ void scan_column(const float* __restrict__ v, const uint8_t* __restrict__ mk, int n, F f) {
+    const int tid = threadIdx.x;
+    auto visit = [&](int i, float x) {
+        if (HAS_MASK && !mk[i]) return;
+        f(i, sel_key<SMALLEST>(x));
+    };
+    int head = (4 - (int)((reinterpret_cast<uintptr_t>(v) >> 2) & 3)) & 3;
+    if (head > n) head = n;
+    if (tid < head) visit(tid, v[tid]);
+    const int n4 = (n - head) >> 2;
+    const float4* v4 = reinterpret_cast<const float4*>(v + head);
+    int k = tid;
+    for (; k + SEL_THREADS < n4; k += 2 * SEL_THREADS) {
+        const float4 a = __ldg(v4 + k), b = __ldg(v4 + k + SEL_THREADS);
+        const int ia = head + 4 * k, ib = ia + 4 * SEL_THREADS;
+        visit(ia, a.x); visit(ia + 1, a.y); visit(ia + 2, a.z); visit(ia + 3, a.w);
+        visit(ib, b.x); visit(ib + 1, b.y); visit(ib + 2, b.z); visit(ib + 3, b.w);
+    }
+    if (k < n4) {
+        const float4 a = __ldg(v4 + k);
+        const int ia = head + 4 * k;
+        visit(ia, a.x); visit(ia + 1, a.y); visit(ia + 2, a.z); visit(ia + 3, a.w);
+    }
+    const int t0 = head + 4 * n4;
+    if (t0 + tid < n) visit(t0 + tid, v[t0 + tid]);
+}
+
+// Block-wide: the bin (counting from the top) where the running count reaches `need`.  Leaves sh.prefix = bin,
+// sh.need = rank inside the bin, sh.n_equal = population of the bin.  NB a multiple of SEL_THREADS.
+template <int NB>
+__device__ void find_bin_desc(const unsigned int* hist, unsigned int need, SelShared& sh) {
+    constexpr int PER = NB / SEL_THREADS;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned int loc[PER], s = 0;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        loc[k] = hist[NB - 1 - (tid * PER + k)];
+        s += loc[k];
+    }
+    unsigned int incl = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int t = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) sh.warp_tot[warp] = incl;
+    __syncthreads();
+    unsigned int before = 0;
+    for (int w = 0; w < warp; ++w) before += sh.warp_tot[w];
+    incl += before;
+    unsigned int run = incl - s;
+    if (run < need && need <= incl) {
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            if (run < need && need <= run + loc[k]) {
+                sh.prefix = (unsigned int)(NB - 1 - (tid * PER + k));
+                sh.need = need - run;
+                sh.n_equal = loc[k];
+            }
+            run += loc[k];
+        }
+    }
+    __syncthreads();
+}
+
+// Marks exactly the j selected rows of a contiguous column (1 <= j < kept rows).
+//   scan 1: min / max of the ordered keys;
+//   scan 2: FS_BINS-bin histogram of (u - min) >> shift, the shift chosen so the occupied range fills the bins
+//           (narrow-range columns such as a 2-class softmax spread out instead of piling into a few bins) -
+//           repeated on the threshold bin's own sub-range while that bin still holds more than FS_CAND keys;
+//   scan 3: rows above the threshold bin are marked, the keys inside it are parked in shared memory, where
+//           the remaining <= 20 bits are resolved with 10-bit digits and ties go to the lowest row indices.
+// Returns false (block-uniform) for columns too degenerate for the on-chip lists (e.g. thousands of equal keys
+// at the threshold); the caller then runs the generic path, which is correct on its own (marking is idempotent).
+template <bool SMALLEST, bool HAS_MASK, typename Emit>
+__device__ bool select_rows_fast(const float* __restrict__ v, const uint8_t* __restrict__ mk, int n, int j,
+                                 SelShared& sh, FastShared& fs, Emit emit) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // ---- scan 1: range of the kept keys
+    uint32_t lo = 0xffffffffu, hi = 0u;
+    scan_column<SMALLEST, HAS_MASK>(v, mk, n, [&](int, uint32_t u) { lo = min(lo, u); hi = max(hi, u); });
+    lo = __reduce_min_sync(FULL, lo);
+    hi = __reduce_max_sync(FULL, hi);
+    if (lane == 0) { fs.hist[warp] = lo; fs.hist[SEL_WARPS + warp] = hi; }
+    __syncthreads();
+    for (int w = 0; w < SEL_WARPS; ++w) { lo = min(lo, fs.hist[w]); hi = max(hi, fs.hist[SEL_WARPS + w]); }
+    __syncthreads();
+    // ---- scan 2 (repeated while the threshold bin is over-full): histogram of the interval [base, base + 2^bits)
+    uint32_t base = lo;
+    int bits = 32 - __clz(hi - lo);            // keys satisfy u - base < 2^bits   (bits == 0: all keys equal)
+    unsigned int need = (unsigned int)j;
+    int shift;
+    uint32_t bin0;
+    unsigned int n_cand;
+    for (int level = 0;; ++level) {
+        shift = bits > FS_BITS ? bits - FS_BITS : 0;
+        for (int b = tid; b < FS_BINS; b += SEL_THREADS) fs.hist[b] = 0;
+        __syncthreads();
+        const uint32_t span_m1 = bits >= 32 ? 0xffffffffu : ((1u << bits) - 1u);
+        scan_column<SMALLEST, HAS_MASK>(v, mk, n, [&](int, uint32_t u) {
+            const uint32_t rel = u - base;
+            if (u >= base && rel <= span_m1) atomicAdd(&fs.hist[rel >> shift], 1u);
+        });
+        __syncthreads();
+        find_bin_desc<FS_BINS>(fs.hist, need, sh);
+        bin0 = sh.prefix;
+        n_cand = sh.n_equal;
+        need = sh.need;
+        __syncthreads();
+        if (n_cand <= (unsigned int)FS_CAND) break;
+        if (shift == 0 || level == 2) return false;   // thousands of identical keys at the threshold
+        base += bin0 << shift;
+        bits = shift;
+    }
+    // ---- scan 3: mark above the threshold bin, park the bin's keys on chip
+    const uint32_t cand_lo = base + (bin0 << shift);                  // first key value of the threshold bin
+    const uint32_t cand_span_m1 = shift == 0 ? 0u : ((1u << shift) - 1u);
+    if (tid == 0) sh.taken = 0;
+    __syncthreads();
+    scan_column<SMALLEST, HAS_MASK>(v, mk, n, [&](int i, uint32_t u) {
+        if (u < cand_lo) return;
+        const uint32_t rel = u - cand_lo;
+        if (rel > cand_span_m1) emit(i);
+        else fs.cand[atomicAdd(&sh.taken, 1u)] = make_uint2(rel, (unsigned int)i);
+    });
+    __syncthreads();
+    if (need == n_cand) {
+        for (unsigned int c = tid; c < n_cand; c += SEL_THREADS) emit((int)fs.cand[c].y);
+        return true;
+    }
+    // ---- the remaining `shift` (<= 20) bits of the candidates, 10 at a time
+    uint32_t prefix = 0, known = 0;
+#pragma unroll 1
+    for (int sh10 = 10; sh10 >= 0; sh10 -= 10) {
+        for (int b = tid; b < 1024; b += SEL_THREADS) fs.hist[b] = 0;
+        __syncthreads();
+        for (unsigned int c = tid; c < n_cand; c += SEL_THREADS) {
+            const uint32_t u = fs.cand[c].x;
+            if ((u & known) == prefix) atomicAdd(&fs.hist[(u >> sh10) & 1023u], 1u);
+        }
+        __syncthreads();
+        find_bin_desc<1024>(fs.hist, need, sh);
+        prefix |= sh.prefix << sh10;
+        known |= 1023u << sh10;
+        need = sh.need;
+        const unsigned int n_eq = sh.n_equal;
+        __syncthreads();
+        if (sh10 == 0) {
+            if (need != n_eq && n_eq > (unsigned int)FS_TIES) return false;
+            for (unsigned int c = tid; c < n_cand; c += SEL_THREADS) {
+                const uint2 e = fs.cand[c];
+                if (e.x > prefix) {
+                    emit((int)e.y);
+                } else if (e.x == prefix) {
+                    bool take = need == n_eq;
+                    if (!take) {  // more rows at the threshold value than needed: lowest row indices first
+                        unsigned int before = 0;
+                        for (unsigned int d = 0; d < n_cand; ++d) before += (fs.cand[d].x == prefix && fs.cand[d].y < e.y);
+                        take = before < need;
+                    }
+                    if (take) emit((int)e.y);
+                }
+            }
+        }
+    }
+    return true;
+}
+
 template <bool HAS_MASK>
 __device__ int count_kept(const uint8_t* __restrict__ mk, int n, SelShared& sh) {
     if (!HAS_MASK) return n;
@@ -166,6 +349,8 @@ __global__ void __launch_bounds__(SEL_THREADS)
 select_mark_kernel(const float* __restrict__ keys, int64_t key_stride, const int64_t* __restrict__ offsets, int C,
                    int topj, unsigned discard_mask, const uint8_t* __restrict__ row_mask,
                    unsigned int* __restrict__ bitmap) {
+    extern __shared__ __align__(16) unsigned char sel_dyn_smem[];
+    FastShared& fs = *reinterpret_cast<FastShared*>(sel_dyn_smem);
     __shared__ SelShared sh;
     const int q = blockIdx.y, slide = blockIdx.x;
     unsigned cls;
@@ -187,6 +372,12 @@ select_mark_kernel(const float* __restrict__ keys, int64_t key_stride, const int
         const int64_t r = row0 + i;
         atomicOr(&bitmap[r >> 5], 1u << (r & 31));
     };
+    if (j > 0 && j < n_kept) {
+        const bool done = smallest ? select_rows_fast<true, HAS_MASK>(v, mk, n, j, sh, fs, mark)
+                                   : select_rows_fast<false, HAS_MASK>(v, mk, n, j, sh, fs, mark);
+        if (done) return;
+        __syncthreads();
+    }
     if (smallest) select_rows<true, HAS_MASK>(v, 1, mk, n, n_kept, j, sh, mark);
     else select_rows<false, HAS_MASK>(v, 1, mk, n, n_kept, j, sh, mark);
 }
@@ -429,14 +620,18 @@ extern "C" int moc_select_union(const float* keys, int64_t key_stride, const int
     unsigned int* bitmap = reinterpret_cast<unsigned int*>(workspace);
     MOC_CUDA(cudaMemsetAsync(bitmap, 0, need, st));
     const dim3 grid(n_slides, 2 * n_classes + 2);
+    MOC_CUDA(cudaFuncSetAttribute(select_mark_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)sizeof(FastShared)));
+    MOC_CUDA(cudaFuncSetAttribute(select_mark_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)sizeof(FastShared)));
     if (row_mask) {
-        select_mark_kernel<true><<<grid, SEL_THREADS, 0, st>>>(keys, key_stride, offsets, n_classes, topj, discard_mask,
+        select_mark_kernel<true><<<grid, SEL_THREADS, sizeof(FastShared), st>>>(keys, key_stride, offsets, n_classes, topj, discard_mask,
                                                               row_mask, bitmap);
         MOC_LAUNCH_CHECK("select_mark_kernel");
         compact_kernel<true><<<n_slides, CMP_THREADS, 0, st>>>(bitmap, offsets, row_mask, sel_base, sel_rows, sel_local,
                                                              sel_count);
     } else {
-        select_mark_kernel<false><<<grid, SEL_THREADS, 0, st>>>(keys, key_stride, offsets, n_classes, topj,
+        select_mark_kernel<false><<<grid, SEL_THREADS, sizeof(FastShared), st>>>(keys, key_stride, offsets, n_classes, topj,
                                                                discard_mask, nullptr, bitmap);
         MOC_LAUNCH_CHECK("select_mark_kernel");
         compact_kernel<false><<<n_slides, CMP_THREADS, 0, st>>>(bitmap, offsets, nullptr, sel_base, sel_rows, sel_local,

@@ -156,6 +156,66 @@ def test_select_union_golden(golden, name):
                 assert got.tolist() == ref.tolist()
 
 
+def _ref_union(keys, offs, c, j, mask=None):
+    """Top-j per selection plane with ties broken towards lower row indices; union per slide, ascending."""
+    out = []
+    for i in range(len(offs) - 1):
+        lo, hi = offs[i], offs[i + 1]
+        keep = np.ones(hi - lo, bool) if mask is None else mask[lo:hi].astype(bool)
+        idx = np.nonzero(keep)[0]
+        jj = min(j, idx.size)
+        sel = set()
+        for plane in list(range(2 * c + 1)) + [2 * c + 1]:
+            v = keys[plane, lo:hi][idx].astype(np.float64)
+            order = np.lexsort((idx, v if plane == 2 * c + 1 else -v))
+            sel |= set(idx[order[:jj]].tolist())
+        out.append(sorted(sel))
+    return out
+
+
+@pytest.mark.parametrize("kind", ["normal", "quantised", "constant", "two_values", "tiny_range"])
+@pytest.mark.parametrize("masked", [False, True])
+def test_select_union_ties_and_degenerate_columns(kind, masked):
+    """Exact set semantics on crafted key planes: heavy ties at the rank-J value, constant columns (every key in one
+    histogram bin: the generic fallback), ragged unaligned slides from 1 row to 70 000 rows, with and without the
+    training row mask."""
+    from moc_b200 import ops
+    c, j = 2, 400
+    sizes = [1, 5, 399, 400, 401, 1003, 4096, 5001, 70000, 33]
+    offs = [0]
+    for n in sizes:
+        offs.append(offs[-1] + n)
+    total = offs[-1]
+    rng = np.random.default_rng(hash(kind) % 1000 + masked)
+    keys = rng.standard_normal((2 * c + 3, total)).astype(np.float32)
+    if kind == "quantised":
+        keys = np.round(keys, 1)
+    elif kind == "constant":
+        keys[:] = 0.25
+    elif kind == "two_values":
+        keys = np.where(keys > 1.5, np.float32(1.0), np.float32(-1.0)).astype(np.float32)
+    elif kind == "tiny_range":
+        keys = (1.0 + keys * 1e-6).astype(np.float32)
+    mask = (rng.random(total) > 0.5) if masked else None
+    kd = torch.from_numpy(keys).to(DEV)
+    md = torch.from_numpy(mask).to(DEV) if masked else None
+    offs_d = torch.tensor(offs, dtype=torch.int64, device=DEV)
+    sel = ops.select_union(kd, offs_d, offs, c, j, 0, md)
+    cnt = sel.sel_count.cpu().tolist()
+    rows = sel.sel_rows.cpu().numpy()
+    local = sel.sel_local.cpu().numpy()
+    ref = _ref_union(keys, offs, c, j, mask)
+    for i in range(len(sizes)):
+        b = sel.sel_base_h[i]
+        got = (rows[b:b + cnt[i]] - offs[i]).tolist()
+        assert got == ref[i], "slide %d (n=%d): %d vs %d rows" % (i, sizes[i], len(got), len(ref[i]))
+        if masked:
+            keep_idx = np.nonzero(mask[offs[i]:offs[i + 1]])[0]
+            assert local[b:b + cnt[i]].tolist() == np.searchsorted(keep_idx, got).tolist()
+        else:
+            assert local[b:b + cnt[i]].tolist() == got
+
+
 @pytest.mark.parametrize("name", SLIDE_CASES)
 def test_topj_sorted_golden(golden, name):
     """The selectors' public return value: sorted top-J indices per column."""
