@@ -34,8 +34,20 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
-N_CLASSES, TOPJ, TOPK = 2, 400, 10
-WORKLOAD = "NSCLC 16-shot eval split: 1000 synthetic slides x 20000 CONCH-shaped patches (C=2, C_ext=6, J=400, K=10)"
+TOPJ, TOPK = 400, 10
+# BASELINE.json configs: [1] is the one the metric is quoted on (the default); the others are the parity-test
+# shapes, benchable with --workload for the tables in DESIGN.md / profiles/.
+WORKLOADS = {
+    "cfg2": dict(n_classes=2, slides=1000, patches=20000,
+                 desc="NSCLC 16-shot eval split: %d synthetic slides x %d CONCH-shaped patches (C=2, C_ext=6, J=400, K=10)"),
+    "cfg3": dict(n_classes=3, slides=1000, patches=20000,
+                 desc="RCC 3-class eval split: %d synthetic slides x %d patches (C=3, C_ext=7, J=400, K=10)"),
+    "cfg4": dict(n_classes=30, slides=400, patches=50000,
+                 desc="EBRAINS-30 eval shard: %d synthetic slides x %d patches (C=30, C_ext=34, J=400, K=10)"),
+    "cfg5": dict(n_classes=2, slides=1000, patches=None,
+                 desc="throughput sweep: %d synthetic slides, bag sizes log-uniform in [1000, 100000] patches%s "
+                      "(C=2, C_ext=6, J=400, K=10)"),
+}
 
 
 def parse():
@@ -44,14 +56,27 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--slides", type=int, default=1000, help="slides per GPU")
-    ap.add_argument("--patches", type=int, default=20000)
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--slides", type=int, default=None, help="slides per GPU (default: the workload's)")
+    ap.add_argument("--patches", type=int, default=None, help="patches per slide (default: the workload's)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--e2e-host-slides", type=int, default=128, help="distinct slides kept in pinned host memory")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    return ap.parse_args()
+    a = ap.parse_args()
+    wl = WORKLOADS[a.workload]
+    a.n_classes = wl["n_classes"]
+    a.slides = a.slides or wl["slides"]
+    if a.workload == "cfg5" and a.patches is None:
+        from moc_b200 import synthetic
+        a.sizes = synthetic.log_uniform_sizes(a.slides)
+        a.desc = wl["desc"] % (a.slides, "")
+    else:
+        a.patches = a.patches or wl["patches"] or 20000
+        a.sizes = [a.patches] * a.slides
+        a.desc = wl["desc"] % ((a.slides, a.patches) if a.workload != "cfg5" else (a.slides, " (fixed %d)" % a.patches))
+    return a
 
 
 def measured_peak():
@@ -64,13 +89,14 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic_bytes(rows_per_launch):
+def ncu_traffic_bytes(kernel, rows_per_launch):
     """dram bytes per launch of the streaming kernel from the committed ncu capture, scaled per row."""
     p = os.path.join(ROOT, "profiles", "score_keys_traffic.json")
     if not os.path.exists(p):
         return None
     try:
         d = json.load(open(p))
+        d = d.get("kernels", {}).get(kernel.split("<")[0]) if "kernels" in d else d
         return float(d["dram_bytes_per_row"]) * rows_per_launch
     except Exception:
         return None
@@ -132,21 +158,29 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_pass(n_slides, n_patches, seconds, threads):
+def sample_sizes(sizes, n):
+    """A bounded sample of the workload's bags for the host-core runs: n sizes spread over the sorted list."""
+    srt = sorted(sizes)
+    if len(srt) <= n:
+        return srt
+    return [srt[(2 * i + 1) * len(srt) // (2 * n)] for i in range(n)]
+
+
+def cpu_reference_pass(n_classes, sizes, seconds, threads):
     """The oracle port of the reference's evaluation() on host cores: returns (slides/s, slides timed, passes)."""
     from moc_b200 import synthetic
     from oracle import moc_oracle as O
     torch.set_num_threads(threads)
-    w, we = synthetic.prompt_matrices(N_CLASSES)
-    bags, labels = synthetic.make_cohort(n_slides, n_patches, N_CLASSES, cohort_seed=99)
+    w, we = synthetic.prompt_matrices(n_classes)
+    bags, labels = synthetic.make_cohort(len(sizes), sizes, n_classes, cohort_seed=99)
     prm = O.SenetParams.init(0)
     with torch.no_grad():
         for x in bags[:2]:  # warm-up
-            O.slide_eval_logits(prm, x, w, we, N_CLASSES, TOPJ, TOPK)
+            O.slide_eval_logits(prm, x, w, we, n_classes, TOPJ, TOPK)
         done, passes, t0 = 0, 0, time.perf_counter()
         while True:
             for x, y in zip(bags, labels):
-                lg = O.slide_eval_logits(prm, x, w, we, N_CLASSES, TOPJ, TOPK)
+                lg = O.slide_eval_logits(prm, x, w, we, n_classes, TOPJ, TOPK)
                 float(O.cross_entropy(lg, y))
                 done += 1
             passes += 1
@@ -162,7 +196,9 @@ def run_reference(a):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    n_slides = 32
+    sizes = sample_sizes(a.sizes, 32)
+    n_slides = len(sizes)
+    N_CLASSES = a.n_classes
     per_step = []
     total = a.steps + a.warmup
     budget = max(1.0, min(150.0, 150.0) / max(total, 1))
@@ -170,8 +206,9 @@ def run_reference(a):
     from oracle import moc_oracle as O
     torch.set_num_threads(threads)
     w, we = synthetic.prompt_matrices(N_CLASSES)
-    bags, labels = synthetic.make_cohort(n_slides, a.patches, N_CLASSES, cohort_seed=99)
+    bags, labels = synthetic.make_cohort(n_slides, sizes, N_CLASSES, cohort_seed=99)
     prm = O.SenetParams.init(0)
+    mean_patches = sum(a.sizes) / len(a.sizes)
 
     def step():
         t0 = time.perf_counter()
@@ -195,14 +232,14 @@ def run_reference(a):
         t_tot += dt
         per_step.append(dt / n)
     value = n_tot / t_tot
-    sample = "%d distinct slides x %d patches in host RAM, looped; %d slides timed over %d steps" % (
-        n_slides, a.patches, n_tot, a.steps)
+    sample = "%d distinct slides (%d..%d patches, spread over the workload's sizes) in host RAM, looped; %d slides " \
+             "timed over %d steps" % (n_slides, min(sizes), max(sizes), n_tot, a.steps)
     line = {
         "impl": "reference", "metric": "slides_per_sec", "value": value, "unit": "slides/s", "n_gpus": a.gpus,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * t_tot / max(a.steps, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "reference algorithm (oracle port) on host cores; bounded sample"},
-        "patches_per_sec": value * a.patches,
+        "config": {"workload": a.desc, "note": "reference algorithm (oracle port) on host cores; bounded sample"},
+        "patches_per_sec": value * mean_patches,
         "cpu_baseline": {"value": value, "unit": "slides/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "slides/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -225,8 +262,10 @@ def run_ours(a):
     if world != a.gpus and rank == 0:
         print("warning: --gpus %d but WORLD_SIZE=%d" % (a.gpus, world), file=sys.stderr)
 
+    N_CLASSES = a.n_classes
     w, we = synthetic.prompt_matrices(N_CLASSES, device=dev)
-    store = RaggedBagStore.synthetic([a.patches] * a.slides, N_CLASSES, we, cohort_seed=1000 + rank, device=dev)
+    store = RaggedBagStore.synthetic(a.sizes, N_CLASSES, we, cohort_seed=1000 + rank, device=dev)
+    rows_per_gpu = store.total_rows
     eng = MocEngine(w, we, TOPJ, TOPK)
     g = torch.Generator().manual_seed(0)
     prm = ops.HeadParams(((torch.rand(64, 512, generator=g) * 2 - 1) * 512 ** -0.5).to(dev),
@@ -276,8 +315,9 @@ def run_ours(a):
     avg_ms = sum(score_ms) / len(score_ms)
     rows_per_launch = sum(score_rows) / len(score_rows)
     achieved = rows_per_launch * 2048 / (avg_ms * 1e-3) / 1e9
-    traffic = ncu_traffic_bytes(rows_per_launch)
-    roofline = {"bound": "hbm", "kernel": "score_keys_regw_kernel<6>", "achieved": achieved, "peak": peak,
+    kernel = "score_keys_regw_kernel<%d>" % (N_CLASSES + 4) if eng.prompts.tc is None else "score_keys_tc_kernel"
+    traffic = ncu_traffic_bytes(kernel, rows_per_launch)
+    roofline = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": rows_per_launch * 2048, "avg_launch_ms": avg_ms,
                 "launches_timed": len(score_ms), "share_of_step": avg_ms * len(score_ms) / a.steps / ms_step,
@@ -287,20 +327,23 @@ def run_ours(a):
     e2e = None
     if not a.no_e2e:
         n_host = min(a.e2e_host_slides, a.slides)
+        while n_host > 1 and store.offsets_h[n_host] > 2_621_440:  # keep the pinned pool within ~5.4 GB
+            n_host -= 1
         per_chunk = 32
         chunks = []
         for lo in range(0, n_host, per_chunk):
-            n = min(per_chunk, n_host - lo)
-            pinned = torch.empty(n * a.patches, 512, dtype=torch.float32, pin_memory=True)
-            pinned.copy_(store.feat[lo * a.patches:(lo + n) * a.patches])
-            chunks.append(HostChunk(pinned, [i * a.patches for i in range(n + 1)], store.labels_h[lo:lo + n], dev))
+            hi = min(lo + per_chunk, n_host)
+            r0, r1 = store.offsets_h[lo], store.offsets_h[hi]
+            pinned = torch.empty(r1 - r0, 512, dtype=torch.float32, pin_memory=True)
+            pinned.copy_(store.feat[r0:r1])
+            chunks.append(HostChunk(pinned, [v - r0 for v in store.offsets_h[lo:hi + 1]], store.labels_h[lo:hi], dev))
         seq, k = [], 0
         remaining = a.slides
         while remaining > 0:  # the step's cohort: cycle through the pinned chunks until every slide is covered
             ch = chunks[k % len(chunks)]
             n = len(ch.labels_h)
             if n > remaining:
-                ch = HostChunk(ch.feat[:remaining * a.patches], ch.offsets_h[:remaining + 1], ch.labels_h[:remaining], dev)
+                ch = HostChunk(ch.feat[:ch.offsets_h[remaining]], ch.offsets_h[:remaining + 1], ch.labels_h[:remaining], dev)
             seq.append(ch)
             remaining -= len(ch.labels_h)
             k += 1
@@ -334,24 +377,27 @@ def run_ours(a):
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        v, done, passes, dt = cpu_reference_pass(32, a.patches, a.cpu_seconds, threads)
+        ss = sample_sizes(a.sizes, 32)
+        v, done, passes, dt = cpu_reference_pass(N_CLASSES, ss, a.cpu_seconds, threads)
         cpu = {"value": v, "unit": "slides/s", "cores": threads, "kind": "port",
-               "sample": "32 distinct slides x %d patches in host RAM, looped %d times (%d slides, %.1f s); "
-                         "oracle port of evaluation(), torch fp32" % (a.patches, passes, done, dt)}
+               "sample": "%d distinct slides (%d..%d patches) in host RAM, looped %d times (%d slides, %.1f s); "
+                         "oracle port of evaluation(), torch fp32" % (len(ss), min(ss), max(ss), passes, done, dt)}
 
     if rank == 0:
         line = {
             "metric": "slides_per_sec", "value": value, "unit": "slides/s", "n_gpus": world, "steps": a.steps,
             "warmup": max(a.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "slides_per_gpu": a.slides, "patches_per_slide": a.patches,
+            "config": {"workload": a.desc, "slides_per_gpu": a.slides,
+                       "patches_per_slide": a.patches if a.patches else "log-uniform 1000..100000 (mean %.0f)"
+                                            % (rows_per_gpu / a.slides),
                        "n_classes": N_CLASSES, "n_ext": N_CLASSES + 4, "topj": TOPJ, "topk": TOPK,
                        "step": "one evaluation pass over every slide: score + select + gate/combine + pool + CE",
                        "l2": "inputs are %.1f GB per GPU, far larger than the 126 MB L2: no flush needed"
                              % (store.nbytes() / 1e9),
                        "sharding": "slides sharded over GPUs, logits all-gathered per step" if world > 1 else "single GPU"},
-            "patches_per_sec": value * a.patches,
-            "algorithmic_GBps_whole_step": slides_total * a.patches * 2048 / (ms_step * 1e-3) / 1e9,
+            "patches_per_sec": rows_per_gpu * world / (ms_step * 1e-3),
+            "algorithmic_GBps_whole_step": rows_per_gpu * world * 2048 / (ms_step * 1e-3) / 1e9,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
             "clocks": sampler.summary(),
         }

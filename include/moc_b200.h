@@ -73,6 +73,18 @@ int moc_packed_cols(int n_classes, int n_ext);
 int moc_pack_prompts(const float* w, int n_classes, const float* w_ext, int n_ext,
                      float* packed, void* stream);
 
+/* A prompt BANK (several prompt embeddings per class: classnames x templates)
+ * collapses to one unit column per class exactly as the reference does it
+ * offline (utils/zeroshot_utils.py:29-50): every prompt row is L2-normalised,
+ * the rows of a class are averaged, the mean is divided by its norm.
+ * bank [n_prompts][512] row-major; class c owns rows class_offsets[c] ..
+ * class_offsets[c+1]-1 (device int32 [n_classes+1]); w_out [512][n_classes]
+ * row-major, i.e. directly usable as zeroshot_weights(_ext).  Scoring against
+ * the collapsed column equals the mean of the per-prompt scores up to that
+ * one scale, so a bank of any size costs nothing on the streaming path. */
+int moc_collapse_prompt_bank(const float* bank, const int32_t* class_offsets, int n_classes, float* w_out,
+                             void* stream);
+
 /* ---- a2 + selection keys: the streaming kernel ----------------------------
  * Replaces `feat @ zeroshot_weights`, `feat @ zeroshot_weights_ext`
  * (main_moc.py:336-337) and the per-row arithmetic of the four selectors

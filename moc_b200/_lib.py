@@ -35,6 +35,7 @@ SIGNATURES = {
     "moc_num_key_planes": (i32, [i32]),
     "moc_packed_cols": (i32, [i32, i32]),
     "moc_pack_prompts": (i32, [p, i32, p, i32, p, p]),
+    "moc_collapse_prompt_bank": (i32, [p, p, i32, p, p]),
     "moc_score_keys": (i32, [p, i64, p, i32, i32, i32, p, i64, p]),
     "moc_prompts_tc_bytes": (sz, [i32, i32]),
     "moc_prompts_tc_flag_offset": (sz, [i32, i32]),

@@ -406,6 +406,36 @@ __global__ void pack_prompts_kernel(const float* __restrict__ w, int C, const fl
     }
 }
 
+// One block per class: column c of W = normalise( mean_p normalise(bank[p]) ) over the class's prompt rows
+// (utils/zeroshot_utils.py:38-44).  Thread k owns embedding component k; norms are block reductions.
+__global__ void __launch_bounds__(D) collapse_bank_kernel(const float* __restrict__ bank, const int32_t* __restrict__ class_offsets,
+                                                         int n_classes, float* __restrict__ w_out) {
+    __shared__ float red[D / 32];
+    __shared__ float total;
+    const int c = blockIdx.x, k = threadIdx.x, lane = k & 31, warp = k >> 5;
+    auto block_norm = [&](float v) -> float {
+        float s = warp_sum(v * v);
+        __syncthreads();
+        if (lane == 0) red[warp] = s;
+        __syncthreads();
+        if (k == 0) {
+            float t = 0.f;
+            for (int w = 0; w < D / 32; ++w) t += red[w];
+            total = sqrtf(t);
+        }
+        __syncthreads();
+        return total;
+    };
+    const int p0 = class_offsets[c], p1 = class_offsets[c + 1];
+    float acc = 0.f;
+    for (int p = p0; p < p1; ++p) {
+        const float v = bank[(size_t)p * D + k];
+        acc += v / fmaxf(block_norm(v), 1e-12f);   // F.normalize(x, dim=-1): x / max(||x||, eps)
+    }
+    const float m = acc / (float)(p1 - p0);
+    w_out[(size_t)k * n_classes + c] = m / block_norm(m);
+}
+
 template <int NC, bool NORM>
 static int launch_regw(const float* feat, int64_t n_rows, const float* packed, int C, float* keys,
                        int64_t key_stride, cudaStream_t st) {
@@ -468,6 +498,15 @@ extern "C" int moc_pack_prompts(const float* w, int n_classes, const float* w_ex
     pack_prompts_kernel<<<(pad * D + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, n_classes, w_ext, n_ext, pad,
                                                                                 packed);
     MOC_LAUNCH_CHECK("pack_prompts_kernel");
+    return MOC_OK;
+}
+
+extern "C" int moc_collapse_prompt_bank(const float* bank, const int32_t* class_offsets, int n_classes, float* w_out,
+                                        void* stream) {
+    MOC_CHECK_ARG(bank && class_offsets && w_out, "moc_collapse_prompt_bank: null pointer");
+    MOC_CHECK_SHAPE(n_classes >= 1 && n_classes <= MOC_MAX_COLS, "moc_collapse_prompt_bank: bad class count %d", n_classes);
+    collapse_bank_kernel<<<n_classes, D, 0, (cudaStream_t)stream>>>(bank, class_offsets, n_classes, w_out);
+    MOC_LAUNCH_CHECK("collapse_bank_kernel");
     return MOC_OK;
 }
 

@@ -84,6 +84,23 @@ class Prompts:
             raise MocError(_lib.E_ARG, "scoring produced non-finite values (non-finite features or |x| >= 65504)")
 
 
+def collapse_prompt_bank(bank: torch.Tensor, prompts_per_class: Sequence[int]) -> torch.Tensor:
+    """[n_prompts,512] prompt embeddings (class after class) -> zero-shot classifier matrix [512,C] with unit
+    columns, as utils/zeroshot_utils.py:29-50 builds it (normalise rows, mean per class, normalise)."""
+    bank = _dev_f32(bank, "bank")
+    counts = [int(c) for c in prompts_per_class]
+    if bank.dim() != 2 or bank.size(1) != D or sum(counts) != bank.size(0) or min(counts, default=0) < 1:
+        raise MocError(_lib.E_SHAPE, "bank must be [sum(prompts_per_class),512] with at least one prompt per class")
+    offs = [0]
+    for c in counts:
+        offs.append(offs[-1] + c)
+    offs_d = torch.tensor(offs, dtype=torch.int32, device=bank.device)
+    out = torch.empty(D, len(counts), dtype=torch.float32, device=bank.device)
+    _count(1)
+    check(_lib.load().moc_collapse_prompt_bank(bank.data_ptr(), offs_d.data_ptr(), len(counts), out.data_ptr(), _stream()))
+    return out
+
+
 def num_key_planes(n_classes: int) -> int:
     return 2 * n_classes + 3
 

@@ -29,6 +29,7 @@ from typing import Dict, Iterable, List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
+import torch.nn.functional as F
 
 TEMPERATURE_CONCH = 56.3477  # main_moc.py:175, :443, :505
 CLASSIFIERS = ("topk", "delta_softmax", "delta_diff", "bottomk")  # main_moc.py:39
@@ -37,6 +38,18 @@ CLASSIFIERS = ("topk", "delta_softmax", "delta_diff", "bottomk")  # main_moc.py:
 # --------------------------------------------------------------------------
 # a2: scoring                                            main_moc.py:336-337
 # --------------------------------------------------------------------------
+def collapse_prompt_bank(bank: torch.Tensor, prompts_per_class: Sequence[int]) -> torch.Tensor:
+    """utils/zeroshot_utils.py:29-50 from the text embeddings on: per class F.normalize every prompt embedding
+    (:38), mean over classnames and templates (:43), divide by the norm (:44), stack as columns (:50)."""
+    cols, p0 = [], 0
+    for n in prompts_per_class:
+        e = F.normalize(bank[p0:p0 + n].float(), dim=-1)
+        m = e.mean(dim=0)
+        cols.append(m / m.norm())
+        p0 += n
+    return torch.stack(cols, dim=1)
+
+
 def score(feat: torch.Tensor, w: torch.Tensor, w_ext: torch.Tensor):
     """``L = feat @ W`` [N,C] and ``Le = feat @ W_ext`` [N,C_ext]; no normalisation."""
     return feat @ w, feat @ w_ext

@@ -422,3 +422,23 @@ def test_tensor_core_head_matches_cuda_core_head():
     subprocess.run([sys.executable, "-c", code, out], check=True, env=dict(os.environ, MOC_HEAD_IMPL="simt"), timeout=120)
     g_simt = torch.load(out)
     assert (g_tc - g_simt).abs().max().item() < 2e-6
+
+
+@pytest.mark.parametrize("name", ["bank_rcc_ext", "bank_stress"])
+def test_collapse_prompt_bank_golden(golden, name):
+    """A prompt bank (cfg3: >= 64 prompts per class) collapses to the reference's classifier matrix, and scoring
+    against the collapsed column is the (rescaled) mean of the per-prompt scores."""
+    from moc_b200 import ops
+    g = golden(name)
+    bank = T(g["bank"]).float()
+    counts = g["prompts_per_class"].tolist()
+    w = ops.collapse_prompt_bank(bank.to(DEV), counts).cpu()
+    close(w, g["W"], rtol=1e-5, atol=1e-7)
+    close(w, O.collapse_prompt_bank(bank, counts), rtol=1e-5, atol=1e-7)
+    x = torch.randn(64, 512, generator=torch.Generator().manual_seed(1))
+    p0 = 0
+    for c, n in enumerate(counts):
+        e = torch.nn.functional.normalize(bank[p0:p0 + n], dim=-1)
+        mean_score = (x @ e.t()).mean(dim=1)
+        close((x @ w[:, c]) * e.mean(dim=0).norm(), mean_score, rtol=1e-4, atol=1e-5)
+        p0 += n

@@ -141,3 +141,12 @@ def test_senet_init_matches_linear_default():
     assert p.w1.shape == (64, 512) and p.b1.shape == (64,) and p.w2.shape == (4, 64) and p.b2.shape == (4,)
     assert float(p.w1.abs().max()) <= 1 / np.sqrt(512) and float(p.w2.abs().max()) <= 1 / 8
     assert sum(t.numel() for t in p.tensors()) == 33092
+
+
+@pytest.mark.parametrize("name", ["bank_rcc_ext", "bank_stress"])
+def test_prompt_bank_collapse(golden, name):
+    """zero_shot_classifier (utils/zeroshot_utils.py:20-51) run on a stand-in text tower vs the oracle's restatement."""
+    g = golden(name)
+    w = O.collapse_prompt_bank(T(g["bank"]).float(), g["prompts_per_class"].tolist())
+    assert torch.equal(w, T(g["W"]))
+    assert torch.allclose(w.norm(dim=0), torch.ones(w.size(1)), atol=1e-6)
