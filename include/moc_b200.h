@@ -203,6 +203,51 @@ int moc_senet_backward(const float* x, int64_t n_rows, const float* dgate, const
                        const float* w2, const float* b2, float* grads, void* workspace, size_t workspace_bytes,
                        void* stream);
 
+/* ---- dense per-patch layers of the secondary MIL heads (tensor cores) -------
+ * y[n][m] = act( sum_k x[n][k] * w[m][k] + bias[m] ) for every patch n: one
+ * nn.Linear (+ activation) applied to a whole bag, the building block of
+ * Conch_CLIP_Ada.adapter (models/model_adapters.py:152-157), CLAM_SB / ABMIL
+ * (models/model_clam.py:83-91, :41-64) and MIL_fc (models/model_mil.py:17-23).
+ * w is nn.Linear.weight, [n_out][k] row-major; k a multiple of 32; bias may be
+ * null.  Columns < split use act0, the others act1 (two layers that share
+ * their input, e.g. the tanh and sigmoid branches of the gated attention,
+ * run as one call on stacked weights).  tcgen05 3xTF32: ~1e-5 relative. */
+#define MOC_ACT_NONE 0
+#define MOC_ACT_RELU 1
+#define MOC_ACT_TANH 2
+#define MOC_ACT_SIGMOID 3
+size_t moc_linear_workspace_bytes(int n_out, int k);
+int moc_linear_forward(const float* x, int64_t ldx, int64_t n_rows, int k, const float* w, const float* bias,
+                       int n_out, int act0, int split, int act1, float* y, int64_t ldy, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
+/* Conch_CLIP_Ada after its adapter MLP (models/model_adapters.py:186-190): f =
+ * adapted * clip_ratio + x * (1 - clip_ratio), f /= |f|, logits = f @ classifier
+ * ([512][C] row-major).  adapted == NULL gives forward_disable_ada (:211-214):
+ * normalise, score.  logits are written as planes logits[c * ld + n] so that
+ * moc_pool_topk finishes the per-class top-j mean (:173-183). */
+int moc_adapter_scores(const float* x, const float* adapted, float clip_ratio, const float* classifier,
+                       int n_classes, int64_t n_rows, float* logits, int64_t ld, void* stream);
+
+/* Attn_Net_Gated (models/model_clam.py:59-62) after the two branch layers:
+ * a_raw[n] = sum_d ab[n][d] * ab[n][hidden + d] * wc[d] + bc, ab = [tanh branch |
+ * sigmoid branch] as one moc_linear_forward on stacked weights writes it. */
+int moc_gated_attention_scores(const float* ab, int64_t ld, int hidden, const float* wc, float bc, int64_t n_rows,
+                               float* a_raw, void* stream);
+
+/* CLAM_SB.forward_single (models/model_clam.py:181, :209-212): softmax of a_raw
+ * over the bag, pooled = softmax(a_raw) h, logits = w_cls pooled + b_cls
+ * (w_cls [C][width] row-major), probs = softmax(logits), y_hat = argmax.
+ * pooled / probs / y_hat may be null.  Deterministic two-stage reduction. */
+size_t moc_attention_pool_workspace_bytes(int64_t n_rows, int width);
+int moc_attention_pool(const float* a_raw, const float* h, int64_t ldh, int width, int64_t n_rows,
+                       const float* w_cls, const float* b_cls, int n_classes, float* pooled, float* logits,
+                       float* probs, int32_t* y_hat, void* workspace, size_t workspace_bytes, void* stream);
+
+/* per-row softmax of [n_rows][n_cols] logits (MIL_fc, models/model_mil.py:38) */
+int moc_row_softmax(const float* logits, int64_t ld, int n_cols, int64_t n_rows, float* probs, int64_t ldp,
+                    void* stream);
+
 /* ---- a12: loss, backward, optimiser ----------------------------------------
  * cross_entropy on [n,C] rows without temperature (main_moc.py:406,:494):
  * loss[i], optional dlogits[i,:] = grad_scale * (softmax - onehot), optional pred[i]. */

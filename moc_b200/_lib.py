@@ -52,6 +52,13 @@ SIGNATURES = {
     "moc_head_forward": (i32, [p, p, i64, i32, p, p, p, i32, i64, p, p, p, p, u32, i32, p, p, p, p, p, sz, p]),
     "moc_ablation_forward": (i32, [p, i64, i32, p, p, p, i32, i64, i32, i32, p, p, p]),
     "moc_pool_topk": (i32, [p, i64, p, i32, i32, i32, i32, i32, i32, i32, i32, p, p]),
+    "moc_linear_workspace_bytes": (sz, [i32, i32]),
+    "moc_linear_forward": (i32, [p, i64, i64, i32, p, p, i32, i32, i32, i32, p, i64, p, sz, p]),
+    "moc_adapter_scores": (i32, [p, p, f32, p, i32, i64, p, i64, p]),
+    "moc_gated_attention_scores": (i32, [p, i64, i32, p, f32, i64, p, p]),
+    "moc_attention_pool_workspace_bytes": (sz, [i64, i32]),
+    "moc_attention_pool": (i32, [p, p, i64, i32, i64, p, p, i32, p, p, p, p, p, sz, p]),
+    "moc_row_softmax": (i32, [p, i64, i32, i64, p, i64, p]),
     "moc_cross_entropy": (i32, [p, p, i32, i32, f32, p, p, p, p]),
     "moc_head_backward_workspace_bytes": (sz, [i32, i32, i32]),
     "moc_head_backward": (i32, [p, p, i64, i32, p, p, p, i32, p, p, p, p, u32, i32, p, p, p, p, sz, p]),

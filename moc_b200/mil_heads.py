@@ -1,0 +1,181 @@
+"""The secondary MIL heads north_star names next to MOC proper, with the reference's module surface.
+
+None of them is instantiated by a shipped driver of the reference, so they are built
+forward-only: parameters live in ordinary ``nn.Linear`` containers under the reference's attribute names (their
+``state_dict``s interchange), ``forward`` runs every dense layer on the tensor cores (``ops.linear``: tcgen05
+3xTF32) and everything else in our row kernels, under ``torch.no_grad``.  Training these heads (their backward)
+is not implemented - MOC itself trains only ``senet``.
+
+* ``Conch_CLIP_Ada``  models/model_adapters.py:148-215 - adapter MLP, residual blend, normalise, score, top-j mean
+* ``CLAM_SB``         models/model_clam.py:77-219 with ``instance_loss_fn=None`` (= ABMIL): gated attention pooling
+* ``MIL_fc``          models/model_mil.py:11-51 - max-probability instance
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+from ._lib import MocError, E_ARG, E_SHAPE
+
+
+def _pool_topj_planes(planes: torch.Tensor, topj: int) -> torch.Tensor:
+    """[C,N] planes -> [1,C]: mean of the min(topj, N) largest per class (Conch_CLIP_Ada.topj_pooling)."""
+    c, n = planes.shape
+    offs = torch.tensor([0, n], dtype=torch.int64, device=planes.device)
+    return ops.pool_topk(planes, offs, 1, c, int(topj), 0, 1, 0, 1, False)
+
+
+class Conch_CLIP_Ada(nn.Module):
+    def __init__(self, c_in=512, reduction=4, num_classes=2, classifier_tensor=None, clip_ratio=0.1, topj=10):
+        super().__init__()
+        if c_in != ops.D:
+            raise ValueError("this build of moc_b200 implements c_in=512 (CONCH embeddings) only")
+        self.adapter = nn.Sequential(
+            nn.Linear(c_in, c_in // reduction, bias=False),
+            nn.ReLU(inplace=True),
+            nn.Linear(c_in // reduction, c_in, bias=False),
+            nn.ReLU(inplace=True),
+        )
+        self.topj = topj
+        nn.init.kaiming_normal_(self.adapter[0].weight, a=np.sqrt(5))
+        nn.init.kaiming_normal_(self.adapter[2].weight, a=np.sqrt(5))
+        self.classifier = classifier_tensor
+        self.num_classes = num_classes
+        self.clip_ratio = clip_ratio
+
+    def topj_pooling(self, logits, topj=10):
+        """logits [N,C] -> [1,C] (models/model_adapters.py:173-183)."""
+        with torch.no_grad():
+            return _pool_topj_planes(logits.t().contiguous().float(), topj)
+
+    @torch.no_grad()
+    def forward(self, feat):
+        a1 = ops.linear(feat, self.adapter[0].weight, None, "relu")
+        a2 = ops.linear(a1, self.adapter[2].weight, None, "relu")
+        planes = ops.adapter_scores(feat, a2, self.clip_ratio, self.classifier)
+        return _pool_topj_planes(planes, self.topj)
+
+    @torch.no_grad()
+    def forward_disable_ada(self, feat):
+        planes = ops.adapter_scores(feat, None, 0.0, self.classifier)
+        return _pool_topj_planes(planes, self.topj)
+
+
+class Attn_Net_Gated(nn.Module):
+    """Parameter container with the reference's names (models/model_clam.py:41-64)."""
+
+    def __init__(self, L=1024, D=256, dropout=False, n_classes=1):
+        super().__init__()
+        a, b = [nn.Linear(L, D), nn.Tanh()], [nn.Linear(L, D), nn.Sigmoid()]
+        if dropout:
+            a.append(nn.Dropout(0.25))
+            b.append(nn.Dropout(0.25))
+        self.attention_a = nn.Sequential(*a)
+        self.attention_b = nn.Sequential(*b)
+        self.attention_c = nn.Linear(D, n_classes)
+
+    @torch.no_grad()
+    def forward(self, x):
+        d = self.attention_a[0].out_features
+        if self.attention_c.out_features != 1:
+            raise MocError(E_SHAPE, "Attn_Net_Gated: only the single-branch attention (n_classes=1) is implemented")
+        w = torch.cat([self.attention_a[0].weight, self.attention_b[0].weight], dim=0)
+        b = torch.cat([self.attention_a[0].bias, self.attention_b[0].bias], dim=0)
+        ab = ops.linear(x, w, b, "tanh", split=d, act_tail="sigmoid")
+        a_raw = ops.gated_attention_scores(ab, d, self.attention_c.weight, float(self.attention_c.bias))
+        return a_raw.unsqueeze(1), x
+
+
+class CLAM_SB(nn.Module):
+    def __init__(self, gate=True, size_arg="small", dropout=False, k_sample=8, n_classes=2,
+                 instance_loss_fn=None, subtyping=False, conch_init=False, conch_freeze=False):
+        super().__init__()
+        self.size_dict = {"small": [1024, 512, 256], "big": [1024, 512, 384], "benchmark": [384, 512, 256],
+                          "conch": [512, 512, 384], "gigapath": [1536, 512, 256], "virchow": [2560, 512, 256]}
+        if not gate:
+            raise ValueError("moc_b200.CLAM_SB implements the gated attention network (gate=True) only")
+        if conch_init:
+            raise ValueError("conch_init loads a checkpoint from the authors' home directory; load a state_dict instead")
+        size = self.size_dict[size_arg]
+        fc = [nn.Linear(size[0], size[1]), nn.ReLU()]
+        if dropout:
+            fc.append(nn.Dropout(0.25))
+        fc.append(Attn_Net_Gated(L=size[1], D=size[2], dropout=dropout, n_classes=1))
+        self.attention_net = nn.Sequential(*fc)
+        self.classifiers = nn.Linear(size[1], n_classes)
+        self.instance_classifiers = nn.ModuleList([nn.Linear(size[1], 2) for _ in range(n_classes)])
+        self.k_sample = k_sample
+        self.instance_loss_fn = instance_loss_fn
+        self.n_classes = n_classes
+        self.subtyping = subtyping
+        for m in self.modules():  # utils/utils.py:399-403
+            if isinstance(m, nn.Linear):
+                nn.init.xavier_normal_(m.weight)
+                m.bias.data.zero_()
+
+    def relocate(self):
+        self.to(torch.device("cuda"))
+
+    @torch.no_grad()
+    def forward_single(self, h, label=None, instance_eval=False, return_features=False, attention_only=False):
+        if instance_eval:
+            raise MocError(E_ARG, "instance-level clustering (instance_eval=True) is outside the ABMIL path built here")
+        if self.training and any(isinstance(m, nn.Dropout) for m in self.modules()):
+            raise MocError(E_ARG, "dropout in training mode is not implemented (forward-only head): call .eval()")
+        fc = self.attention_net[0]
+        hh = ops.linear(h, fc.weight, fc.bias, "relu")
+        a_raw, _ = self.attention_net[-1](hh)
+        a_row = a_raw.t()
+        if attention_only:
+            return a_row
+        pooled, logits, probs, yhat = ops.attention_pool(a_raw.reshape(-1), hh, self.classifiers.weight,
+                                                         self.classifiers.bias)
+        results = {}
+        if return_features:
+            results["features"] = pooled
+        return logits, probs, yhat.to(torch.int64).view(1, 1), a_row, results
+
+    def forward(self, h, label=None, instance_eval=False, return_features=False, attention_only=False):
+        if h.dim() == 3:
+            outs = [self.forward_single(h[i], None, instance_eval, return_features, attention_only)
+                    for i in range(h.shape[0])]
+            if attention_only:
+                return torch.stack(outs, dim=0)
+            return tuple(torch.stack([o[k] for o in outs], dim=0) for k in range(4)) + ([o[4] for o in outs],)
+        return self.forward_single(h, label, instance_eval, return_features, attention_only)
+
+
+class MIL_fc(nn.Module):
+    def __init__(self, gate=True, size_arg="benchmark", dropout=False, n_classes=2, top_k=1):
+        super().__init__()
+        assert n_classes == 2
+        self.size_dict = {"small": [1024, 512], "benchmark": [384, 512]}
+        size = self.size_dict[size_arg]
+        fc = [nn.Linear(size[0], size[1]), nn.ReLU()]
+        if dropout:
+            fc.append(nn.Dropout(0.25))
+        fc.append(nn.Linear(size[1], n_classes))
+        self.classifier = nn.Sequential(*fc)
+        self.top_k = top_k
+
+    def relocate(self):
+        self.classifier.to(torch.device("cuda"))
+
+    @torch.no_grad()
+    def forward(self, h, return_features=False):
+        if self.top_k != 1:
+            raise MocError(E_ARG, "MIL_fc: the reference's .view(1,) admits top_k=1 only (models/model_mil.py:40)")
+        l0, l1 = self.classifier[0], self.classifier[-1]
+        hid = ops.linear(h, l0.weight, l0.bias, "relu")
+        logits = ops.linear(hid, l1.weight, l1.bias, None).contiguous()
+        y_probs = ops.row_softmax(logits)
+        top_idx = ops.topj_sorted(y_probs[:, 1], 1, largest=True).view(1,)
+        top_instance = ops.take_rows(logits, top_idx, logits.size(1))
+        y_prob = ops.row_softmax(top_instance)
+        y_hat = ops.topj_sorted(top_instance.t().contiguous(), 1, largest=True).view(1, 1)
+        results = {}
+        if return_features:
+            results["features"] = ops.take_rows(hid, top_idx, hid.size(1))
+        return top_instance, y_prob, y_hat, y_probs, results

@@ -394,3 +394,93 @@ def ablation_pool(keys: torch.Tensor, n_classes: int, sel: Selection, how: str, 
                                            sel.capacity, _ABLATION_MODES[how], int(topk), final.data_ptr(),
                                            bag.data_ptr(), _stream()))
     return bag
+
+
+# ---------------------------------------------------------------------------------------------
+# dense layers and row-wise pieces of the secondary MIL heads (moc_b200.mil_heads)
+ACT = {None: 0, "none": 0, "relu": 1, "tanh": 2, "sigmoid": 3}
+
+
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, act: Optional[str] = None,
+           split: Optional[int] = None, act_tail: Optional[str] = None) -> torch.Tensor:
+    """act(x @ weight.T + bias) for a whole bag on the tensor cores (tcgen05 3xTF32).  Columns >= split use act_tail."""
+    x = _dev_f32(x, "x")
+    w = _dev_f32(weight, "weight")
+    if x.dim() != 2 or w.dim() != 2 or x.size(1) != w.size(1):
+        raise MocError(_lib.E_SHAPE, "linear: x [N,K] and weight [M,K] expected, got %s and %s" % (tuple(x.shape), tuple(w.shape)))
+    n, k = x.shape
+    m = w.size(0)
+    b = _dev_f32(bias, "bias") if bias is not None else None
+    ldy = (m + 3) & ~3
+    y = torch.empty(n, ldy, dtype=torch.float32, device=x.device)
+    lib = _lib.load()
+    ws_bytes = lib.moc_linear_workspace_bytes(m, k)
+    if ws_bytes == 0:
+        raise MocError(_lib.E_SHAPE, "linear: in_features must be a multiple of 32, got %d" % k)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+    sp = m if split is None else int(split)
+    _count(2)
+    check(lib.moc_linear_forward(x.data_ptr(), x.stride(0), n, k, w.data_ptr(), _ptr(b), m, ACT[act], sp,
+                                 ACT[act_tail if split is not None else act], y.data_ptr(), ldy, ws.data_ptr(), ws_bytes,
+                                 _stream()))
+    return y[:, :m]
+
+
+def adapter_scores(x: torch.Tensor, adapted: Optional[torch.Tensor], clip_ratio: float, classifier: torch.Tensor
+                   ) -> torch.Tensor:
+    """Planes [C,N] of normalise(adapted * ratio + x * (1 - ratio)) @ classifier ([512,C]); adapted=None: normalise(x)."""
+    x = _dev_f32(x, "x")
+    cl = _dev_f32(classifier, "classifier")
+    if x.dim() != 2 or x.size(1) != D or cl.dim() != 2 or cl.size(0) != D:
+        raise MocError(_lib.E_SHAPE, "adapter_scores: x [N,512] and classifier [512,C] expected")
+    a = None
+    if adapted is not None:
+        a = _dev_f32(adapted, "adapted")
+        if a.shape != x.shape:
+            raise MocError(_lib.E_SHAPE, "adapter_scores: adapted must have the shape of x")
+    n, c = x.size(0), cl.size(1)
+    out = torch.empty(c, max(n, 1), dtype=torch.float32, device=x.device)
+    _count(1)
+    check(_lib.load().moc_adapter_scores(x.data_ptr(), _ptr(a), float(clip_ratio), cl.data_ptr(), c, n, out.data_ptr(),
+                                         out.stride(0), _stream()))
+    return out[:, :n]
+
+
+def gated_attention_scores(ab: torch.Tensor, hidden: int, wc: torch.Tensor, bc: float) -> torch.Tensor:
+    """a_raw [N] from the stacked [tanh | sigmoid] branch activations ab [N, 2*hidden]."""
+    n = ab.size(0)
+    out = torch.empty(max(n, 1), dtype=torch.float32, device=ab.device)
+    wc = _dev_f32(wc, "wc").reshape(-1)
+    _count(1)
+    check(_lib.load().moc_gated_attention_scores(ab.data_ptr(), ab.stride(0), int(hidden), wc.data_ptr(), float(bc), n,
+                                                 out.data_ptr(), _stream()))
+    return out[:n]
+
+
+def attention_pool(a_raw: torch.Tensor, h: torch.Tensor, w_cls: torch.Tensor, b_cls: Optional[torch.Tensor]):
+    """(pooled [1,L], logits [1,C], probs [1,C], y_hat int32 [1]) of softmax(a_raw) @ h through the bag classifier."""
+    n, width = h.shape
+    w_cls = _dev_f32(w_cls, "w_cls")
+    c = w_cls.size(0)
+    dev = h.device
+    pooled = torch.empty(1, width, dtype=torch.float32, device=dev)
+    logits = torch.empty(1, c, dtype=torch.float32, device=dev)
+    probs = torch.empty(1, c, dtype=torch.float32, device=dev)
+    yhat = torch.empty(1, dtype=torch.int32, device=dev)
+    lib = _lib.load()
+    ws_bytes = lib.moc_attention_pool_workspace_bytes(n, width)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    b = _dev_f32(b_cls, "b_cls") if b_cls is not None else None
+    _count(2)
+    check(lib.moc_attention_pool(a_raw.data_ptr(), h.data_ptr(), h.stride(0), width, n, w_cls.data_ptr(), _ptr(b), c,
+                                 pooled.data_ptr(), logits.data_ptr(), probs.data_ptr(), yhat.data_ptr(), ws.data_ptr(),
+                                 ws_bytes, _stream()))
+    return pooled, logits, probs, yhat
+
+
+def row_softmax(logits: torch.Tensor) -> torch.Tensor:
+    n, c = logits.shape
+    out = torch.empty(n, c, dtype=torch.float32, device=logits.device)
+    _count(1)
+    check(_lib.load().moc_row_softmax(logits.data_ptr(), logits.stride(0), c, n, out.data_ptr(), c, _stream()))
+    return out

@@ -1,0 +1,129 @@
+"""Golden vectors for the secondary MIL heads from the reference's own modules  --  TEST INFRASTRUCTURE.
+
+    python oracle/make_golden_heads.py         (build container only: needs /root/reference)
+
+Imports models/model_adapters.py, models/model_clam.py and models/model_mil.py UNMODIFIED from the read-only
+checkout (with empty stand-ins for the absent third-party imports they make at module level: openslide, the CONCH
+model factory, nystrom_attention), instantiates Conch_CLIP_Ada, CLAM_SB (instance_loss_fn=None = ABMIL) and MIL_fc
+with seeded initialisation, runs their forward on seeded bags and stores inputs, parameters and outputs in
+tests/golden/heads_*.npz.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+from moc_b200 import synthetic  # noqa: E402
+from oracle import ref_loader  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def import_reference_models():
+    ref = ref_loader.REFERENCE_ROOT
+    for name in ("openslide", "nystrom_attention"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["nystrom_attention"].NystromAttention = object
+    sys.path.insert(0, ref)
+    stub = types.ModuleType("models.model_conch")
+    stub.conch_coca = stub.conch_lora = lambda *a, **k: None
+    import importlib
+    models = importlib.import_module("models")
+    sys.modules["models.model_conch"] = stub
+    models.model_conch = stub
+    clam = importlib.import_module("models.model_clam")
+    mil = importlib.import_module("models.model_mil")
+    ada = importlib.import_module("models.model_adapters")
+    return clam, mil, ada
+
+
+def sd_np(sd, prefix):
+    """Parameters were rounded to fp16-representable values before the reference ran (fp16_exact), so storing
+    them as fp16 loses nothing and halves the fixtures."""
+    return {prefix + k: v.detach().half().numpy().copy() for k, v in sd.items()}
+
+
+def fp16_exact(module):
+    with torch.no_grad():
+        for p_ in module.parameters():
+            p_.copy_(p_.half().float())
+
+
+def main():
+    assert ref_loader.available()
+    torch.set_num_threads(1)
+    clam, mil, ada = import_reference_models()
+    out_all = {}
+
+    # ---- Conch_CLIP_Ada (C = 2 and 3), bags of 37 / 700 patches (N < topj and N > topj), un-normalised inputs
+    for c, sizes, topj, seed in ((2, [37, 700], 50, 31), (3, [300], 10, 32)):
+        w, _ = synthetic.prompt_matrices(c)
+        torch.manual_seed(seed)
+        m = ada.Conch_CLIP_Ada(c_in=512, reduction=4, num_classes=c, classifier_tensor=w, clip_ratio=0.1, topj=topj).eval()
+        fp16_exact(m)
+        out = {"C": c, "topj": topj, "clip_ratio": 0.1, "classifier": w.numpy(), "n_bags": len(sizes)}
+        out.update(sd_np(m.state_dict(), "sd_"))
+        bags, _ = synthetic.make_cohort(len(sizes), sizes, c, cohort_seed=seed)
+        g = torch.Generator().manual_seed(seed)
+        with torch.no_grad():
+            for i, x in enumerate(bags):
+                x = (x * (0.5 + 2.0 * torch.rand(x.size(0), 1, generator=g))).half().float()
+                out["feat_%d" % i] = x.half().numpy()
+                out["forward_%d" % i] = m.forward(x).numpy()
+                out["forward_disable_ada_%d" % i] = m.forward_disable_ada(x).numpy()
+        np.savez_compressed(os.path.join(OUT, "heads_clip_ada_c%d.npz" % c), **out)
+        print("wrote heads_clip_ada_c%d" % c)
+
+    # ---- ABMIL = CLAM_SB(size_arg="conch", instance_loss_fn=None)
+    for c, sizes, seed in ((2, [65, 900], 41), (3, [513], 42)):
+        torch.manual_seed(seed)
+        m = clam.CLAM_SB(gate=True, size_arg="conch", dropout=False, n_classes=c, instance_loss_fn=None).eval()
+        # initialize_weights zeroes every bias; give them values so the bias paths are exercised
+        with torch.no_grad():
+            for p_ in m.parameters():
+                if p_.dim() == 1:
+                    p_.copy_(0.05 * torch.randn(p_.shape))
+        fp16_exact(m)
+        out = {"C": c, "n_bags": len(sizes)}
+        out.update(sd_np(m.state_dict(), "sd_"))
+        bags, _ = synthetic.make_cohort(len(sizes), sizes, c, cohort_seed=seed)
+        with torch.no_grad():
+            for i, x in enumerate(bags):
+                x = (x * 4.0).half().float()
+                out["feat_%d" % i] = x.half().numpy()
+                logits, y_prob, y_hat, a_raw, res = m(x, return_features=True)
+                out["logits_%d" % i], out["y_prob_%d" % i] = logits.numpy(), y_prob.numpy()
+                out["y_hat_%d" % i], out["a_raw_%d" % i] = y_hat.numpy(), a_raw.numpy()
+                out["features_%d" % i] = res["features"].numpy()
+                out["attention_only_%d" % i] = m(x, attention_only=True).numpy()
+        np.savez_compressed(os.path.join(OUT, "heads_abmil_c%d.npz" % c), **out)
+        print("wrote heads_abmil_c%d" % c)
+
+    # ---- MIL_fc (384-d "benchmark" inputs, 2 classes)
+    torch.manual_seed(51)
+    m = mil.MIL_fc(size_arg="benchmark", dropout=False, n_classes=2, top_k=1).eval()
+    fp16_exact(m)
+    out = {"n_bags": 2}
+    out.update(sd_np(m.state_dict(), "sd_"))
+    g = torch.Generator().manual_seed(52)
+    with torch.no_grad():
+        for i, n in enumerate((40, 777)):
+            x = torch.randn(n, 384, generator=g).half().float()
+            out["feat_%d" % i] = x.half().numpy()
+            top, y_prob, y_hat, y_probs, _ = m(x)
+            out["top_instance_%d" % i], out["y_prob_%d" % i] = top.numpy(), y_prob.numpy()
+            out["y_hat_%d" % i], out["y_probs_%d" % i] = y_hat.numpy(), y_probs.numpy()
+    np.savez_compressed(os.path.join(OUT, "heads_mil_fc.npz"), **out)
+    print("wrote heads_mil_fc")
+
+
+if __name__ == "__main__":
+    main()

@@ -150,3 +150,41 @@ def test_prompt_bank_collapse(golden, name):
     w = O.collapse_prompt_bank(T(g["bank"]).float(), g["prompts_per_class"].tolist())
     assert torch.equal(w, T(g["W"]))
     assert torch.allclose(w.norm(dim=0), torch.ones(w.size(1)), atol=1e-6)
+
+
+# ---- secondary MIL heads: oracle restatement vs the reference's own modules (oracle/make_golden_heads.py) ----------
+def _sd(g):
+    return {k[3:]: T(v).float() for k, v in g.items() if k.startswith("sd_")}
+
+
+@pytest.mark.parametrize("name", ["heads_clip_ada_c2", "heads_clip_ada_c3"])
+def test_heads_clip_ada(golden, name):
+    from oracle import moc_oracle_heads as H
+    g = golden(name)
+    sd, cl = _sd(g), T(g["classifier"])
+    for i in range(int(g["n_bags"])):
+        x = T(g["feat_%d" % i]).float()
+        assert torch.equal(H.clip_ada_forward(sd, cl, x, float(g["clip_ratio"]), int(g["topj"])), T(g["forward_%d" % i]))
+        assert torch.equal(H.clip_ada_forward_disable_ada(cl, x, int(g["topj"])), T(g["forward_disable_ada_%d" % i]))
+
+
+@pytest.mark.parametrize("name", ["heads_abmil_c2", "heads_abmil_c3"])
+def test_heads_abmil(golden, name):
+    from oracle import moc_oracle_heads as H
+    g = golden(name)
+    sd = _sd(g)
+    for i in range(int(g["n_bags"])):
+        logits, y_prob, y_hat, a_raw, pooled = H.abmil_forward(sd, T(g["feat_%d" % i]).float())
+        assert torch.equal(logits, T(g["logits_%d" % i])) and torch.equal(y_prob, T(g["y_prob_%d" % i]))
+        assert torch.equal(y_hat, T(g["y_hat_%d" % i])) and torch.equal(a_raw, T(g["a_raw_%d" % i]))
+        assert torch.equal(pooled, T(g["features_%d" % i])) and torch.equal(a_raw, T(g["attention_only_%d" % i]))
+
+
+def test_heads_mil_fc(golden):
+    from oracle import moc_oracle_heads as H
+    g = golden("heads_mil_fc")
+    sd = _sd(g)
+    for i in range(int(g["n_bags"])):
+        top, y_prob, y_hat, y_probs = H.mil_fc_forward(sd, T(g["feat_%d" % i]).float())
+        assert torch.equal(top, T(g["top_instance_%d" % i])) and torch.equal(y_prob, T(g["y_prob_%d" % i]))
+        assert torch.equal(y_hat, T(g["y_hat_%d" % i])) and torch.equal(y_probs, T(g["y_probs_%d" % i]))
