@@ -26,9 +26,9 @@
 //   warp 12     MMA issuer (one elected lane), two TMEM accumulators.
 //   warps 0-3   epilogue, thread = patch: softmax / top-2 / background sum+max, key planes written as full
 //               128-byte lines.
-// The prompt tile is [b0 ; b1] stacked along N (b1 starts at row NPa = round8(cols)), so a0 needs ONE MMA of
-// width N_wide = round16(2 NPa) for its two products and a1 one of width N_narrow = round16(NPa) (when that
-// overlaps the first rows of b1 it only adds part of the negligible a1.b1 term).
+// The prompt tile is [b0 ; b1] stacked along N (b1 starts at row NPa = round8(cols)); the three products a0 b1,
+// a1 b0, a0 b0 are three MMAs of width N_narrow = round16(NPa) into the same TMEM columns, so the accumulator
+// holds the finished sum (columns past the real prompt count pick up rows of the neighbouring block: unused).
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <stddef.h>
@@ -120,8 +120,8 @@ struct ScoreTcTail {
 
 struct ScoreTcGeom {
     int npa;       // row of b1 inside a tile = columns rounded up to 8
-    int n_wide;    // MMA width of a0 x [b0 ; b1]
-    int n_narrow;  // MMA width of a1 x b0
+    int n_wide;    // rows of one K-block tile: [b0 ; b1] rounded up to 16
+    int n_narrow;  // MMA width (N) of each of the three products
     __host__ __device__ size_t tile_bytes() const { return (size_t)n_wide * 128; }
     __host__ __device__ size_t b_bytes() const { return (size_t)ST_NKB * tile_bytes(); }
 };
@@ -191,7 +191,7 @@ score_keys_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const float* 
     unsigned char* bsm = smem;                                    // resident prompt tiles
     unsigned char* asm_ = smem + b_bytes;                         // A stages (a0 | a1)
     unsigned char* rawsm = asm_ + ST_A_STAGES * ST_STAGE_BYTES;   // per-warp raw fp32 rings
-    const int tmem_cols = g.n_wide > 64 ? 256 : 128;              // two accumulators of n_wide (<= 128) columns
+    const int tmem_cols = 128;                                    // two accumulators of n_narrow (<= 64) columns
 
     // resident prompt tiles (already swizzled): plain copy, then make them visible to the async proxy
     for (int i = tid; i < b_bytes / 16; i += ST_THREADS)
@@ -286,7 +286,8 @@ score_keys_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const float* 
         }
     } else if (warp == ST_WARP_MMA) {
         // =============================== MMA issuer ================================================
-        const uint32_t idesc_wide = st_idesc_f16(g.n_wide), idesc_narrow = st_idesc_f16(g.n_narrow);
+        const uint32_t idesc_narrow = st_idesc_f16(g.n_narrow);
+        const uint32_t b1_off = (uint32_t)g.npa * 128u;   // b1 starts npa rows into the tile (a whole number of swizzle atoms)
         int stage = 0, acc = 0;
         uint32_t parity = 0, acc_parity = 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -306,9 +307,12 @@ score_keys_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const float* 
 #pragma unroll
                     for (int ks = 0; ks < ST_KB / 16; ++ks) {
                         const uint32_t o = ks * 32;  // 16 halves = 32 bytes along K inside the swizzled row
-                        // a0 x [b0 ; b1] -> columns [0, n_wide);  a1 x b0 -> columns [0, n_narrow)
-                        umma_f16(tmem_d, st_desc_sw128(a0 + o), st_desc_sw128(bt + o), idesc_wide, (kb | ks) != 0 ? 1u : 0u);
-                        umma_f16(tmem_d, st_desc_sw128(a1 + o), st_desc_sw128(bt + o), idesc_narrow, 1u);
+                        // a0 b0 + a0 b1 + a1 b0, all into columns [0, n_narrow): the accumulator holds the finished sum
+                        const uint64_t da0 = st_desc_sw128(a0 + o), da1 = st_desc_sw128(a1 + o);
+                        const uint64_t db0 = st_desc_sw128(bt + o), db1 = st_desc_sw128(bt + b1_off + o);
+                        umma_f16(tmem_d, da0, db1, idesc_narrow, (kb | ks) != 0 ? 1u : 0u);
+                        umma_f16(tmem_d, da1, db0, idesc_narrow, 1u);
+                        umma_f16(tmem_d, da0, db0, idesc_narrow, 1u);
                     }
                     st_commit(&empty_bar[stage]);
                     if (kb == ST_NKB - 1) st_commit(&tfull_bar[acc]);
@@ -330,14 +334,20 @@ score_keys_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const float* 
             mbar_wait(&tfull_bar[acc], acc_parity);
             st_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * acc_cols;
+            // Columns are handled in groups of 8 behind warp-uniform guards: whole groups of classes run without
+            // per-element predicates (C = 30 -> three of four), only the group straddling C / n_cols is predicated.
             float v[NCHUNK * 32];
 #pragma unroll
             for (int ch = 0; ch < NCHUNK; ++ch) {
-                float d0[32], d1[32];
-                st_tmem_ld32(taddr + ch * 32, d0);
-                st_tmem_ld32(taddr + g.npa + ch * 32, d1);
+                float d[32];
+                st_tmem_ld32(taddr + ch * 32, d);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[ch * 32 + i] = (d0[i] + d1[i]) * descale;
+                for (int i0 = 0; i0 < 32; i0 += 8) {
+                    if (ch * 32 + i0 < n_cols) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) v[ch * 32 + i0 + e] = d[i0 + e] * descale;
+                    }
+                }
             }
             st_fence_before();
             __syncwarp();
@@ -354,34 +364,86 @@ score_keys_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const float* 
                 }
                 const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
 #pragma unroll
-                for (int i = 0; i < NCHUNK * 32; ++i) v[i] *= inv;
-            }
-            float m1 = -INFINITY, m2 = -INFINITY, bsum = 0.f, bmax = -INFINITY;
+                for (int i0 = 0; i0 < NCHUNK * 32; i0 += 8) {
+                    if (i0 < n_cols) {
 #pragma unroll
-            for (int c = 0; c < NCHUNK * 32; ++c) {
-                if (c < n_cols) bad |= !(fabsf(v[c]) <= 3.0e38f);
-                if (c < C) {
-                    m2 = fmaxf(m2, fminf(m1, v[c]));
-                    m1 = fmaxf(m1, v[c]);
-                } else if (c < n_cols) {
-                    bsum += v[c];
-                    bmax = fmaxf(bmax, v[c]);
+                        for (int e = 0; e < 8; ++e) v[i0 + e] *= inv;
+                    }
                 }
             }
+            // pass 1: top-2 over the classes, sum / max over the background, raw similarities out, finiteness probe
+            // (0 * v is NaN exactly when v is NaN or infinite)
+            float m1 = -INFINITY, m2 = -INFINITY, bsum = 0.f, bmax = -INFINITY, probe = 0.f;
             float* kp = keys + row;
+#pragma unroll
+            for (int c0 = 0; c0 < NCHUNK * 32; c0 += 8) {
+                if (c0 < n_cols) {
+                    if (c0 + 8 <= C) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const float x = v[c0 + e];
+                            probe = fmaf(x, 0.f, probe);
+                            m2 = fmaxf(m2, fminf(m1, x));
+                            m1 = fmaxf(m1, x);
+                            kp[(int64_t)(c0 + e) * key_stride] = x;
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const int c = c0 + e;
+                            const float x = v[c];
+                            if (c < C) {
+                                probe = fmaf(x, 0.f, probe);
+                                m2 = fmaxf(m2, fminf(m1, x));
+                                m1 = fmaxf(m1, x);
+                                kp[(int64_t)c * key_stride] = x;
+                            } else if (c < n_cols) {
+                                probe = fmaf(x, 0.f, probe);
+                                bsum += x;
+                                bmax = fmaxf(bmax, x);
+                            }
+                        }
+                    }
+                }
+            }
+            bad |= (probe != probe);
+            // pass 2: exp(v - max) and its sum; pass 3: the normalised softmax planes
             float esum = 0.f;
 #pragma unroll
-            for (int c = 0; c < NCHUNK * 32; ++c) {
-                if (c < C) {
-                    kp[(int64_t)c * key_stride] = v[c];
-                    v[c] = expf(v[c] - m1);
-                    esum += v[c];
+            for (int c0 = 0; c0 < NCHUNK * 32; c0 += 8) {
+                if (c0 < C) {
+                    if (c0 + 8 <= C) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            v[c0 + e] = expf(v[c0 + e] - m1);
+                            esum += v[c0 + e];
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            if (c0 + e < C) {
+                                v[c0 + e] = expf(v[c0 + e] - m1);
+                                esum += v[c0 + e];
+                            }
+                        }
+                    }
                 }
             }
             const float inv_sum = 1.0f / esum;
+            float* ks = kp + (int64_t)C * key_stride;
 #pragma unroll
-            for (int c = 0; c < NCHUNK * 32; ++c)
-                if (c < C) kp[(int64_t)(C + c) * key_stride] = v[c] * inv_sum;
+            for (int c0 = 0; c0 < NCHUNK * 32; c0 += 8) {
+                if (c0 < C) {
+                    if (c0 + 8 <= C) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) ks[(int64_t)(c0 + e) * key_stride] = v[c0 + e] * inv_sum;
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e)
+                            if (c0 + e < C) ks[(int64_t)(c0 + e) * key_stride] = v[c0 + e] * inv_sum;
+                    }
+                }
+            }
             kp[(int64_t)(2 * C) * key_stride] = fabsf(m1 - m2);
             kp[(int64_t)(2 * C + 1) * key_stride] = bsum;
             kp[(int64_t)(2 * C + 2) * key_stride] = bmax;
