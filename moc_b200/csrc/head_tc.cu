@@ -158,12 +158,13 @@ head_rows_tc_kernel(const float* __restrict__ feat, const float* __restrict__ ke
         // runs across tile boundaries): the gather is latency-bound, so bytes in flight are what buys bandwidth.
         const int pw = warp - TC_EPI_WARPS;      // 0..7 : rows 16*pw .. 16*pw+15 of the tile
         const int rsub = lane >> 3, chunk = lane & 7;
-        int roff[4];
+        uint32_t roff[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int r = pw * 16 + i * 4 + rsub;
-            roff[i] = r * 128 + ((chunk ^ (r & 7)) << 4);
+            roff[i] = (uint32_t)(r * 128 + ((chunk ^ (r & 7)) << 4));
         }
+        const uint32_t smem_base = smem_u32(smem);
         // load cursor
         int64_t ltile = blockIdx.x;
         int lkb = 0;
@@ -202,8 +203,7 @@ head_rows_tc_kernel(const float* __restrict__ feat, const float* __restrict__ ke
             for (int s = 0; s < TC_PF; ++s) {
                 if (pending[s]) {
                     mbar_wait(&empty_bar[stage], parity ^ 1u);
-                    unsigned char* a_hi = smem + (size_t)stage * TC_STAGE_BYTES;
-                    unsigned char* a_lo = a_hi + TC_A_BYTES;
+                    const uint32_t a_hi = smem_base + stage * TC_STAGE_BYTES, a_lo = a_hi + TC_A_BYTES;
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const float4 cur = buf[s][i];
@@ -213,8 +213,8 @@ head_rows_tc_kernel(const float* __restrict__ feat, const float* __restrict__ ke
                         hi.z = __uint_as_float(__float_as_uint(cur.z) & 0xffffe000u);
                         hi.w = __uint_as_float(__float_as_uint(cur.w) & 0xffffe000u);
                         lo = make_float4(cur.x - hi.x, cur.y - hi.y, cur.z - hi.z, cur.w - hi.w);
-                        *reinterpret_cast<float4*>(a_hi + roff[i]) = hi;
-                        *reinterpret_cast<float4*>(a_lo + roff[i]) = lo;
+                        sts128(a_hi + roff[i], hi);   // explicit st.shared: the aligned-by-arithmetic base pointer would
+                        sts128(a_lo + roff[i], lo);   // otherwise compile to generic ST.E
                     }
                     fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async proxy
                     __syncwarp();
