@@ -244,7 +244,8 @@ def run_reference(a):
         "e2e": {"value": value, "unit": "slides/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    OUT.write(json.dumps(line) + "\n")
+    OUT.flush()
 
 
 # ------------------------------------------------------------------------------------------------
@@ -401,14 +402,25 @@ def run_ours(a):
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
             "clocks": sampler.summary(),
         }
-        print(json.dumps(line))
+        OUT.write(json.dumps(line) + "\n")
+        OUT.flush()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+def _quiet_stdout():
+    """Libraries (NCCL's version banner, torchrun notices) write to fd 1; the contract is ONE JSON line on stdout.
+    Everything else goes to stderr: fd 1 is pointed at fd 2 and the JSON line is written to the saved descriptor."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(real, "w")
+
+
 if __name__ == "__main__":
     args = parse()
+    globals()["OUT"] = _quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
