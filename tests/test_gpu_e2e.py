@@ -95,3 +95,17 @@ def test_config3_rcc_shapes_short():
         for k in r:
             _same(g[k], r[k], "epoch %d %s" % (e, k))
     assert best == g_best
+
+
+def test_config4_ebrains30_shapes_short():
+    """EBRAINS-30-shaped (C=30, C_ext=34): the tensor-core scoring kernel, 62 selections per slide and the
+    30-class ovo/macro AUC inside the full few-shot loop, exact metric equality with the CPU oracle."""
+    ref, got, best, g_best, _, _ = _run_case(c=30, shot=1, n_patches=2500, n_val=60, n_test=60, topj=100, topk=10,
+                                             epochs=2, seed=70)
+    for r, g, name in zip(ref["zs"], got["zs"], ("zs_train", "zs_val", "zs_test")):
+        _same(g, r, name)
+    for e, (r, g) in enumerate(zip(ref["epochs"], got["epochs"])):
+        assert set(r) == set(g)
+        for k in r:
+            _same(g[k], r[k], "epoch %d %s" % (e, k))
+    assert best == g_best
