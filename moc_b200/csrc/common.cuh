@@ -63,17 +63,20 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// try_wait with a suspend-time hint: a waiting warp sleeps in hardware until the phase completes (or the hint
+// expires) instead of spinning through the loop and taking issue slots from the warps it is waiting for.
+constexpr uint32_t MBAR_SUSPEND_NS = 1000000u;
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n"
         ".reg .pred P1;\n"
         "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
         "@P1 bra DONE;\n"
         "bra LAB_WAIT;\n"
         "DONE:\n"
         "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
+        "r"(parity), "r"(MBAR_SUSPEND_NS)
         : "memory");
 }
 __device__ __forceinline__ uint64_t l2_policy_evict_first() {
@@ -126,12 +129,12 @@ __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
         "{\n"
         ".reg .pred P1;\n"
         "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
         "@P1 bra DONE;\n"
         "bra LAB_WAIT;\n"
         "DONE:\n"
         "}\n" ::"r"(bar),
-        "r"(parity)
+        "r"(parity), "r"(MBAR_SUSPEND_NS)
         : "memory");
 }
 
