@@ -274,6 +274,19 @@ int moc_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
                   int64_t step, float lr, float beta1, float beta2, float eps, float weight_decay,
                   void* stream);
 
+/* ---- a1: on-disk bags -------------------------------------------------------
+ * Native reader for CLAM-style HDF5 bag files, replacing h5py.File(path)['features'][:] /
+ * ['coords'][:] (datasets/dataset_generic.py:424-430) for the subset of the format those
+ * files use (h5py defaults: superblock v0/v1, version-1 object headers, symbol-table groups;
+ * chunked, contiguous or compact layout; no filters).  HOST pointers; no CUDA calls.
+ * moc_h5_read writes the dataset densely (row-major, file element type, little endian)
+ * into dst_h, e.g. straight into a pinned staging buffer.  type_class: 0 integer, 1 float. */
+int moc_h5_open(const char* path, void** handle);
+void moc_h5_close(void* handle);
+int moc_h5_dataset_info(void* handle, const char* name, int* rank, int64_t* dims4, int* type_class,
+                        int* elem_size);
+int moc_h5_read(void* handle, const char* name, void* dst_h, size_t dst_bytes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -66,6 +66,10 @@ SIGNATURES = {
     "moc_senet_forward": (i32, [p, i64, p, p, p, p, p, p, sz, p]),
     "moc_senet_backward_workspace_bytes": (sz, [i64]),
     "moc_senet_backward": (i32, [p, i64, p, p, p, p, p, p, p, sz, p]),
+    "moc_h5_open": (i32, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "moc_h5_close": (None, [p]),
+    "moc_h5_dataset_info": (i32, [p, C.c_char_p, C.POINTER(i32), C.POINTER(i64), C.POINTER(i32), C.POINTER(i32)]),
+    "moc_h5_read": (i32, [p, C.c_char_p, p, sz]),
     "moc_adam_step": (i32, [p, p, p, p, i64, i64, f32, f32, f32, f32, f32, p]),
 }
 

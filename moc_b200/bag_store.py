@@ -89,6 +89,53 @@ class RaggedBagStore:
         bags = [torch.load(os.path.join(data_dir, "pt_files", "%s.pt" % s), map_location="cpu") for s in slide_ids]
         return RaggedBagStore.from_bags(bags, labels, device, slide_ids)
 
+    @staticmethod
+    def from_h5_dir(data_dir: str, slide_ids: Sequence[str], labels: Sequence[int], device="cuda",
+                    return_coords: bool = False):
+        """CLAM-style ``h5_files/<slide_id>.h5`` bags (datasets/dataset_generic.py:424-430), parsed by the native
+        reader (moc_b200/h5bag.py; no h5py) straight into pinned staging buffers and copied to the device while the
+        next file is being read.  ``return_coords`` also returns the per-slide ``coords`` arrays (host, numpy)."""
+        import os
+        from .h5bag import H5File
+        paths = [os.path.join(data_dir, "h5_files", "%s.h5" % s) for s in slide_ids]
+        files = [H5File(p) for p in paths]
+        try:
+            sets = [f["features"] for f in files]
+            offs = [0]
+            for p, d in zip(paths, sets):
+                if len(d.shape) != 2 or d.shape[1] != D:
+                    raise ValueError("%s: 'features' has shape %s, expected [N,%d]" % (p, d.shape, D))
+                offs.append(offs[-1] + d.shape[0])
+            feat = torch.empty(offs[-1], D, dtype=torch.float32, device=device)
+            use_pin = torch.device(device).type == "cuda"
+            max_rows = max([d.shape[0] for d in sets] + [1])
+            stage = [torch.empty(max_rows, D, dtype=torch.float32, pin_memory=use_pin) for _ in range(2 if use_pin else 1)]
+            ev = [None, None]
+            for i, d in enumerate(sets):
+                n = d.shape[0]
+                if n == 0:
+                    continue
+                k = i % len(stage)
+                if ev[k] is not None:
+                    ev[k].synchronize()
+                if d.dtype == np.float32:
+                    d.read_into(stage[k].data_ptr(), n * D * 4)
+                else:       # float16 / float64 feature files: convert on the host
+                    stage[k][:n].copy_(torch.from_numpy(d[:].astype(np.float32)))
+                feat[offs[i]:offs[i + 1]].copy_(stage[k][:n], non_blocking=use_pin)
+                if use_pin:
+                    ev[k] = torch.cuda.Event()
+                    ev[k].record()
+            if use_pin:
+                torch.cuda.current_stream().synchronize()
+            store = RaggedBagStore(feat, offs, labels, slide_ids)
+            if return_coords:
+                return store, [f["coords"][:] for f in files]
+            return store
+        finally:
+            for f in files:
+                f.close()
+
     # ---- access --------------------------------------------------------------------------------
     def __len__(self) -> int:
         return len(self.labels_h)

@@ -4,7 +4,7 @@ needed to run without a CONCH checkpoint or slide data:
     python -m moc_b200.main_moc --fold 0 --shot 4 --topj 400 --topk 10 --dataset nsclc --synthetic
     torchrun --nproc-per-node 8 -m moc_b200.main_moc --dataset ebrains30 --shot 16 --synthetic --n_patches 50000
 
-Real data: ``--data_dir`` with CLAM-style ``pt_files/<slide_id>.pt`` bags, ``--csv`` (slide_id,label) and
+Real data: ``--data_dir`` with CLAM-style ``h5_files/<slide_id>.h5`` (native reader) or ``pt_files/<slide_id>.pt`` bags, ``--csv`` (slide_id,label) and
 ``--splits_csv`` (train,val,test columns, as ``splits/*_fewshot/*shots/splits_*.csv``), and ``--weights`` /
 ``--weights_ext`` pointing at the cached prompt matrices the reference writes to ``models/classifier_weights``.
 Outputs keep the reference's names and JSON schema (zs_results_*, best_results_*, best_model_*.pt).
@@ -66,7 +66,10 @@ def _real_stores(args, device):
     for key in ("train", "val", "test"):
         ids = set(splits[key].dropna().tolist())
         part = df[df["slide_id"].isin(ids)]  # dataset-csv order, as get_split_from_df (dataset_generic.py:206-207)
-        out.append(RaggedBagStore.from_pt_dir(args.data_dir, part["slide_id"].tolist(), part["y"].tolist(), device))
+        ids_, ys = part["slide_id"].tolist(), part["y"].tolist()
+        # h5_files/ first, as the reference's loader does with use_h5 (dataset_generic.py:424-430); else pt_files/
+        use_h5 = os.path.isdir(os.path.join(args.data_dir, "h5_files"))
+        out.append((RaggedBagStore.from_h5_dir if use_h5 else RaggedBagStore.from_pt_dir)(args.data_dir, ids_, ys, device))
     return out
 
 
@@ -126,8 +129,15 @@ def run(args):
         torch.manual_seed(args.seed)
     model = senet(512, 4).to(device)
     optimizer = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4)
+    import time
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
     res = loops.main(args, model, optimizer, loaders["train"], loaders["val"], loaders["test"], device,
                      num_epoch=args.epochs, is_main=(rank == 0))
+    torch.cuda.synchronize()
+    if rank == 0:
+        print("zero-shot + %d epochs (train %d steps, eval train/val every epoch, test on improvement): %.2f s"
+              % (args.epochs, len(loaders["train"]), time.perf_counter() - t0))
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
