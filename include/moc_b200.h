@@ -221,6 +221,14 @@ int moc_linear_forward(const float* x, int64_t ldx, int64_t n_rows, int k, const
                        int n_out, int act0, int split, int act1, float* y, int64_t ldy, void* workspace,
                        size_t workspace_bytes, void* stream);
 
+/* Weight gradient of such a layer (autograd of y = x W^T): dw[m][j] (+)= sum_n g[n][m] * x[n][j]
+ * with g = d(loss)/dy [n_rows][n_out] - the contraction runs over the patches of the bag.
+ * tcgen05 3xTF32, split over the bag with a fixed-order (deterministic) reduction.
+ * n_out and k multiples of 4; accumulate != 0 adds to dw instead of overwriting it. */
+size_t moc_linear_wgrad_workspace_bytes(int64_t n_rows, int n_out, int k);
+int moc_linear_wgrad(const float* g, int64_t ldg, int n_out, const float* x, int64_t ldx, int k, int64_t n_rows,
+                     float* dw, int64_t lddw, int accumulate, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Conch_CLIP_Ada after its adapter MLP (models/model_adapters.py:186-190): f =
  * adapted * clip_ratio + x * (1 - clip_ratio), f /= |f|, logits = f @ classifier
  * ([512][C] row-major).  adapted == NULL gives forward_disable_ada (:211-214):
@@ -243,6 +251,23 @@ size_t moc_attention_pool_workspace_bytes(int64_t n_rows, int width);
 int moc_attention_pool(const float* a_raw, const float* h, int64_t ldh, int width, int64_t n_rows,
                        const float* w_cls, const float* b_cls, int n_classes, float* pooled, float* logits,
                        float* probs, int32_t* y_hat, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Backward of ABMIL = CLAM_SB(instance_loss_fn=None).forward_single for one bag, from
+ * dlogits = d(loss)/d(logits) [C]  (what loss.backward() computes through autograd in
+ * utils/core_utils.py:398-414 for models/model_clam.py:175-212).  Inputs are the forward's
+ * activations: h1 = relu(fc x) [N][width], ab = [tanh branch | sigmoid branch] [N][2*hidden],
+ * a_raw [N], pooled [width]; w_ab = [attention_a.weight; attention_b.weight] stacked
+ * [2*hidden][width], wc = attention_c.weight [hidden], w_cls [C][width].
+ * Outputs (written, not accumulated): d_wfc [width][k_in], d_bfc [width], d_wab [2*hidden][width],
+ * d_bab [2*hidden], d_wc [hidden], d_bc [1], d_wcls [C][width], d_bcls [C].
+ * width a multiple of 128, hidden a multiple of 16 (<= 512); workspace 256-byte aligned. */
+size_t moc_abmil_backward_workspace_bytes(int64_t n_rows, int k_in, int width, int hidden);
+int moc_abmil_backward(const float* x, int64_t ldx, int k_in, int64_t n_rows, const float* h1, int64_t ldh,
+                       int width, const float* ab, int64_t ldab, int hidden, const float* a_raw,
+                       const float* pooled, const float* w_ab, const float* wc, const float* w_cls,
+                       int n_classes, const float* dlogits, float* d_wfc, float* d_bfc, float* d_wab,
+                       float* d_bab, float* d_wc, float* d_bc, float* d_wcls, float* d_bcls, void* workspace,
+                       size_t workspace_bytes, void* stream);
 
 /* per-row softmax of [n_rows][n_cols] logits (MIL_fc, models/model_mil.py:38) */
 int moc_row_softmax(const float* logits, int64_t ld, int n_cols, int64_t n_rows, float* probs, int64_t ldp,

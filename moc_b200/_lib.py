@@ -66,6 +66,11 @@ SIGNATURES = {
     "moc_senet_forward": (i32, [p, i64, p, p, p, p, p, p, sz, p]),
     "moc_senet_backward_workspace_bytes": (sz, [i64]),
     "moc_senet_backward": (i32, [p, i64, p, p, p, p, p, p, p, sz, p]),
+    "moc_linear_wgrad_workspace_bytes": (sz, [i64, i32, i32]),
+    "moc_linear_wgrad": (i32, [p, i64, i32, p, i64, i32, i64, p, i64, i32, p, sz, p]),
+    "moc_abmil_backward_workspace_bytes": (sz, [i64, i32, i32, i32]),
+    "moc_abmil_backward": (i32, [p, i64, i32, i64, p, i64, i32, p, i64, i32, p, p, p, p, p, i32, p,
+                                 p, p, p, p, p, p, p, p, p, sz, p]),
     "moc_h5_open": (i32, [C.c_char_p, C.POINTER(C.c_void_p)]),
     "moc_h5_close": (None, [p]),
     "moc_h5_dataset_info": (i32, [p, C.c_char_p, C.POINTER(i32), C.POINTER(i64), C.POINTER(i32), C.POINTER(i32)]),

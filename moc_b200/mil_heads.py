@@ -1,10 +1,12 @@
 """The secondary MIL heads north_star names next to MOC proper, with the reference's module surface.
 
 None of them is instantiated by a shipped driver of the reference, so they are built
-forward-only: parameters live in ordinary ``nn.Linear`` containers under the reference's attribute names (their
-``state_dict``s interchange), ``forward`` runs every dense layer on the tensor cores (``ops.linear``: tcgen05
-3xTF32) and everything else in our row kernels, under ``torch.no_grad``.  Training these heads (their backward)
-is not implemented - MOC itself trains only ``senet``.
+with the reference's attribute names: parameters live in ordinary ``nn.Linear`` containers (their ``state_dict``s
+interchange), ``forward`` runs every dense layer on the tensor cores (``ops.linear``: tcgen05 3xTF32) and
+everything else in our row kernels.  ABMIL also trains: with gradients enabled its ``forward`` returns logits that
+carry a graph whose backward is ours (``ops.abmil_backward``: tcgen05 weight gradients, deterministic reductions),
+so the reference's ``loss.backward(); optimizer.step()`` loop (utils/core_utils.py:398-416) runs unchanged.  The
+other two heads are forward-only (``torch.no_grad``).
 
 * ``Conch_CLIP_Ada``  models/model_adapters.py:148-215 - adapter MLP, residual blend, normalise, score, top-j mean
 * ``CLAM_SB``         models/model_clam.py:77-219 with ``instance_loss_fn=None`` (= ABMIL): gated attention pooling
@@ -25,6 +27,41 @@ def _pool_topj_planes(planes: torch.Tensor, topj: int) -> torch.Tensor:
     c, n = planes.shape
     offs = torch.tensor([0, n], dtype=torch.int64, device=planes.device)
     return ops.pool_topk(planes, offs, 1, c, int(topj), 0, 1, 0, 1, False)
+
+
+
+def _abmil_forward(h, w_fc, b_fc, w_a, b_a, w_b, b_b, w_c, b_c, w_cls, b_cls):
+    """CLAM_SB.forward_single (models/model_clam.py:175-212) on our kernels; also returns what the backward needs."""
+    d = w_a.size(0)
+    hh = ops.linear(h, w_fc, b_fc, "relu")
+    w_ab = torch.cat([w_a, w_b], dim=0)
+    b_ab = torch.cat([b_a, b_b], dim=0)
+    ab = ops.linear(hh, w_ab, b_ab, "tanh", split=d, act_tail="sigmoid")
+    a_raw = ops.gated_attention_scores(ab, d, w_c, float(b_c))
+    pooled, logits, probs, yhat = ops.attention_pool(a_raw, hh, w_cls, b_cls)
+    return logits, probs, yhat.to(torch.int64).view(1, 1), a_raw.unsqueeze(0), pooled, hh, ab, w_ab
+
+
+class _AbmilFunction(torch.autograd.Function):
+    """logits = ABMIL(h; parameters) with the hand-written backward (ops.abmil_backward): gradients for the ten
+    parameter tensors, none for the bag (the reference never differentiates with respect to the features)."""
+
+    @staticmethod
+    def forward(ctx, h, w_fc, b_fc, w_a, b_a, w_b, b_b, w_c, b_c, w_cls, b_cls):
+        logits, probs, yhat, a_row, pooled, hh, ab, w_ab = _abmil_forward(h, w_fc, b_fc, w_a, b_a, w_b, b_b, w_c, b_c,
+                                                                          w_cls, b_cls)
+        ctx.save_for_backward(h, hh, ab, a_row, pooled, w_ab, w_c, w_cls)
+        ctx.hidden = w_a.size(0)
+        ctx.mark_non_differentiable(probs, yhat, a_row, pooled)
+        return logits, probs, yhat, a_row, pooled
+
+    @staticmethod
+    def backward(ctx, dlogits, *unused):
+        h, hh, ab, a_row, pooled, w_ab, w_c, w_cls = ctx.saved_tensors
+        d = ctx.hidden
+        d_wfc, d_bfc, d_wab, d_bab, d_wc, d_bc, d_wcls, d_bcls = ops.abmil_backward(
+            h, hh, ab, d, a_row.reshape(-1), pooled, w_ab, w_c, w_cls, dlogits.contiguous())
+        return (None, d_wfc, d_bfc, d_wab[:d], d_bab[:d], d_wab[d:], d_bab[d:], d_wc.view(1, d), d_bc, d_wcls, d_bcls)
 
 
 class Conch_CLIP_Ada(nn.Module):
@@ -118,24 +155,34 @@ class CLAM_SB(nn.Module):
     def relocate(self):
         self.to(torch.device("cuda"))
 
-    @torch.no_grad()
+    def _params(self):
+        att = self.attention_net[-1]
+        fc = self.attention_net[0]
+        return (fc.weight, fc.bias, att.attention_a[0].weight, att.attention_a[0].bias, att.attention_b[0].weight,
+                att.attention_b[0].bias, att.attention_c.weight, att.attention_c.bias, self.classifiers.weight,
+                self.classifiers.bias)
+
     def forward_single(self, h, label=None, instance_eval=False, return_features=False, attention_only=False):
         if instance_eval:
             raise MocError(E_ARG, "instance-level clustering (instance_eval=True) is outside the ABMIL path built here")
         if self.training and any(isinstance(m, nn.Dropout) for m in self.modules()):
-            raise MocError(E_ARG, "dropout in training mode is not implemented (forward-only head): call .eval()")
-        fc = self.attention_net[0]
-        hh = ops.linear(h, fc.weight, fc.bias, "relu")
-        a_raw, _ = self.attention_net[-1](hh)
-        a_row = a_raw.t()
+            raise MocError(E_ARG, "dropout in training mode is not implemented: build the model with dropout=False or call .eval()")
+        if self.attention_net[-1].attention_c.out_features != 1:
+            raise MocError(E_SHAPE, "Attn_Net_Gated: only the single-branch attention (n_classes=1) is implemented")
+        params = self._params()
         if attention_only:
-            return a_row
-        pooled, logits, probs, yhat = ops.attention_pool(a_raw.reshape(-1), hh, self.classifiers.weight,
-                                                         self.classifiers.bias)
+            with torch.no_grad():
+                return _abmil_forward(h, *params)[3]
+        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            # training (utils/core_utils.py:391-416): logits carry the graph; loss.backward() runs our backward kernels
+            logits, probs, yhat, a_row, pooled = _AbmilFunction.apply(h, *params)
+        else:
+            with torch.no_grad():
+                logits, probs, yhat, a_row, pooled = _abmil_forward(h, *params)[:5]
         results = {}
         if return_features:
             results["features"] = pooled
-        return logits, probs, yhat.to(torch.int64).view(1, 1), a_row, results
+        return logits, probs, yhat, a_row, results
 
     def forward(self, h, label=None, instance_eval=False, return_features=False, attention_only=False):
         if h.dim() == 3:

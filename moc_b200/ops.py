@@ -484,3 +484,49 @@ def row_softmax(logits: torch.Tensor) -> torch.Tensor:
     _count(1)
     check(_lib.load().moc_row_softmax(logits.data_ptr(), logits.stride(0), c, n, out.data_ptr(), c, _stream()))
     return out
+
+
+def linear_wgrad(g: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate: bool = False
+                 ) -> torch.Tensor:
+    """dW [M,K] = g^T @ x for g = d(loss)/dy [N,M] and the layer input x [N,K] (tcgen05 3xTF32, deterministic)."""
+    g = _dev_f32(g, "g")
+    x = _dev_f32(x, "x")
+    if g.dim() != 2 or x.dim() != 2 or g.size(0) != x.size(0):
+        raise MocError(_lib.E_SHAPE, "linear_wgrad: g [N,M] and x [N,K] expected, got %s and %s" % (tuple(g.shape), tuple(x.shape)))
+    n, m = g.shape
+    k = x.size(1)
+    if out is None:
+        out = torch.empty(m, k, dtype=torch.float32, device=g.device)
+        accumulate = False
+    lib = _lib.load()
+    ws_bytes = lib.moc_linear_wgrad_workspace_bytes(n, m, k)
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=g.device)
+    _count(2)
+    check(lib.moc_linear_wgrad(g.data_ptr(), g.stride(0), m, x.data_ptr(), x.stride(0), k, n, out.data_ptr(), out.stride(0),
+                               1 if accumulate else 0, ws.data_ptr(), ws_bytes, _stream()))
+    return out
+
+
+def abmil_backward(x: torch.Tensor, h1: torch.Tensor, ab: torch.Tensor, hidden: int, a_raw: torch.Tensor,
+                   pooled: torch.Tensor, w_ab: torch.Tensor, wc: torch.Tensor, w_cls: torch.Tensor, dlogits: torch.Tensor):
+    """Parameter gradients of ABMIL for one bag: (d_wfc, d_bfc, d_wab, d_bab, d_wc, d_bc, d_wcls, d_bcls)."""
+    x = _dev_f32(x, "x")
+    n, k_in = x.shape
+    width = h1.size(1)
+    c = w_cls.size(0)
+    dev = x.device
+    w_ab, wc, w_cls = _dev_f32(w_ab, "w_ab"), _dev_f32(wc, "wc").reshape(-1), _dev_f32(w_cls, "w_cls")
+    dl = _dev_f32(dlogits, "dlogits").reshape(-1)
+    f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+    d_wfc, d_bfc, d_wab, d_bab = f(width, k_in), f(width), f(2 * hidden, width), f(2 * hidden)
+    d_wc, d_bc, d_wcls, d_bcls = f(hidden), f(1), f(c, width), f(c)
+    lib = _lib.load()
+    ws_bytes = lib.moc_abmil_backward_workspace_bytes(n, k_in, width, hidden)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    _count(14)
+    check(lib.moc_abmil_backward(x.data_ptr(), x.stride(0), k_in, n, h1.data_ptr(), h1.stride(0), width, ab.data_ptr(),
+                                 ab.stride(0), int(hidden), a_raw.data_ptr(), pooled.data_ptr(), w_ab.data_ptr(),
+                                 wc.data_ptr(), w_cls.data_ptr(), c, dl.data_ptr(), d_wfc.data_ptr(), d_bfc.data_ptr(),
+                                 d_wab.data_ptr(), d_bab.data_ptr(), d_wc.data_ptr(), d_bc.data_ptr(), d_wcls.data_ptr(),
+                                 d_bcls.data_ptr(), ws.data_ptr(), ws_bytes, _stream()))
+    return d_wfc, d_bfc, d_wab, d_bab, d_wc, d_bc, d_wcls, d_bcls

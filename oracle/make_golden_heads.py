@@ -6,7 +6,7 @@ Imports models/model_adapters.py, models/model_clam.py and models/model_mil.py U
 checkout (with empty stand-ins for the absent third-party imports they make at module level: openslide, the CONCH
 model factory, nystrom_attention), instantiates Conch_CLIP_Ada, CLAM_SB (instance_loss_fn=None = ABMIL) and MIL_fc
 with seeded initialisation, runs their forward on seeded bags and stores inputs, parameters and outputs in
-tests/golden/heads_*.npz.
+tests/golden/heads_*.npz.  ``--backward`` writes only the ABMIL training-step gradients (heads_abmil_bwd_c*.npz).
 """
 from __future__ import annotations
 
@@ -125,5 +125,51 @@ def main():
     print("wrote heads_mil_fc")
 
 
+def main_backward():
+    """ABMIL training step through the reference's own module and torch autograd (utils/core_utils.py:391-416:
+    logits = model(data); loss = CE(logits, label); loss.backward()): parameter gradients of the last bag of
+    each heads_abmil_c*.npz configuration, rebuilt from the same seeds (checked against the stored parameters).
+    Stored in heads_abmil_bwd_c*.npz: loss, every bias / small gradient in full, the three large matrices in full
+    for C=2 and as every 5th element for C=3."""
+    assert ref_loader.available()
+    torch.set_num_threads(1)
+    clam, _, _ = import_reference_models()
+    for c, sizes, seed in ((2, [65, 900], 41), (3, [513], 42)):
+        torch.manual_seed(seed)
+        m = clam.CLAM_SB(gate=True, size_arg="conch", dropout=False, n_classes=c, instance_loss_fn=None).train()
+        with torch.no_grad():
+            for p_ in m.parameters():
+                if p_.dim() == 1:
+                    p_.copy_(0.05 * torch.randn(p_.shape))
+        fp16_exact(m)
+        stored = np.load(os.path.join(OUT, "heads_abmil_c%d.npz" % c))
+        for k, v in m.state_dict().items():
+            assert np.array_equal(v.half().numpy(), stored["sd_" + k]), k
+        i = len(sizes) - 1
+        x = torch.from_numpy(stored["feat_%d" % i]).float()
+        label = torch.tensor([(i + 1) % c])
+        logits, _, _, _, _ = m(x)
+        assert np.array_equal(logits.detach().numpy(), stored["logits_%d" % i])
+        loss = torch.nn.CrossEntropyLoss()(logits, label)
+        loss.backward()
+        out = {"bag": i, "label": int(label), "loss": float(loss)}
+        for k, p_ in m.named_parameters():
+            if k.startswith("instance_classifiers"):
+                assert p_.grad is None
+                continue
+            g = p_.grad.numpy()
+            if c == 3 and g.size > 4096:
+                out["grad5_" + k] = g.reshape(-1)[::5].copy()
+                out["norm_" + k] = np.float64(np.linalg.norm(g.astype(np.float64)))
+            else:
+                out["grad_" + k] = g
+        np.savez_compressed(os.path.join(OUT, "heads_abmil_bwd_c%d.npz" % c), **out)
+        print("wrote heads_abmil_bwd_c%d  loss %.6f" % (c, float(loss)))
+
+
 if __name__ == "__main__":
-    main()
+    if "--backward" in sys.argv:
+        main_backward()
+    else:
+        main()
+        main_backward()

@@ -59,3 +59,15 @@ def mil_fc_forward(sd: Dict[str, torch.Tensor], h: torch.Tensor):
     idx = torch.topk(y_probs[:, 1], 1, dim=0)[1].view(1,)                 # :40
     top = torch.index_select(logits, dim=0, index=idx)                    # :42
     return top, F.softmax(top, dim=1), torch.topk(top, 1, dim=1)[1], y_probs   # :44-45
+
+
+def abmil_loss_and_grads(sd: Dict[str, torch.Tensor], h: torch.Tensor, label: int):
+    """One ABMIL training step's loss and parameter gradients, as utils/core_utils.py:391-414 obtains them:
+    logits = model(data); loss = CrossEntropyLoss()(logits, label); loss.backward()  -  torch autograd over the
+    restated forward above.  Returns (loss, {state_dict key: gradient})."""
+    names = [k for k in sd if not k.startswith("instance_classifiers")]
+    leaf = {k: sd[k].detach().clone().requires_grad_(True) for k in names}
+    logits = abmil_forward(leaf, h)[0]
+    loss = F.cross_entropy(logits, torch.tensor([int(label)]))
+    grads = torch.autograd.grad(loss, [leaf[k] for k in names])
+    return loss.detach(), dict(zip(names, grads))

@@ -180,6 +180,24 @@ def test_heads_abmil(golden, name):
         assert torch.equal(pooled, T(g["features_%d" % i])) and torch.equal(a_raw, T(g["attention_only_%d" % i]))
 
 
+@pytest.mark.parametrize("name", ["heads_abmil_c2", "heads_abmil_c3"])
+def test_heads_abmil_backward(golden, name):
+    """The oracle's training-step gradients (autograd over the restated forward) against the ones autograd produced
+    through the reference's own CLAM_SB module."""
+    from oracle import moc_oracle_heads as H
+    g, gb = golden(name), golden(name.replace("abmil", "abmil_bwd"))
+    sd = _sd(g)
+    loss, grads = H.abmil_loss_and_grads(sd, T(g["feat_%d" % int(gb["bag"])]).float(), int(gb["label"]))
+    assert abs(float(loss) - float(gb["loss"])) < 1e-6
+    for k, gr in grads.items():
+        if "grad_" + k in gb:
+            ref = T(gb["grad_" + k])
+            assert (gr - ref).abs().max() <= 1e-6 * ref.abs().max() + 1e-12, k
+        else:
+            ref = T(gb["grad5_" + k])
+            assert (gr.reshape(-1)[::5] - ref).abs().max() <= 1e-6 * ref.abs().max() + 1e-12, k
+
+
 def test_heads_mil_fc(golden):
     from oracle import moc_oracle_heads as H
     g = golden("heads_mil_fc")
