@@ -214,6 +214,95 @@ pool_final_kernel(const float* __restrict__ final_scores, const int64_t* __restr
     }
 }
 
+// Block per slide, one coalesced pass over the slide's [S][C] block of combined scores (the version above reads it
+// K times with a stride of C floats: 30 x the sectors at C = 30).  The block uses T = C * floor(512 / C) threads, so a
+// thread striding the flat array by T always meets the same class; it keeps its POOL_MAXK best 64-bit keys
+// (value, lowest position first) sorted in registers, loading 8 elements at a time so that 8 x T loads are in flight.
+// Then K rounds: every thread offers the head of its list to a shared-memory atomicMax per class, the owner of the
+// winning key pops it.  Same keys and the same order as pool_final_kernel, so results and pool_pos are identical.
+constexpr int POOL_MAXK = 16;
+constexpr int POOL_T = 512;
+constexpr int POOL_BATCH = 8;
+__global__ void __launch_bounds__(POOL_T)
+pool_final_block_kernel(const float* __restrict__ final_scores, const int64_t* __restrict__ sel_base,
+                        const int32_t* __restrict__ sel_count, int C, int topk, float* __restrict__ bag_logits,
+                        int32_t* __restrict__ pool_pos) {
+    extern __shared__ unsigned long long pool_best[];   // [C] round winners, then float sums [C]
+    const int slide = blockIdx.x, tid = threadIdx.x;
+    const int per = POOL_T / C, T = per * C;            // threads in use; thread t owns class t % C
+    const int S = sel_count[slide];
+    const float* f = final_scores + sel_base[slide] * C;
+    const int64_t total = (int64_t)S * C;
+    float* sums = reinterpret_cast<float*>(pool_best + C);
+    unsigned long long lst[POOL_MAXK];
+#pragma unroll
+    for (int j = 0; j < POOL_MAXK; ++j) lst[j] = 0ull;
+    if (tid < C) { pool_best[tid] = 0ull; sums[tid] = 0.f; }
+    if (tid < T) {
+        uint32_t i = (uint32_t)(tid / C);               // row of element e = tid + m * T is tid / C + m * per
+        for (int64_t e = tid; e < total; e += (int64_t)POOL_BATCH * T, i += (uint32_t)(POOL_BATCH * per)) {
+            float v[POOL_BATCH];
+#pragma unroll
+            for (int u = 0; u < POOL_BATCH; ++u) v[u] = e + (int64_t)u * T < total ? f[e + (int64_t)u * T] : 0.f;
+#pragma unroll
+            for (int u = 0; u < POOL_BATCH; ++u) {
+                if (e + (int64_t)u * T < total) {
+                    const unsigned long long key = ((unsigned long long)f2ord(v[u]) << 32) |
+                                                   (unsigned long long)(0xffffffffu - (i + (uint32_t)(u * per)));
+                    if (key > lst[POOL_MAXK - 1]) {
+                        lst[POOL_MAXK - 1] = key;
+#pragma unroll
+                        for (int j = POOL_MAXK - 1; j > 0; --j) {
+                            const unsigned long long a = lst[j - 1], b = lst[j];
+                            lst[j - 1] = a > b ? a : b;
+                            lst[j] = a > b ? b : a;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const int c = tid % C;
+    const int k_eff = topk < S ? topk : S;
+    for (int r = 0; r < k_eff; ++r) {
+        if (tid < T && lst[0] != 0ull) atomicMax(&pool_best[c], lst[0]);
+        __syncthreads();
+        const unsigned long long win = pool_best[c];
+        const bool mine = tid < T && lst[0] == win && win != 0ull;   // keys are unique: exactly one owner per class
+        __syncthreads();
+        if (mine) {
+#pragma unroll
+            for (int j = 0; j + 1 < POOL_MAXK; ++j) lst[j] = lst[j + 1];
+            lst[POOL_MAXK - 1] = 0ull;
+            sums[c] += ord2f((uint32_t)(win >> 32));      // one writer per class and round: the summation order is fixed
+            if (pool_pos) pool_pos[((int64_t)slide * C + c) * topk + r] = (int32_t)(0xffffffffu - (uint32_t)(win & 0xffffffffull));
+            pool_best[c] = 0ull;
+        }
+        __syncthreads();
+    }
+    if (tid < C) {
+        bag_logits[(int64_t)slide * C + tid] = k_eff > 0 ? sums[tid] / (float)k_eff : 0.f;
+        if (pool_pos)
+            for (int r = k_eff; r < topk; ++r) pool_pos[((int64_t)slide * C + tid) * topk + r] = -1;
+    }
+}
+
+static int launch_pool_final(const float* final_scores, const int64_t* sel_base, const int32_t* sel_count, int n_slides,
+                             int C, int topk, float* bag_logits, int32_t* pool_pos, cudaStream_t st) {
+    if (topk <= POOL_MAXK && C <= POOL_T) {
+        const size_t smem = (size_t)C * (sizeof(unsigned long long) + sizeof(float));
+        pool_final_block_kernel<<<n_slides, POOL_T, smem, st>>>(final_scores, sel_base, sel_count, C, topk, bag_logits, pool_pos);
+        MOC_LAUNCH_CHECK("pool_final_block_kernel");
+        return MOC_OK;
+    }
+    const int64_t items = (int64_t)n_slides * C;
+    pool_final_kernel<<<(unsigned)((items + POOL_WARPS - 1) / POOL_WARPS), POOL_WARPS * 32, 0, st>>>(
+        final_scores, sel_base, sel_count, n_slides, C, topk, bag_logits, pool_pos);
+    MOC_LAUNCH_CHECK("pool_final_kernel");
+    return MOC_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // cross_entropy(logits[1,C], label) per slide; optional gradient and argmax.
 // ------------------------------------------------------------------------------------------------
@@ -498,10 +587,10 @@ extern "C" int moc_head_forward(const float* feat, const float* keys, int64_t ke
             if (rc != MOC_OK) return rc;
         }
     }
-    const int64_t items = (int64_t)n_slides * n_classes;
-    pool_final_kernel<<<(unsigned)((items + POOL_WARPS - 1) / POOL_WARPS), POOL_WARPS * 32, 0, st>>>(
-        final_scores, sel_base, sel_count, n_slides, n_classes, topk, bag_logits, pool_pos);
-    MOC_LAUNCH_CHECK("pool_final_kernel");
+    {
+        const int rc = launch_pool_final(final_scores, sel_base, sel_count, n_slides, n_classes, topk, bag_logits, pool_pos, st);
+        if (rc != MOC_OK) return rc;
+    }
     return MOC_OK;
 }
 
@@ -638,9 +727,5 @@ extern "C" int moc_ablation_forward(const float* keys, int64_t key_stride, int n
                                                                             sel_capacity_total, mode, final_scores);
         MOC_LAUNCH_CHECK("ablation_rows_kernel");
     }
-    const int64_t pi = (int64_t)n_slides * n_classes;
-    pool_final_kernel<<<(unsigned)((pi + POOL_WARPS - 1) / POOL_WARPS), POOL_WARPS * 32, 0, st>>>(
-        final_scores, sel_base, sel_count, n_slides, n_classes, topk, bag_logits, nullptr);
-    MOC_LAUNCH_CHECK("pool_final_kernel");
-    return MOC_OK;
+    return launch_pool_final(final_scores, sel_base, sel_count, n_slides, n_classes, topk, bag_logits, nullptr, st);
 }

@@ -8,16 +8,20 @@
 // (exact in fp32); D = A_hi B_hi + A_lo B_hi + A_hi B_lo accumulated in fp32 in TMEM.  The dropped lo*lo term
 // and the TF32 truncation of the lo operands are ~2^-22 relative per product, i.e. fp32-level.
 //
-// Structure (persistent, one CTA per SM, 14 warps):
-//   warps 0-3   epilogue: tcgen05.ld the 128x64 accumulator (thread = row), +b1, ReLU, 4x64 second layer,
-//               sigmoid, gated combination with the row's key planes, stores
-//   warps 4-11  A producers: gather 128 B of 16 rows each per K-block straight from HBM/L2 (TC_PF K-blocks of
-//               loads in flight per thread, across tile boundaries), split hi/lo in registers, store into the
-//               128B-swizzled K-major smem tiles the UMMA descriptor describes
-//   warp 12     MMA issuer (one elected lane): 4 k-steps x 3 products of tcgen05.mma.kind::tf32 M128 N64 K8
+// Structure (persistent, one CTA per SM, 14 warps; a work item is a super-tile of 256 selected-row slots = two
+// M128 row tiles that share every K-block of W1, which halves both the W1 bytes streamed from L2 per row and the
+// number of producer -> MMA -> producer barrier round trips per row - with 128-row items and four 48 KB stages
+// those round trips, not the gather or the tensor pipe, set the pace):
+//   warps 0-3   epilogue: tcgen05.ld the two 128x64 accumulators (thread = one row of each), +b1, ReLU, 4x64
+//               second layer, sigmoid, gated combination with the row's key planes, stores
+//   warps 4-11  A producers: gather 128 B of 2 x 16 rows each per K-block straight from HBM/L2 (TC_PF K-blocks
+//               of loads in flight per thread, across item boundaries), split hi/lo in registers, store into
+//               the 128B-swizzled K-major smem tiles the UMMA descriptor describes
+//   warp 12     MMA issuer (one elected lane): per K-block 4 k-steps x 2 row tiles x 3 products of
+//               tcgen05.mma.kind::tf32 M128 N64 K8
 //   warp 13     B copier: one 16 KB bulk copy per K-block of the pre-split, pre-swizzled W1 (hi|lo)
-// Four smem stages of {A_hi 16K, A_lo 16K, B_hi 8K, B_lo 8K}; full/empty mbarriers; two TMEM accumulators so
-// the epilogue of tile i overlaps the MMAs of tile i+1.
+// Two smem stages of {A0_hi, A0_lo, A1_hi, A1_lo 16K each, B_hi 8K, B_lo 8K}; full/empty mbarriers; two pairs of
+// TMEM accumulators so the epilogue of item i overlaps the MMAs of item i+1.
 #include "common.cuh"
 
 namespace moc {
@@ -27,16 +31,17 @@ constexpr int TC_G = MOC_GATES;
 constexpr int TC_M = 128;          // rows per tile (UMMA M)
 constexpr int TC_KB = 32;          // K elements per stage (one 128-byte swizzle row)
 constexpr int TC_NKB = D / TC_KB;  // 16 K-blocks
-constexpr int TC_STAGES = 4;
-constexpr int TC_PF = 5;            // K-block register sets each producer thread keeps in flight (5 x 16 KB per CTA; the register file of an SM sub-partition caps 4 resident warps at 128 registers)
+constexpr int TC_SUB = 2;           // row tiles per work item
+constexpr int TC_STAGES = 2;
+constexpr int TC_PF = 2;            // K-block register sets (8 x 16 B each) a producer thread keeps in flight: 64 KB per CTA
 constexpr int TC_A_BYTES = TC_M * 128;            // 16 KB per component
 constexpr int TC_B_BYTES = TC_H * 128;            // 8 KB per component
-constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;  // 48 KB
+constexpr int TC_STAGE_BYTES = TC_SUB * 2 * TC_A_BYTES + 2 * TC_B_BYTES;  // 80 KB
 constexpr int TC_EPI_WARPS = 4, TC_PROD_WARPS = 8;
 constexpr int TC_WARP_MMA = TC_EPI_WARPS + TC_PROD_WARPS;  // 12
 constexpr int TC_WARP_B = TC_WARP_MMA + 1;                 // 13
 constexpr int TC_THREADS = (TC_WARP_B + 1) * 32;           // 448
-constexpr int TC_TMEM_COLS = 128;                          // two 64-column accumulators
+constexpr int TC_TMEM_COLS = 256;                          // two pairs of 64-column accumulators
 constexpr size_t TC_SMEM = (size_t)TC_STAGES * TC_STAGE_BYTES + 1024;  // + alignment slack
 
 // tcgen05 instruction descriptor: D=f32, A=B=tf32, both K-major, N=64, M=128 (cute::UMMA::InstrDescriptor)
@@ -104,7 +109,7 @@ __device__ __forceinline__ bool tile_has_rows(const int32_t* __restrict__ sel_ro
     if (sel_rows == nullptr) return true;
     bool any = false;
 #pragma unroll
-    for (int i = 0; i < TC_M / 32; ++i) {
+    for (int i = 0; i < TC_SUB * TC_M / 32; ++i) {
         const int64_t s = slot0 + lane + 32 * i;
         any |= (s < n_slots) && (sel_rows[s] >= 0);
     }
@@ -149,7 +154,7 @@ head_rows_tc_kernel(const float* __restrict__ feat, const float* __restrict__ ke
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
 
-    const int64_t n_tiles = (n_slots + TC_M - 1) / TC_M;
+    const int64_t n_tiles = (n_slots + TC_SUB * TC_M - 1) / (TC_SUB * TC_M);   // work items
 
     if (warp >= TC_EPI_WARPS && warp < TC_WARP_MMA) {
         // =============================== A producers ===============================================
@@ -168,22 +173,23 @@ head_rows_tc_kernel(const float* __restrict__ feat, const float* __restrict__ ke
         // load cursor
         int64_t ltile = blockIdx.x;
         int lkb = 0;
-        const float4* lsrc[4];
-        auto seek = [&]() {  // move ltile to the next tile with rows and fetch its row pointers
-            while (ltile < n_tiles && !tile_has_rows(sel_rows, ltile * TC_M, n_slots, lane)) ltile += gridDim.x;
+        const float4* lsrc[TC_SUB * 4];
+        auto seek = [&]() {  // move ltile to the next item with rows and fetch its row pointers
+            while (ltile < n_tiles && !tile_has_rows(sel_rows, ltile * (TC_SUB * TC_M), n_slots, lane)) ltile += gridDim.x;
             if (ltile >= n_tiles) return;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int64_t sl = ltile * TC_M + pw * 16 + i * 4 + rsub;
+            for (int q = 0; q < TC_SUB * 4; ++q) {
+                const int64_t sl = ltile * (TC_SUB * TC_M) + (q >> 2) * TC_M + pw * 16 + (q & 3) * 4 + rsub;
                 int64_t row = -1;
                 if (sl < n_slots) row = sel_rows ? (int64_t)sel_rows[sl] : sl;
-                lsrc[i] = row >= 0 ? reinterpret_cast<const float4*>(feat + row * D) + chunk : nullptr;
+                lsrc[q] = row >= 0 ? reinterpret_cast<const float4*>(feat + row * D) + chunk : nullptr;
             }
         };
-        auto issue = [&](float4 (&b)[4]) -> bool {  // load the cursor's step into b and advance; false when done
+        auto issue = [&](float4 (&b)[TC_SUB * 4]) -> bool {  // load the cursor's step into b and advance; false when done
             if (ltile >= n_tiles) return false;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) b[i] = lsrc[i] ? __ldg(lsrc[i] + lkb * 8) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int q = 0; q < TC_SUB * 4; ++q)
+                b[q] = lsrc[q] ? __ldg(lsrc[q] + lkb * 8) : make_float4(0.f, 0.f, 0.f, 0.f);
             if (++lkb == TC_NKB) {
                 lkb = 0;
                 ltile += gridDim.x;
@@ -191,7 +197,7 @@ head_rows_tc_kernel(const float* __restrict__ feat, const float* __restrict__ ke
             }
             return true;
         };
-        float4 buf[TC_PF][4];
+        float4 buf[TC_PF][TC_SUB * 4];
         bool pending[TC_PF];
         seek();
 #pragma unroll
@@ -203,18 +209,19 @@ head_rows_tc_kernel(const float* __restrict__ feat, const float* __restrict__ ke
             for (int s = 0; s < TC_PF; ++s) {
                 if (pending[s]) {
                     mbar_wait(&empty_bar[stage], parity ^ 1u);
-                    const uint32_t a_hi = smem_base + stage * TC_STAGE_BYTES, a_lo = a_hi + TC_A_BYTES;
+                    const uint32_t st0 = smem_base + stage * TC_STAGE_BYTES;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float4 cur = buf[s][i];
+                    for (int q = 0; q < TC_SUB * 4; ++q) {
+                        const uint32_t a_hi = st0 + (q >> 2) * 2 * TC_A_BYTES, a_lo = a_hi + TC_A_BYTES;
+                        const float4 cur = buf[s][q];
                         float4 hi, lo;
                         hi.x = __uint_as_float(__float_as_uint(cur.x) & 0xffffe000u);
                         hi.y = __uint_as_float(__float_as_uint(cur.y) & 0xffffe000u);
                         hi.z = __uint_as_float(__float_as_uint(cur.z) & 0xffffe000u);
                         hi.w = __uint_as_float(__float_as_uint(cur.w) & 0xffffe000u);
                         lo = make_float4(cur.x - hi.x, cur.y - hi.y, cur.z - hi.z, cur.w - hi.w);
-                        sts128(a_hi + roff[i], hi);   // explicit st.shared: the aligned-by-arithmetic base pointer would
-                        sts128(a_lo + roff[i], lo);   // otherwise compile to generic ST.E
+                        sts128(a_hi + roff[q & 3], hi);   // explicit st.shared: the aligned-by-arithmetic base pointer would
+                        sts128(a_lo + roff[q & 3], lo);   // otherwise compile to generic ST.E
                     }
                     fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async proxy
                     __syncwarp();
@@ -230,12 +237,12 @@ head_rows_tc_kernel(const float* __restrict__ feat, const float* __restrict__ ke
         int stage = 0;
         uint32_t parity = 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            if (!tile_has_rows(sel_rows, tile * TC_M, n_slots, lane)) continue;
+            if (!tile_has_rows(sel_rows, tile * (TC_SUB * TC_M), n_slots, lane)) continue;
             for (int kb = 0; kb < TC_NKB; ++kb) {
                 if (lane == 0) {
                     mbar_wait(&empty_bar[stage], parity ^ 1u);
                     mbar_arrive_expect_tx(&full_bar[stage], 2 * TC_B_BYTES);
-                    bulk_g2s(smem + (size_t)stage * TC_STAGE_BYTES + 2 * TC_A_BYTES,
+                    bulk_g2s(smem + (size_t)stage * TC_STAGE_BYTES + TC_SUB * 2 * TC_A_BYTES,
                              reinterpret_cast<const char*>(w1_split) + (size_t)kb * 2 * TC_B_BYTES, 2 * TC_B_BYTES,
                              &full_bar[stage], policy);
                 }
@@ -248,29 +255,32 @@ head_rows_tc_kernel(const float* __restrict__ feat, const float* __restrict__ ke
         int stage = 0, acc = 0;
         uint32_t parity = 0, acc_parity = 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            if (!tile_has_rows(sel_rows, tile * TC_M, n_slots, lane)) continue;
+            if (!tile_has_rows(sel_rows, tile * (TC_SUB * TC_M), n_slots, lane)) continue;
             if (lane == 0) {
-                mbar_wait(&tempty_bar[acc], acc_parity ^ 1u);  // epilogue has drained this accumulator
+                mbar_wait(&tempty_bar[acc], acc_parity ^ 1u);  // epilogue has drained this accumulator pair
                 tc_fence_after();
             }
             __syncwarp();
-            const uint32_t tmem_d = tmem_base + acc * TC_H;
+            const uint32_t tmem_d = tmem_base + acc * (TC_SUB * TC_H);
             for (int kb = 0; kb < TC_NKB; ++kb) {
                 if (lane == 0) {
                     mbar_wait(&full_bar[stage], parity);
                     tc_fence_after();
-                    const uint32_t a_hi = smem_u32(smem + (size_t)stage * TC_STAGE_BYTES);
-                    const uint32_t a_lo = a_hi + TC_A_BYTES;
-                    const uint32_t b_hi = a_hi + 2 * TC_A_BYTES;
+                    const uint32_t st0 = smem_u32(smem + (size_t)stage * TC_STAGE_BYTES);
+                    const uint32_t b_hi = st0 + TC_SUB * 2 * TC_A_BYTES;
                     const uint32_t b_lo = b_hi + TC_B_BYTES;
 #pragma unroll
                     for (int ks = 0; ks < TC_KB / 8; ++ks) {
                         const uint32_t o = ks * 32;  // 8 tf32 = 32 bytes along K inside the swizzled row
-                        const uint64_t dah = umma_desc_sw128(a_hi + o), dal = umma_desc_sw128(a_lo + o);
                         const uint64_t dbh = umma_desc_sw128(b_hi + o), dbl = umma_desc_sw128(b_lo + o);
-                        umma_tf32(tmem_d, dal, dbh, (kb | ks) != 0 ? 1u : 0u);
-                        umma_tf32(tmem_d, dah, dbl, 1u);
-                        umma_tf32(tmem_d, dah, dbh, 1u);
+#pragma unroll
+                        for (int sub = 0; sub < TC_SUB; ++sub) {
+                            const uint32_t a_hi = st0 + sub * 2 * TC_A_BYTES, a_lo = a_hi + TC_A_BYTES;
+                            const uint64_t dah = umma_desc_sw128(a_hi + o), dal = umma_desc_sw128(a_lo + o);
+                            umma_tf32(tmem_d + sub * TC_H, dal, dbh, (kb | ks) != 0 ? 1u : 0u);
+                            umma_tf32(tmem_d + sub * TC_H, dah, dbl, 1u);
+                            umma_tf32(tmem_d + sub * TC_H, dah, dbh, 1u);
+                        }
                     }
                     umma_commit(&empty_bar[stage]);               // stage free once these MMAs have read it
                     if (kb == TC_NKB - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete
@@ -289,46 +299,68 @@ head_rows_tc_kernel(const float* __restrict__ feat, const float* __restrict__ ke
         int acc = 0;
         uint32_t acc_parity = 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int64_t slot0 = tile * TC_M;
+            const int64_t slot0 = tile * (TC_SUB * TC_M);
             if (!tile_has_rows(sel_rows, slot0, n_slots, lane)) continue;
-            const int64_t slot = slot0 + warp * 32 + lane;
-            int64_t row = -1;
-            if (slot < n_slots) row = sel_rows ? (int64_t)sel_rows[slot] : slot;
             mbar_wait(&tfull_bar[acc], acc_parity);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * TC_H;
-            float z[TC_G] = {0.f, 0.f, 0.f, 0.f};
+            float z[TC_SUB][TC_G];
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                float d[32];
-                tmem_ld32(taddr + half * 32, d);
+            for (int sub = 0; sub < TC_SUB; ++sub) {
+                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * (TC_SUB * TC_H) + sub * TC_H;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int jj = half * 32 + j;
-                    const float h = fmaxf(d[j] + b1s[jj], 0.f);
+                for (int m = 0; m < TC_G; ++m) z[sub][m] = 0.f;
 #pragma unroll
-                    for (int m = 0; m < TC_G; ++m) z[m] = fmaf(h, w2s[m * TC_H + jj], z[m]);
+                for (int half = 0; half < 2; ++half) {
+                    float d[32];
+                    tmem_ld32(taddr + half * 32, d);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int jj = half * 32 + j;
+                        const float h = fmaxf(d[j] + b1s[jj], 0.f);
+#pragma unroll
+                        for (int m = 0; m < TC_G; ++m) z[sub][m] = fmaf(h, w2s[m * TC_H + jj], z[sub][m]);
+                    }
                 }
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);  // accumulator is in registers: MMA may reuse it
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);  // accumulators are in registers: MMA may reuse them
             if (++acc == 2) { acc = 0; acc_parity ^= 1u; }
-            if (row < 0) continue;
-            float g[TC_G];
 #pragma unroll
-            for (int m = 0; m < TC_G; ++m) g[m] = sigmoidf_exact(z[m] + b2s[m]);
-            if (gate != nullptr) *reinterpret_cast<float4*>(gate + slot * TC_G) = make_float4(g[0], g[1], g[2], g[3]);
-            if (final_scores == nullptr) continue;
-            const float* kp = keys + row;
-            const float dlt = kp[(int64_t)(2 * C) * key_stride];
-            const float bgm = kp[(int64_t)(2 * C + 2) * key_stride];
-            for (int c = 0; c < C; ++c) {
-                float f = a0 * __fmul_rn(g[0], kp[(int64_t)c * key_stride]);
-                f = __fadd_rn(f, a1 * __fmul_rn(g[1], kp[(int64_t)(C + c) * key_stride]));
-                f = __fadd_rn(f, a2 * __fmul_rn(g[2], dlt));
-                f = __fadd_rn(f, a3 * __fmul_rn(g[3], bgm));
-                final_scores[slot * C + c] = f;
+            for (int sub = 0; sub < TC_SUB; ++sub) {
+                const int64_t slot = slot0 + sub * TC_M + warp * 32 + lane;
+                int64_t row = -1;
+                if (slot < n_slots) row = sel_rows ? (int64_t)sel_rows[slot] : slot;
+                if (row < 0) continue;
+                float g[TC_G];
+#pragma unroll
+                for (int m = 0; m < TC_G; ++m) g[m] = sigmoidf_exact(z[sub][m] + b2s[m]);
+                if (gate != nullptr) *reinterpret_cast<float4*>(gate + slot * TC_G) = make_float4(g[0], g[1], g[2], g[3]);
+                if (final_scores == nullptr) continue;
+                const float* kp = keys + row;
+                const float dlt = kp[(int64_t)(2 * C) * key_stride];
+                const float bgm = kp[(int64_t)(2 * C + 2) * key_stride];
+                // four classes at a time with their eight key loads issued together: at C = 30 one load pair per
+                // iteration left the epilogue waiting on 30 dependent round trips per row
+                for (int c0 = 0; c0 < C; c0 += 4) {
+                    float lt[4], ls[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int cc = c0 + u < C ? c0 + u : C - 1;
+                        lt[u] = kp[(int64_t)cc * key_stride];
+                        ls[u] = kp[(int64_t)(C + cc) * key_stride];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (c0 + u < C) {
+                            float f = a0 * __fmul_rn(g[0], lt[u]);
+                            f = __fadd_rn(f, a1 * __fmul_rn(g[1], ls[u]));
+                            f = __fadd_rn(f, a2 * __fmul_rn(g[2], dlt));
+                            f = __fadd_rn(f, a3 * __fmul_rn(g[3], bgm));
+                            final_scores[slot * C + c0 + u] = f;
+                        }
+                    }
+                }
             }
         }
     }
@@ -350,7 +382,7 @@ int launch_head_rows_tc(const float* feat, const float* keys, int64_t key_stride
     head_tc_prep_kernel<<<(TC_H * (D / 4) + 255) / 256, 256, 0, st>>>(w1, w1_split);
     MOC_LAUNCH_CHECK("head_tc_prep_kernel");
     MOC_CUDA(cudaFuncSetAttribute(head_rows_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
-    const int64_t n_tiles = (n_slots + TC_M - 1) / TC_M;
+    const int64_t n_tiles = (n_slots + TC_SUB * TC_M - 1) / (TC_SUB * TC_M);
     const int grid = (int)(n_tiles < sm_count() ? n_tiles : sm_count());
     head_rows_tc_kernel<<<grid, TC_THREADS, TC_SMEM, st>>>(feat, keys, key_stride, C, sel_rows, n_slots, w1_split, b1, w2,
                                                            b2, active_mask, gate, final_scores);
