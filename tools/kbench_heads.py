@@ -56,6 +56,24 @@ def main():
     ab = ab.to(dev)
     print("ABMIL (CLAM_SB conch)        N=%d  gpu %.3f ms   cpu-oracle %.1f ms" % (
         n, gpu_ms(lambda: ab(xd)), cpu_ms(lambda: H.abmil_forward(sd, x))))
+    # one ABMIL training step as utils/core_utils.py:391-416 runs it: forward, CE, backward (ours), against the same
+    # step through torch autograd on the CPU oracle
+    abt = moc_b200.CLAM_SB(size_arg="conch", n_classes=2).to(dev).train()
+    lab = torch.tensor([1], device=dev)
+
+    def step():
+        for p_ in abt.parameters():
+            p_.grad = None
+        logits = abt(xd)[0]
+        torch.nn.functional.cross_entropy(logits, lab).backward()
+    sdt = {k: v.detach().cpu().clone() for k, v in abt.state_dict().items()}
+    print("ABMIL fwd + CE + bwd         N=%d  gpu %.3f ms   cpu-oracle %.1f ms" % (
+        n, gpu_ms(step), cpu_ms(lambda: H.abmil_loss_and_grads(sdt, x, 1))))
+    for m_out, k_in in ((768, 512), (512, 512)):
+        gg = torch.randn(n, m_out, device=dev)
+        xx = torch.randn(n, k_in, device=dev)
+        t = gpu_ms(lambda: ops.linear_wgrad(gg, xx))
+        print("wgrad  dW[%d,%d] = G^T X  N=%d  %.3f ms  %.1f TFLOP/s (useful fp32-accurate)" % (m_out, k_in, n, t, 2.0 * n * m_out * k_in / t / 1e9))
     mf = moc_b200.MIL_fc().eval()
     sd = {k: v.detach().clone() for k, v in mf.state_dict().items()}
     mf = mf.to(dev)
