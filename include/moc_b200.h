@@ -156,10 +156,13 @@ int moc_col_prefix_mean(const float* vals, int64_t ld, int n_cols, int j, float*
  * the four score planes (main_moc.py:391-403 / :482-492, planes chosen by
  * active_mask), then per (slide, class) the mean of the min(topk, S) largest
  * (topj_pooling, utils/patch_selection_classifier.py:18-32).
- * The first layer runs on the tensor cores (tcgen05, 3xTF32 = fp32-accurate);
- * the workspace (moc_head_forward_workspace_bytes(), 16-byte aligned) holds W1
- * split and swizzled for them.  MOC_HEAD_IMPL=simt in the environment selects
- * the CUDA-core kernel instead.
+ * The first layer runs on the tensor cores, fp32-accurate through operand
+ * splitting: FP16x3 (tcgen05 kind::f16, W1 resident in shared memory; features
+ * must satisfy |x| < 4094, beyond that the gates come out non-finite) for up to
+ * 8 classes, 3xTF32 (kind::tf32, no range limit) for wider class sets; the
+ * workspace (moc_head_forward_workspace_bytes(), 16-byte aligned) holds W1 split
+ * and swizzled for them.  MOC_HEAD_IMPL=f16|tf32|simt in the environment forces
+ * one kernel (simt = the CUDA-core cross-check).
  * gate [S_total,4], final [S_total,C], bag_logits [n_slides,C],
  * pool_pos [n_slides,C,topk] (positions inside the slide's selected list,
  * -1 padded), all indexed through sel_base/sel_count. gate may be null. */

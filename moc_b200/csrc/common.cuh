@@ -152,6 +152,12 @@ __device__ __forceinline__ float warp_sum(float v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
     return v;
 }
+// ReLU that keeps NaN, like torch.relu (fmaxf(NaN, 0) is 0): non-finite features must surface as non-finite gates
+__device__ __forceinline__ float relu_nan(float v) {
+    float r;
+    asm("max.NaN.f32 %0, %1, 0f00000000;" : "=f"(r) : "f"(v));
+    return r;
+}
 __device__ __forceinline__ float sigmoidf_exact(float z) { return 1.0f / (1.0f + expf(-z)); }
 
 }  // namespace moc

@@ -21,14 +21,36 @@ int launch_head_rows_tc(const float* feat, const float* keys, int64_t key_stride
                         int64_t n_slots, const float* w1, const float* b1, const float* w2, const float* b2,
                         unsigned active_mask, float* gate, float* final_scores, void* workspace, cudaStream_t st);
 
-// MOC_HEAD_IMPL=simt selects the CUDA-core kernel (kept as the in-tree cross-check of the tensor-core path)
-static bool use_simt_head() {
+// head_f16.cu: the tcgen05 FP16x3 implementation (default): half the shared-memory bytes per unit of K, W1 resident
+size_t head_f16_workspace_bytes();
+int launch_head_rows_f16(const float* feat, const float* keys, int64_t key_stride, int C, const int32_t* sel_rows,
+                         int64_t n_slots, const float* w1, const float* b1, const float* w2, const float* b2,
+                         unsigned active_mask, float* gate, float* final_scores, void* workspace, cudaStream_t st);
+
+// MOC_HEAD_IMPL = auto (default: FP16x3 up to 8 classes, 3xTF32 beyond - see head_f16.cu) | f16 | tf32 | simt.  The
+// 3xTF32 and CUDA-core kernels also serve as in-tree cross-checks of the FP16x3 path and for features outside its
+// |x| < 4094 domain.
+static int head_impl() {
     static int cached = -1;
     if (cached < 0) {
         const char* e = getenv("MOC_HEAD_IMPL");
-        cached = (e && e[0] == 's') ? 1 : 0;
+        cached = (e && e[0] == 's') ? 2 : (e && e[0] == 't') ? 1 : (e && e[0] == 'f') ? 0 : 3;
     }
-    return cached == 1;
+    return cached;
+}
+static bool use_simt_head() { return head_impl() == 2; }
+static size_t head_ws_bytes() {
+    const size_t a = head_tc_workspace_bytes(), b = head_f16_workspace_bytes();
+    return a > b ? a : b;
+}
+static int launch_head_rows_mma(const float* feat, const float* keys, int64_t key_stride, int C, const int32_t* sel_rows,
+                                int64_t n_slots, const float* w1, const float* b1, const float* w2, const float* b2,
+                                unsigned active_mask, float* gate, float* final_scores, void* workspace, cudaStream_t st) {
+    const int impl = head_impl();
+    return (impl == 1 || (impl == 3 && C > 8)) ? launch_head_rows_tc(feat, keys, key_stride, C, sel_rows, n_slots, w1, b1, w2, b2, active_mask,
+                                                  gate, final_scores, workspace, st)
+                            : launch_head_rows_f16(feat, keys, key_stride, C, sel_rows, n_slots, w1, b1, w2, b2, active_mask,
+                                                   gate, final_scores, workspace, st);
 }
 
 constexpr int H = MOC_HIDDEN;  // 64
@@ -132,7 +154,7 @@ head_rows_kernel(const float* __restrict__ feat, const float* __restrict__ keys,
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int j = tx + 16 * u;
-                    const float h = fmaxf(acc[r][u] + b1s[j], 0.f);
+                    const float h = relu_nan(acc[r][u] + b1s[j]);
 #pragma unroll
                     for (int m = 0; m < G; ++m) z[r][m] = fmaf(h, w2s[m * H + j], z[r][m]);
                 }
@@ -578,11 +600,11 @@ extern "C" int moc_head_forward(const float* feat, const float* keys, int64_t ke
                                                              final_scores);
             MOC_LAUNCH_CHECK("head_rows_kernel");
         } else {
-            if (workspace == nullptr || workspace_bytes < head_tc_workspace_bytes()) {
-                set_error("moc_head_forward: workspace %zu B < required %zu B", workspace_bytes, head_tc_workspace_bytes());
+            if (workspace == nullptr || workspace_bytes < head_ws_bytes()) {
+                set_error("moc_head_forward: workspace %zu B < required %zu B", workspace_bytes, head_ws_bytes());
                 return MOC_E_WORKSPACE;
             }
-            const int rc = launch_head_rows_tc(feat, keys, key_stride, n_classes, sel_rows, sel_capacity_total, w1, b1,
+            const int rc = launch_head_rows_mma(feat, keys, key_stride, n_classes, sel_rows, sel_capacity_total, w1, b1,
                                                w2, b2, active_mask, gate, final_scores, workspace, st);
             if (rc != MOC_OK) return rc;
         }
@@ -665,7 +687,7 @@ extern "C" int moc_gather_selected(const float* feat, const float* keys, int64_t
     return MOC_OK;
 }
 
-extern "C" size_t moc_head_forward_workspace_bytes(void) { return head_tc_workspace_bytes(); }
+extern "C" size_t moc_head_forward_workspace_bytes(void) { return head_ws_bytes(); }
 
 extern "C" int moc_senet_forward(const float* x, int64_t n_rows, const float* w1, const float* b1, const float* w2,
                                  const float* b2, float* gate, void* workspace, size_t workspace_bytes, void* stream) {
@@ -673,11 +695,11 @@ extern "C" int moc_senet_forward(const float* x, int64_t n_rows, const float* w1
     MOC_CHECK_SHAPE(n_rows < (1ll << 31), "moc_senet_forward: too many rows");
     if (n_rows == 0) return MOC_OK;
     if (!use_simt_head()) {
-        if (workspace == nullptr || workspace_bytes < head_tc_workspace_bytes()) {
-            set_error("moc_senet_forward: workspace %zu B < required %zu B", workspace_bytes, head_tc_workspace_bytes());
+        if (workspace == nullptr || workspace_bytes < head_ws_bytes()) {
+            set_error("moc_senet_forward: workspace %zu B < required %zu B", workspace_bytes, head_ws_bytes());
             return MOC_E_WORKSPACE;
         }
-        return launch_head_rows_tc(x, nullptr, 0, 0, nullptr, n_rows, w1, b1, w2, b2, 0u, gate, nullptr, workspace,
+        return launch_head_rows_mma(x, nullptr, 0, 0, nullptr, n_rows, w1, b1, w2, b2, 0u, gate, nullptr, workspace,
                                    (cudaStream_t)stream);
     }
     const size_t smem = (size_t)(H + HR_TM) * HR_LD * sizeof(float);

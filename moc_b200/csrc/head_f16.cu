@@ -1,0 +1,425 @@
+// Gate MLP of the head on the 5th-generation tensor cores with FP16x3 operands (fp32-accurate), W1 resident in
+// shared memory.  Same contract as head_tc.cu (senet's Linear(512,64) for every selected patch, main_moc.py:303, fused
+// with ReLU, the 64->4 layer, the sigmoid and the classifier-bank combination, main_moc.py:390-403); this is the
+// default for up to 8 classes; head_tc.cu (3xTF32) serves wider class sets and stays selectable with MOC_HEAD_IMPL=tf32.
+//
+// Why: an M128 N64 K8 tf32 MMA reads 6 KB of operands for 32 cycles of tensor work, more than the 128 B/clk the
+// SM's shared memory delivers, and the producers' stores and the W1 bulk copies share that port (measured on the
+// TF32 kernel: no loads -> same time, no MMAs -> -26 %, neither -> -45 %).  FP16 operands halve every one of those
+// byte streams per unit of K, halve the number of producer -> MMA hand-offs per row, and the whole split W1
+// (64 x 512 x 2 halves = 128 KB) then fits in shared memory once per CTA instead of being streamed from L2 for every
+// row tile.  Measured: 0.274 -> 0.225 ms per 200 NSCLC slides; at C = 30, where the epilogue's 62 key loads and 30
+// stores per row weigh more, the 256-row TF32 kernel is still ahead (1.28 vs 1.47 ms per 100 slides), so
+// moc_head_forward uses this kernel up to 8 classes and head_tc.cu beyond.
+//
+// Precision: x * 2^4 = a0 + a1 and w * 2^SW = b0 + b1 with a0, b0 the nearest FP16 and a1, b1 the FP16 of the
+// remainder (exact to 2^-22 relative, or 2^-29 absolute on x where a1 becomes subnormal); D = a0 b0 + a0 b1 + a1 b0
+// with fp32 accumulation in TMEM - FP16 products are exact in fp32 - then scaled back by 2^-(4+SW).  SW is chosen on
+// the device from max|W1|.  Same error class as 3xTF32 (measured ~1e-6 relative on the gate pre-activations).
+// Domain: |x| < 4094; larger (or non-finite) features give non-finite gates, hence non-finite bag logits.
+//
+// Structure (persistent, one CTA per SM, 21 warps; work item = 128 selected-row slots):
+//   warps 0-3   epilogue: tcgen05.ld the 128x64 accumulator (thread = row), descale, +b1, ReLU, 4x64 second layer,
+//               sigmoid, gated combination with the row's key planes, stores
+//   warps 4-19  A producers: per 64-wide K-block gather 256 B of 8 rows each (32 B per thread and row, HF_PF
+//               K-blocks of loads in flight per thread, across tile boundaries), split into FP16 halves in registers,
+//               one 16-byte store each into the 128B-swizzled K-major a0 / a1 tiles.  Sixteen warps, not eight: a
+//               producer's ~100 dependent ALU / store / fence instructions per K-block are latency-bound, and two
+//               warps per scheduler could not hide that (0.2 IPC per scheduler in the TF32 kernel)
+//   warp 20     MMA issuer (one elected lane): 4 k-steps x 3 products of tcgen05.mma.kind::f16 M128 N64 K16
+// Three A stages of {a0 16K, a1 16K}; W1 image 8 x {b0 8K, b1 8K}; two TMEM accumulators.
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace moc {
+
+constexpr int HF_H = MOC_HIDDEN;   // 64 (UMMA N)
+constexpr int HF_G = MOC_GATES;
+constexpr int HF_M = 128;          // rows per tile (UMMA M)
+constexpr int HF_KB = 64;          // K elements per stage (one 128-byte swizzle row of halves)
+constexpr int HF_NKB = D / HF_KB;  // 8
+constexpr int HF_STAGES = 3;
+constexpr int HF_PF = 2;           // K-block register sets (4 x 16 B) a producer thread keeps in flight: 64 KB per CTA
+constexpr int HF_RPT = 2;          // (row, 32-byte chunk) items per producer thread and K-block
+constexpr int HF_SX = 4;           // features are split as x * 2^4
+constexpr int HF_A_BYTES = HF_M * 128;            // 16 KB per component
+constexpr int HF_STAGE_BYTES = 2 * HF_A_BYTES;    // 32 KB
+constexpr int HF_B_BYTES = HF_H * 128;            // 8 KB per component and K-block
+constexpr int HF_BIMG_BYTES = HF_NKB * 2 * HF_B_BYTES;  // 128 KB
+constexpr int HF_EPI_WARPS = 4, HF_PROD_WARPS = 16;  // 16 producer warps: 4 per scheduler, enough to hide their own ALU / store latency
+constexpr int HF_WARP_MMA = HF_EPI_WARPS + HF_PROD_WARPS;  // 20
+constexpr int HF_THREADS = (HF_WARP_MMA + 1) * 32;         // 672
+constexpr int HF_TMEM_COLS = 128;
+constexpr size_t HF_SMEM = (size_t)HF_BIMG_BYTES + (size_t)HF_STAGES * HF_STAGE_BYTES + 1024;
+
+struct HeadF16Tail {   // after the W1 image in the workspace
+    float scale, descale;
+    int pad0, pad1;
+};
+
+// D=f32, A=B=f16, both K-major, N=64, M=128
+constexpr uint32_t HF_IDESC = (1u << 4) | ((uint32_t)(HF_H >> 3) << 17) | ((uint32_t)(HF_M >> 4) << 24);
+
+__device__ __forceinline__ uint64_t hf_desc_sw128(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3fffu) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ void hf_umma(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(a_desc), "l"(b_desc), "r"(HF_IDESC), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+        : "memory");
+}
+__device__ __forceinline__ void hf_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void hf_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void hf_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void hf_tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32"
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15,"
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31},"
+        "[%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// 8 floats (already scaled) -> 8 halves hi + 8 halves lo, packed as two 16-byte chunks
+__device__ __forceinline__ void hf_split8(const float4& u, const float4& v, float s, uint4& hi, uint4& lo) {
+    const float x[8] = {u.x * s, u.y * s, u.z * s, u.w * s, v.x * s, v.y * s, v.z * s, v.w * s};
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const __half2 a = __floats2half2_rn(x[2 * p], x[2 * p + 1]);
+        const float2 f = __half22float2(a);
+        const __half2 b = __floats2half2_rn(x[2 * p] - f.x, x[2 * p + 1] - f.y);
+        h[p] = *reinterpret_cast<const uint32_t*>(&a);
+        l[p] = *reinterpret_cast<const uint32_t*>(&b);
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+__device__ __forceinline__ void sts128u(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// One block.  SW = 13 - floor(log2(max|W1|)) so that max|w| * 2^SW lies in [2^13, 2^14); W1 [64][512] -> per K-block
+// (64) one tile {b0: 64 rows x 128 B | b1: 64 rows x 128 B} in the swizzled K-major layout, then the tail.
+__global__ void __launch_bounds__(1024)
+head_f16_prep_kernel(const float* __restrict__ w1, unsigned char* __restrict__ img) {
+    __shared__ float red[32];
+    __shared__ float scale_s;
+    float m = 0.f;
+    for (int i = threadIdx.x; i < HF_H * D; i += blockDim.x) {
+        const float a = fabsf(w1[i]);
+        if (a <= 3.0e38f) m = fmaxf(m, a);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, red[w]);
+        int sw = 0;
+        if (m > 0.f) sw = 13 - ilogbf(m);
+        sw = sw > 100 ? 100 : (sw < -100 ? -100 : sw);
+        scale_s = ldexpf(1.0f, sw);
+        HeadF16Tail* tail = reinterpret_cast<HeadF16Tail*>(img + HF_BIMG_BYTES);
+        tail->scale = scale_s;
+        tail->descale = ldexpf(1.0f, -(HF_SX + sw));
+        tail->pad0 = tail->pad1 = 0;
+    }
+    __syncthreads();
+    const float sc = scale_s;
+    for (int i = threadIdx.x; i < HF_H * (D / 8); i += blockDim.x) {   // one 8-element chunk of W1
+        const int n = i / (D / 8), c8 = i % (D / 8);
+        const int kb = c8 / 8, chunk = c8 % 8;
+        const float4 u = reinterpret_cast<const float4*>(w1 + (size_t)n * D)[2 * c8];
+        const float4 v = reinterpret_cast<const float4*>(w1 + (size_t)n * D)[2 * c8 + 1];
+        uint4 hi, lo;
+        hf_split8(u, v, sc, hi, lo);
+        unsigned char* tile = img + (size_t)kb * 2 * HF_B_BYTES;
+        const int off = n * 128 + ((chunk ^ (n & 7)) << 4);
+        *reinterpret_cast<uint4*>(tile + off) = hi;
+        *reinterpret_cast<uint4*>(tile + HF_B_BYTES + off) = lo;
+    }
+}
+
+__device__ __forceinline__ bool hf_tile_has_rows(const int32_t* __restrict__ sel_rows, int64_t slot0, int64_t n_slots,
+                                                 int lane) {
+    if (sel_rows == nullptr) return true;
+    bool any = false;
+#pragma unroll
+    for (int i = 0; i < HF_M / 32; ++i) {
+        const int64_t s = slot0 + lane + 32 * i;
+        any |= (s < n_slots) && (sel_rows[s] >= 0);
+    }
+    return __any_sync(FULL, any);
+}
+
+__global__ void __launch_bounds__(HF_THREADS, 1)
+head_rows_f16_kernel(const float* __restrict__ feat, const float* __restrict__ keys, int64_t key_stride, int C,
+                     const int32_t* __restrict__ sel_rows, int64_t n_slots, const unsigned char* __restrict__ img,
+                     const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
+                     unsigned active_mask, float* __restrict__ gate, float* __restrict__ final_scores) {
+    extern __shared__ unsigned char hf_smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[HF_STAGES], empty_bar[HF_STAGES], tfull_bar[2], tempty_bar[2], b_bar;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float w2s[HF_G * HF_H], b1s[HF_H], b2s[HF_G];
+
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(hf_smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* bsm = smem;                       // resident W1 image
+    unsigned char* asm_ = smem + HF_BIMG_BYTES;      // A stages
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (tid < HF_G * HF_H) w2s[tid] = w2[tid];
+    if (tid < HF_H) b1s[tid] = b1[tid];
+    if (tid < HF_G) b2s[tid] = b2[tid];
+    if (tid == 0) {
+        for (int s = 0; s < HF_STAGES; ++s) {
+            mbar_init(&full_bar[s], HF_PROD_WARPS);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tfull_bar[a], 1);
+            mbar_init(&tempty_bar[a], HF_EPI_WARPS);
+        }
+        mbar_init(&b_bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == HF_WARP_MMA) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                     "r"((uint32_t)HF_TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    hf_fence_before();
+    __syncthreads();
+    hf_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    const int64_t n_tiles = (n_slots + HF_M - 1) / HF_M;
+    const float descale = reinterpret_cast<const HeadF16Tail*>(img + HF_BIMG_BYTES)->descale;
+
+    if (warp >= HF_EPI_WARPS && warp < HF_WARP_MMA) {
+        // =============================== A producers ===============================================
+        const int pw = warp - HF_EPI_WARPS;      // 0..15 : rows 8*pw .. 8*pw+7 of the tile
+        const int rsub = lane >> 3, chunk = lane & 7;
+        uint32_t roff[HF_RPT];
+#pragma unroll
+        for (int i = 0; i < HF_RPT; ++i) {
+            const int r = pw * (4 * HF_RPT) + i * 4 + rsub;
+            roff[i] = (uint32_t)(r * 128 + ((chunk ^ (r & 7)) << 4));
+        }
+        const uint32_t a_base = smem_u32(asm_);
+        const float sx = (float)(1 << HF_SX);
+        int64_t ltile = blockIdx.x;
+        int lkb = 0;
+        const float4* lsrc[HF_RPT];
+        auto seek = [&]() {  // move ltile to the next tile with rows and fetch its row pointers
+            while (ltile < n_tiles && !hf_tile_has_rows(sel_rows, ltile * HF_M, n_slots, lane)) ltile += gridDim.x;
+            if (ltile >= n_tiles) return;
+#pragma unroll
+            for (int i = 0; i < HF_RPT; ++i) {
+                const int64_t sl = ltile * HF_M + pw * (4 * HF_RPT) + i * 4 + rsub;
+                int64_t row = -1;
+                if (sl < n_slots) row = sel_rows ? (int64_t)sel_rows[sl] : sl;
+                lsrc[i] = row >= 0 ? reinterpret_cast<const float4*>(feat + row * D) + chunk * 2 : nullptr;
+            }
+        };
+        auto issue = [&](float4 (&b)[2 * HF_RPT]) -> bool {  // load the cursor's step into b and advance; false when done
+            if (ltile >= n_tiles) return false;
+#pragma unroll
+            for (int i = 0; i < HF_RPT; ++i) {
+                if (lsrc[i]) {
+                    b[2 * i] = __ldg(lsrc[i] + lkb * (HF_KB / 4));
+                    b[2 * i + 1] = __ldg(lsrc[i] + lkb * (HF_KB / 4) + 1);
+                } else {
+                    b[2 * i] = b[2 * i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+            if (++lkb == HF_NKB) {
+                lkb = 0;
+                ltile += gridDim.x;
+                seek();
+            }
+            return true;
+        };
+        float4 buf[HF_PF][2 * HF_RPT];
+        bool pending[HF_PF];
+        seek();
+#pragma unroll
+        for (int s = 0; s < HF_PF; ++s) pending[s] = issue(buf[s]);
+        int stage = 0;
+        uint32_t parity = 0;
+        while (pending[0]) {
+#pragma unroll
+            for (int s = 0; s < HF_PF; ++s) {
+                if (pending[s]) {
+                    uint4 hi[HF_RPT], lo[HF_RPT];
+#pragma unroll
+                    for (int i = 0; i < HF_RPT; ++i) hf_split8(buf[s][2 * i], buf[s][2 * i + 1], sx, hi[i], lo[i]);
+                    mbar_wait(&empty_bar[stage], parity ^ 1u);
+                    const uint32_t a0 = a_base + stage * HF_STAGE_BYTES, a1 = a0 + HF_A_BYTES;
+#pragma unroll
+                    for (int i = 0; i < HF_RPT; ++i) {
+                        sts128u(a0 + roff[i], hi[i]);
+                        sts128u(a1 + roff[i], lo[i]);
+                    }
+                    fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async proxy
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&full_bar[stage]);
+                    if (++stage == HF_STAGES) { stage = 0; parity ^= 1u; }
+                    pending[s] = issue(buf[s]);
+                }
+            }
+        }
+    } else if (warp == HF_WARP_MMA) {
+        // =============================== MMA issuer ================================================
+        if (lane == 0) {   // W1 image -> shared memory, once per CTA
+            const uint64_t policy = l2_policy_evict_last();
+            mbar_arrive_expect_tx(&b_bar, HF_BIMG_BYTES);
+            for (int kb = 0; kb < HF_NKB; ++kb)
+                bulk_g2s(bsm + (size_t)kb * 2 * HF_B_BYTES, img + (size_t)kb * 2 * HF_B_BYTES, 2 * HF_B_BYTES, &b_bar, policy);
+            mbar_wait(&b_bar, 0);
+        }
+        __syncwarp();
+        int stage = 0, acc = 0;
+        uint32_t parity = 0, acc_parity = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            if (!hf_tile_has_rows(sel_rows, tile * HF_M, n_slots, lane)) continue;
+            if (lane == 0) {
+                mbar_wait(&tempty_bar[acc], acc_parity ^ 1u);  // epilogue has drained this accumulator
+                hf_fence_after();
+            }
+            __syncwarp();
+            const uint32_t tmem_d = tmem_base + acc * HF_H;
+            for (int kb = 0; kb < HF_NKB; ++kb) {
+                if (lane == 0) {
+                    mbar_wait(&full_bar[stage], parity);
+                    hf_fence_after();
+                    const uint32_t a0 = smem_u32(asm_ + (size_t)stage * HF_STAGE_BYTES);
+                    const uint32_t a1 = a0 + HF_A_BYTES;
+                    const uint32_t b0 = smem_u32(bsm + (size_t)kb * 2 * HF_B_BYTES);
+                    const uint32_t bl = b0 + HF_B_BYTES;
+#pragma unroll
+                    for (int ks = 0; ks < HF_KB / 16; ++ks) {
+                        const uint32_t o = ks * 32;  // 16 halves = 32 bytes along K inside the swizzled row
+                        const uint64_t da0 = hf_desc_sw128(a0 + o), da1 = hf_desc_sw128(a1 + o);
+                        const uint64_t db0 = hf_desc_sw128(b0 + o), db1 = hf_desc_sw128(bl + o);
+                        hf_umma(tmem_d, da0, db1, (kb | ks) != 0 ? 1u : 0u);
+                        hf_umma(tmem_d, da1, db0, 1u);
+                        hf_umma(tmem_d, da0, db0, 1u);
+                    }
+                    hf_commit(&empty_bar[stage]);               // stage free once these MMAs have read it
+                    if (kb == HF_NKB - 1) hf_commit(&tfull_bar[acc]);  // accumulator complete
+                }
+                __syncwarp();
+                if (++stage == HF_STAGES) { stage = 0; parity ^= 1u; }
+            }
+            if (++acc == 2) { acc = 0; acc_parity ^= 1u; }
+        }
+    } else {
+        // =============================== epilogue (warps 0-3) =======================================
+        const float a0 = (active_mask & MOC_CLS_TOPK) ? 1.f : 0.f;
+        const float a1 = (active_mask & MOC_CLS_DELTA_SOFTMAX) ? 1.f : 0.f;
+        const float a2 = (active_mask & MOC_CLS_DELTA_DIFF) ? 1.f : 0.f;
+        const float a3 = (active_mask & MOC_CLS_BOTTOMK) ? 1.f : 0.f;
+        int acc = 0;
+        uint32_t acc_parity = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int64_t slot0 = tile * HF_M;
+            if (!hf_tile_has_rows(sel_rows, slot0, n_slots, lane)) continue;
+            const int64_t slot = slot0 + warp * 32 + lane;
+            int64_t row = -1;
+            if (slot < n_slots) row = sel_rows ? (int64_t)sel_rows[slot] : slot;
+            mbar_wait(&tfull_bar[acc], acc_parity);
+            hf_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * HF_H;
+            float z[HF_G] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                float d[32];
+                hf_tmem_ld32(taddr + half * 32, d);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int jj = half * 32 + j;
+                    const float h = relu_nan(fmaf(d[j], descale, b1s[jj]));
+#pragma unroll
+                    for (int m = 0; m < HF_G; ++m) z[m] = fmaf(h, w2s[m * HF_H + jj], z[m]);
+                }
+            }
+            hf_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);  // accumulator is in registers: MMA may reuse it
+            if (++acc == 2) { acc = 0; acc_parity ^= 1u; }
+            if (row < 0) continue;
+            float g[HF_G];
+#pragma unroll
+            for (int m = 0; m < HF_G; ++m) g[m] = sigmoidf_exact(z[m] + b2s[m]);
+            if (gate != nullptr) *reinterpret_cast<float4*>(gate + slot * HF_G) = make_float4(g[0], g[1], g[2], g[3]);
+            if (final_scores == nullptr) continue;
+            const float* kp = keys + row;
+            const float dlt = kp[(int64_t)(2 * C) * key_stride];
+            const float bgm = kp[(int64_t)(2 * C + 2) * key_stride];
+            for (int c0 = 0; c0 < C; c0 += 4) {   // four classes at a time, their eight key loads issued together
+                float lt[4], ls[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int cc = c0 + u < C ? c0 + u : C - 1;
+                    lt[u] = kp[(int64_t)cc * key_stride];
+                    ls[u] = kp[(int64_t)(C + cc) * key_stride];
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (c0 + u < C) {
+                        float f = a0 * __fmul_rn(g[0], lt[u]);
+                        f = __fadd_rn(f, a1 * __fmul_rn(g[1], ls[u]));
+                        f = __fadd_rn(f, a2 * __fmul_rn(g[2], dlt));
+                        f = __fadd_rn(f, a3 * __fmul_rn(g[3], bgm));
+                        final_scores[slot * C + c0 + u] = f;
+                    }
+                }
+            }
+        }
+    }
+
+    hf_fence_before();
+    __syncthreads();
+    if (warp == HF_WARP_MMA) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)HF_TMEM_COLS)
+                     : "memory");
+    }
+}
+
+size_t head_f16_workspace_bytes() { return (size_t)HF_BIMG_BYTES + sizeof(HeadF16Tail); }
+
+int launch_head_rows_f16(const float* feat, const float* keys, int64_t key_stride, int C, const int32_t* sel_rows,
+                         int64_t n_slots, const float* w1, const float* b1, const float* w2, const float* b2,
+                         unsigned active_mask, float* gate, float* final_scores, void* workspace, cudaStream_t st) {
+    unsigned char* img = reinterpret_cast<unsigned char*>(workspace);
+    head_f16_prep_kernel<<<1, 1024, 0, st>>>(w1, img);
+    MOC_LAUNCH_CHECK("head_f16_prep_kernel");
+    MOC_CUDA(cudaFuncSetAttribute(head_rows_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HF_SMEM));
+    const int64_t n_tiles = (n_slots + HF_M - 1) / HF_M;
+    const int grid = (int)(n_tiles < sm_count() ? n_tiles : sm_count());
+    head_rows_f16_kernel<<<grid, HF_THREADS, HF_SMEM, st>>>(feat, keys, key_stride, C, sel_rows, n_slots, img, b1, w2, b2,
+                                                           active_mask, gate, final_scores);
+    MOC_LAUNCH_CHECK("head_rows_f16_kernel");
+    return MOC_OK;
+}
+
+}  // namespace moc

@@ -316,7 +316,7 @@ head_rows_tc_kernel(const float* __restrict__ feat, const float* __restrict__ ke
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const int jj = half * 32 + j;
-                        const float h = fmaxf(d[j] + b1s[jj], 0.f);
+                        const float h = relu_nan(d[j] + b1s[jj]);
 #pragma unroll
                         for (int m = 0; m < TC_G; ++m) z[sub][m] = fmaf(h, w2s[m * TC_H + jj], z[sub][m]);
                     }

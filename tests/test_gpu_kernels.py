@@ -419,9 +419,34 @@ def test_tensor_core_head_matches_cuda_core_head():
             "p=O.SenetParams.init(11);q=ops.HeadParams(p.w1.cuda(),p.b1.cuda(),p.w2.cuda(),p.b2.cuda());"
             "torch.save(ops.senet_forward(x.cuda(),q).cpu(),sys.argv[1])") % os.path.dirname(os.path.dirname(__file__))
     out = "/tmp/moc_simt_gate.pt"
-    subprocess.run([sys.executable, "-c", code, out], check=True, env=dict(os.environ, MOC_HEAD_IMPL="simt"), timeout=120)
-    g_simt = torch.load(out)
-    assert (g_tc - g_simt).abs().max().item() < 2e-6
+    for impl in ("simt", "tf32", "f16"):   # default (auto) above = FP16x3 here; every kernel against the others
+        subprocess.run([sys.executable, "-c", code, out], check=True, env=dict(os.environ, MOC_HEAD_IMPL=impl), timeout=120)
+        g_other = torch.load(out)
+        assert (g_tc - g_other).abs().max().item() < 2e-6, impl
+
+
+def test_head_f16_domain():
+    """The FP16x3 gate kernel splits x * 16 into two halves: |x| < 4094 is its domain.  Inside it, rows of very
+    different magnitudes (1e-6 .. 2000) stay fp32-accurate; outside it the gate comes out non-finite (loud), which is
+    what MOC_HEAD_IMPL=tf32 is for."""
+    from moc_b200 import ops
+    gen = torch.Generator().manual_seed(5)
+    x = torch.randn(512, 512, generator=gen)
+    scale = torch.logspace(-6, 2.7, 512).unsqueeze(1)          # row magnitudes 1e-6 .. 500 (entries up to ~2000)
+    x = x * scale
+    oprm = O.SenetParams.init(13)
+    prm = ops.HeadParams(oprm.w1.to(DEV), oprm.b1.to(DEV), oprm.w2.to(DEV), oprm.b2.to(DEV))
+    g32, _ = O.senet_forward(oprm, x)
+    h64 = torch.relu(x.double() @ oprm.w1.double().t() + oprm.b1.double())
+    g64 = torch.sigmoid(h64 @ oprm.w2.double().t() + oprm.b2.double())
+    got = ops.senet_forward(x.to(DEV), prm).cpu()
+    assert torch.isfinite(got).all()
+    # pre-activations reach the hundreds here, so fp32 itself is ~1e-5 off float64: the kernel must be as good
+    err32 = (g32.double() - g64).abs().max().item()
+    assert (got.double() - g64).abs().max().item() <= 3 * err32 + 2e-6
+    x[7, 3] = 5000.0
+    bad = ops.senet_forward(x.to(DEV), prm).cpu()
+    assert not torch.isfinite(bad[7]).all() and torch.isfinite(bad[8:]).all()
 
 
 @pytest.mark.parametrize("name", ["bank_rcc_ext", "bank_stress"])
