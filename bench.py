@@ -328,7 +328,8 @@ def run_ours(a):
     e2e = None
     if not a.no_e2e:
         n_host = min(a.e2e_host_slides, a.slides)
-        while n_host > 1 and store.offsets_h[n_host] > 2_621_440:  # keep the pinned pool within ~5.4 GB
+        pool_rows = 2_621_440 if world <= 4 else 1_310_720   # pinned pool per rank: ~5.4 GB, ~2.7 GB on an 8-GPU box
+        while n_host > 1 and store.offsets_h[n_host] > pool_rows:
             n_host -= 1
         per_chunk = 32
         chunks = []
