@@ -17,6 +17,7 @@ _LAZY = {
     "set_prompts": "loops", "main": "loops",
     "MocEngine": "engine", "RaggedBagStore": "bag_store", "BagDataset": "bag_store", "BagLoader": "bag_store",
     "MocError": "_lib",
+    "Generic_MIL_Dataset": "datasets", "Generic_Split": "datasets", "Generic_WSI_Classification_Dataset": "datasets",
     "Conch_CLIP_Ada": "mil_heads", "CLAM_SB": "mil_heads", "MIL_fc": "mil_heads", "Attn_Net_Gated": "mil_heads",
 }
 

@@ -55,21 +55,26 @@ def get_args(argv=None):
 
 
 def _real_stores(args, device):
-    import pandas as pd
-    from .bag_store import RaggedBagStore
+    from .datasets import Generic_MIL_Dataset
     n_classes, names, _, _ = DATASETS[args.dataset]
-    df = pd.read_csv(args.csv, dtype={"slide_id": str})
-    lab = {n: i for i, n in enumerate(names)} if names else None
-    df["y"] = df["label"].map(lab) if lab else df["label"].astype("category").cat.codes
-    splits = pd.read_csv(args.splits_csv, dtype=str)
+    if names:
+        label_dict = {n: i for i, n in enumerate(names)}
+    else:   # no label names shipped for this dataset (ebrains30): classes in order of first appearance in the csv
+        import pandas as pd
+        label_dict = {n: i for i, n in enumerate(pd.read_csv(args.csv, dtype=str)["label"].drop_duplicates())}
+    # main_moc.py:268-289
+    dataset = Generic_MIL_Dataset(csv_path=args.csv, data_dir=args.data_dir, shuffle=False, seed=1, print_info=True,
+                                  label_dict=label_dict, patient_strat=False, ignore=[])
+    # h5_files/ as the reference's driver reads them (load_from_h5(True)); pt_files/ when only those exist
+    use_h5 = os.path.isdir(os.path.join(args.data_dir, "h5_files"))
+    splits = dataset.return_splits(from_id=False, csv_path=args.splits_csv, repeat_num=int(args.shot) * n_classes)
     out = []
-    for key in ("train", "val", "test"):
-        ids = set(splits[key].dropna().tolist())
-        part = df[df["slide_id"].isin(ids)]  # dataset-csv order, as get_split_from_df (dataset_generic.py:206-207)
-        ids_, ys = part["slide_id"].tolist(), part["y"].tolist()
-        # h5_files/ first, as the reference's loader does with use_h5 (dataset_generic.py:424-430); else pt_files/
-        use_h5 = os.path.isdir(os.path.join(args.data_dir, "h5_files"))
-        out.append((RaggedBagStore.from_h5_dir if use_h5 else RaggedBagStore.from_pt_dir)(args.data_dir, ids_, ys, device))
+    for sp in splits:
+        if sp is None:
+            raise SystemExit("the split file %s leaves a split empty" % args.splits_csv)
+        sp.load_full_path(True)
+        sp.load_from_h5(use_h5)
+        out.append(sp.to_store(device))
     return out
 
 

@@ -109,3 +109,53 @@ def test_config4_ebrains30_shapes_short():
         for k in r:
             _same(g[k], r[k], "epoch %d %s" % (e, k))
     assert best == g_best
+
+
+def test_cli_on_h5_dataset_directory(tmp_path):
+    """python -m moc_b200.main_moc on a CLAM-style dataset directory: dataset csv + split csv + h5_files/*.h5 (read by
+    the native HDF5 reader into the ragged store) + cached prompt matrices, as the reference's driver consumes them
+    (main_moc.py:268-293).  The zero-shot metrics it writes must equal the oracle's on the same bags in the
+    reference's split order, and a 2-epoch few-shot run must complete and write the reference's output files."""
+    import json
+    import os
+    import subprocess
+    import sys
+    from moc_b200 import synthetic
+    from tests.h5_writer import write_h5
+    c, n = 3, 900
+    names = ["KICH", "KIRC", "KIRP"]
+    w, we = synthetic.prompt_matrices(c)
+    root = str(tmp_path)
+    os.makedirs(os.path.join(root, "feats", "h5_files"))
+    rows, bags = [], {}
+    for i in range(21):
+        sid, y = "slide_%03d" % i, i % c
+        x = synthetic.make_bag(n + 13 * i, y, we, c, seed=900 + i)
+        bags[sid] = (x, y)
+        rows.append(("case_%d" % i, sid, names[y]))
+        write_h5(os.path.join(root, "feats", "h5_files", sid + ".h5"),
+                 {"features": x.numpy(), "coords": np.zeros((x.size(0), 2), np.int64)}, batch=256)
+    with open(os.path.join(root, "data.csv"), "w") as f:
+        f.write("case_id,slide_id,label\n" + "".join("%s,%s,%s\n" % r for r in rows))
+    split = {"train": ["slide_%03d" % i for i in (5, 0, 1, 2, 4, 3)], "val": ["slide_%03d" % i for i in range(6, 12)],
+             "test": ["slide_%03d" % i for i in range(12, 21)]}
+    with open(os.path.join(root, "splits_0.csv"), "w") as f:
+        f.write(",train,val,test\n")
+        for i in range(9):
+            f.write("%d,%s\n" % (i, ",".join(split[k][i] if i < len(split[k]) else "" for k in ("train", "val", "test"))))
+    torch.save(w, os.path.join(root, "w.pt"))
+    torch.save(we, os.path.join(root, "we.pt"))
+    res = os.path.join(root, "results")
+    cmd = [sys.executable, "-m", "moc_b200.main_moc", "--dataset", "rcc", "--shot", "2", "--fold", "0", "--topj", "50",
+           "--topk", "10", "--epochs", "2", "--seed", "3", "--data_dir", os.path.join(root, "feats"), "--csv",
+           os.path.join(root, "data.csv"), "--splits_csv", os.path.join(root, "splits_0.csv"), "--weights",
+           os.path.join(root, "w.pt"), "--weights_ext", os.path.join(root, "we.pt"), "--result_dir", res]
+    subprocess.run(cmd, check=True, timeout=600, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    zs = json.load(open(os.path.join(res, "zs_results_shot_2_fold_0.json")))
+    for key in ("train", "val", "test"):
+        ids = sorted(split[key])                       # dataset-csv order = sorted here
+        ds = O.BagList([bags[s][0] for s in ids], [bags[s][1] for s in ids], repeat_num=6 if key == "train" else None)
+        _same(zs["zs_" + key], O.zs_evaluation(ds, w, we, c, 10), "zs_" + key)
+    best = json.load(open(os.path.join(res, "best_results_shot_2_fold_0.json")))
+    assert set(best) >= {"zero_shot_test", "best_val", "test_at_best_val", "test_acc_at_best_val", "best_epoch", "best_model_path"}
+    assert os.path.exists(os.path.join(res, "best_model_shot_2_fold_0.pt"))
