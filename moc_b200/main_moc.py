@@ -38,6 +38,8 @@ def get_args(argv=None):
     p.add_argument("--load_weight", type=bool, default=True, help="load stored classifier weight")
     p.add_argument("--check_zeroshot", type=bool, default=True, help="get zero-shot results")
     p.add_argument("--ablation_study", type=str, default="none", choices=["none", "avg", "sum", "max"])
+    p.add_argument("--summary", action="store_true", help="summary results, no training")
+    p.add_argument("--summary_dir", type=str, default="")
     # additions
     p.add_argument("--synthetic", action="store_true", help="synthetic CONCH-shaped bags and random prompt matrices")
     p.add_argument("--n_patches", type=int, default=8000)
@@ -52,6 +54,60 @@ def get_args(argv=None):
     p.add_argument("--weights", type=str, default=None)
     p.add_argument("--weights_ext", type=str, default=None)
     return p.parse_args(argv)
+
+
+def summarize_results(summary_dir: str, shots=(1, 2, 4, 8), folds=(0, 1, 2, 3, 4)) -> None:
+    """``--summary`` (main_moc.py:53-130): per shot, collect the five folds' result files under
+    ``<summary_dir>/<shot>_shot`` into ``<summary_dir>/summary_<shot>.csv`` with a trailing "mean" row.  Three file
+    shapes are tried in the reference's order: best_results with zero-shot numbers (columns fold, test_auc,
+    zs_test_auc, test_acc, zs_test_acc), best_results without them (fold, test_auc, test_acc), ablation results
+    (fold, auc, acc); a shot whose files fit none prints "shot <n> summary failed"."""
+    import glob
+    import json
+
+    import numpy as np
+    import pandas as pd
+
+    def load(shot_dir, shot, fold, pattern="best_results"):
+        if pattern is None:
+            path = glob.glob(os.path.join(shot_dir, "*_shot_%d_fold_%d.json" % (shot, fold)))[0]
+        else:
+            path = os.path.join(shot_dir, "%s_shot_%d_fold_%d.json" % (pattern, shot, fold))
+        with open(path) as f:
+            return json.load(f)
+
+    def table(shot_dir, shot, columns, pattern="best_results"):
+        cols = {name: [] for name in columns}
+        for fold in folds:
+            res = load(shot_dir, shot, fold, pattern)
+            for name, pick in columns.items():
+                cols[name].append(pick(res))
+        out = {"fold": list(folds) + ["mean"]}
+        for name, vals in cols.items():
+            out[name] = vals + [np.mean(vals)]
+        return pd.DataFrame(out)
+
+    shapes = [
+        ({"test_auc": lambda r: r["test_at_best_val"], "zs_test_auc": lambda r: r["zero_shot_test"]["auc"],
+          "test_acc": lambda r: r["test_acc_at_best_val"], "zs_test_acc": lambda r: r["zero_shot_test"]["acc"]}, "best_results"),
+        ({"test_auc": lambda r: r["test_at_best_val"], "test_acc": lambda r: r["test_acc_at_best_val"]}, "best_results"),
+        ({"auc": lambda r: r["auc"], "acc": lambda r: r["acc"]}, None),
+    ]
+    print("start summary")
+    for shot in shots:
+        shot_dir = summary_dir + "/%d_shot" % shot
+        summary_file = os.path.join(summary_dir, "summary_%d.csv" % shot)
+        for columns, pattern in shapes:
+            try:
+                if os.path.exists(summary_file):
+                    os.remove(summary_file)
+                table(shot_dir, shot, columns, pattern).to_csv(summary_file, index=False)
+                break
+            except Exception:
+                continue
+        else:
+            print("shot %d summary failed" % shot)
+    print("end summary")
 
 
 def _real_stores(args, device):
@@ -84,6 +140,9 @@ def run(args):
     from .dist import Shard, init_from_env
     from .model import senet
 
+    if getattr(args, "summary", False):      # no training, no GPU (main_moc.py:53-130)
+        summarize_results(args.summary_dir)
+        return None
     rank, local, world = init_from_env()
     if not torch.cuda.is_available():
         raise SystemExit("moc_b200 needs a CUDA device: there is no CPU path")

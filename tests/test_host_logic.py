@@ -147,3 +147,60 @@ def test_gloo_world2_gather_and_allreduce(tmp_path):
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, o
         assert "rank %d ok" % r in o
+
+
+def _summary_tree(root):
+    import json
+    os.makedirs(os.path.join(root, "1_shot"))
+    os.makedirs(os.path.join(root, "2_shot"))
+    os.makedirs(os.path.join(root, "4_shot"))
+    for fold in range(5):
+        full = {"zero_shot_test": {"loss": 1.0, "acc": 0.5 + 0.01 * fold, "auc": 0.6 + 0.02 * fold}, "best_val": 0.9,
+                "test_at_best_val": 0.7 + 0.03 * fold, "test_acc_at_best_val": 0.65 + 0.01 * fold, "best_epoch": fold}
+        json.dump(full, open(os.path.join(root, "1_shot", "best_results_shot_1_fold_%d.json" % fold), "w"))
+        nozs = dict(full, zero_shot_test=-1)          # --check_zeroshot off: main_moc.py:599 leaves -1
+        json.dump(nozs, open(os.path.join(root, "2_shot", "best_results_shot_2_fold_%d.json" % fold), "w"))
+        abl = {"loss": 0.3, "acc": 0.8 - 0.01 * fold, "auc": 0.85 + 0.01 * fold}
+        json.dump(abl, open(os.path.join(root, "4_shot", "ablation_results_avg_shot_4_fold_%d.json" % fold), "w"))
+
+
+def test_cli_summary_mode(tmp_path, capsys):
+    """--summary / --summary_dir (main_moc.py:53-130): the three result-file shapes, the trailing mean row, the
+    "summary failed" line for a shot without files; compared with the reference's own block where it is present."""
+    import types
+    import pandas as pd
+    from moc_b200 import main_moc
+    ours = str(tmp_path / "ours")
+    _summary_tree(ours)
+    main_moc.run(main_moc.get_args(["--summary", "--summary_dir", ours]))
+    out = capsys.readouterr().out
+    assert "start summary" in out and "shot 8 summary failed" in out and "end summary" in out
+    s1 = pd.read_csv(os.path.join(ours, "summary_1.csv"))
+    assert list(s1.columns) == ["fold", "test_auc", "zs_test_auc", "test_acc", "zs_test_acc"]
+    assert s1["fold"].tolist() == ["0", "1", "2", "3", "4", "mean"] and abs(s1["test_auc"].iloc[-1] - 0.76) < 1e-12
+    assert list(pd.read_csv(os.path.join(ours, "summary_2.csv")).columns) == ["fold", "test_auc", "test_acc"]
+    s4 = pd.read_csv(os.path.join(ours, "summary_4.csv"))
+    assert list(s4.columns) == ["fold", "auc", "acc"] and abs(s4["acc"].iloc[-1] - 0.78) < 1e-12
+    assert not os.path.exists(os.path.join(ours, "summary_8.csv"))
+
+    from oracle import ref_loader
+    if not ref_loader.available():
+        return
+    import ast
+    import json
+    from glob import glob
+    import numpy as np
+    path = os.path.join(ref_loader.REFERENCE_ROOT, "main_moc.py")
+    tree = ast.parse(open(path).read())
+    block = [n for n in tree.body if isinstance(n, ast.If) and isinstance(n.test, ast.Attribute) and n.test.attr == "summary"]
+    assert len(block) == 1
+    ref = str(tmp_path / "ref")
+    _summary_tree(ref)
+    glb = {"args": types.SimpleNamespace(summary=True, summary_dir=ref), "os": os, "json": json, "np": np, "pd": pd,
+           "glob": glob, "print": print, "exit": lambda *a: None}
+    exec(compile(ast.Module(body=block, type_ignores=[]), path, "exec"), glb)
+    for shot in (1, 2, 4):
+        a = open(os.path.join(ours, "summary_%d.csv" % shot)).read()
+        b = open(os.path.join(ref, "summary_%d.csv" % shot)).read()
+        assert a == b, shot
+    assert not os.path.exists(os.path.join(ref, "summary_8.csv"))
