@@ -34,7 +34,12 @@ NUM_PARAMS = _lib.NUM_PARAMS
 
 
 def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    """Raw handle of torch's current CUDA stream (every kernel is enqueued there).  The two C accessors are ~20x
+    cheaper than building a torch.cuda.Stream object, which showed up as a quarter of a training step's host time."""
+    try:
+        return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
+    except AttributeError:  # private accessors moved: fall back to the public object
+        return torch.cuda.current_stream().cuda_stream
 
 
 def _dev_f32(t: torch.Tensor, name: str) -> torch.Tensor:
