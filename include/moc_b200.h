@@ -272,6 +272,23 @@ int moc_abmil_backward(const float* x, int64_t ldx, int k_in, int64_t n_rows, co
                        float* d_bab, float* d_wc, float* d_bc, float* d_wcls, float* d_bcls, void* workspace,
                        size_t workspace_bytes, void* stream);
 
+/* Backward pieces of the two heads whose gradient lives on a few rows only.
+ * Conch_CLIP_Ada.forward (models/model_adapters.py:185-193): for R "virtual rows" (a row pooled into the top-j mean
+ * of class cls_of_row[v], carrying g_of_row[v] = d(loss)/d(its logit)), x_rows / a2_rows [R][512] the gathered
+ * features and adapter outputs: da2 [R][512] = gradient at the adapter output (through the blend, the
+ * normalisation and the adapter's last ReLU).  The adapter's weight gradients then are moc_linear_wgrad of da2 and
+ * of moc_mask_positive(da2 W2, a1).  moc_transpose: out[c][r] = in[r][c].
+ * MIL_fc.forward (models/model_mil.py:30-51): gradients of the two Linear layers from dtop = d(loss)/d(top_instance)
+ * [C]; only the selected instance (x_row [k_in], hid_row [width] after ReLU) carries gradient. */
+int moc_adapter_backward_rows(const float* x_rows, const float* a2_rows, float clip_ratio, const float* classifier,
+                              int n_classes, const int32_t* cls_of_row, const float* g_of_row, int64_t n_rows,
+                              float* da2, void* stream);
+int moc_mask_positive(float* g, const float* ref, int64_t n, void* stream);
+int moc_transpose(const float* in, int rows, int cols, float* out, void* stream);
+int moc_mil_fc_backward(const float* x_row, int k_in, const float* hid_row, int width, const float* w_last,
+                        int n_classes, const float* dtop, float* d_w0, float* d_b0, float* d_wl, float* d_bl,
+                        void* stream);
+
 /* per-row softmax of [n_rows][n_cols] logits (MIL_fc, models/model_mil.py:38) */
 int moc_row_softmax(const float* logits, int64_t ld, int n_cols, int64_t n_rows, float* probs, int64_t ldp,
                     void* stream);

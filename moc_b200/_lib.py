@@ -71,6 +71,10 @@ SIGNATURES = {
     "moc_abmil_backward_workspace_bytes": (sz, [i64, i32, i32, i32]),
     "moc_abmil_backward": (i32, [p, i64, i32, i64, p, i64, i32, p, i64, i32, p, p, p, p, p, i32, p,
                                  p, p, p, p, p, p, p, p, p, sz, p]),
+    "moc_adapter_backward_rows": (i32, [p, p, f32, p, i32, p, p, i64, p, p]),
+    "moc_mask_positive": (i32, [p, p, i64, p]),
+    "moc_transpose": (i32, [p, i32, i32, p, p]),
+    "moc_mil_fc_backward": (i32, [p, i32, p, i32, p, i32, p, p, p, p, p, p]),
     "moc_h5_open": (i32, [C.c_char_p, C.POINTER(C.c_void_p)]),
     "moc_h5_close": (None, [p]),
     "moc_h5_dataset_info": (i32, [p, C.c_char_p, C.POINTER(i32), C.POINTER(i64), C.POINTER(i32), C.POINTER(i32)]),

@@ -299,3 +299,118 @@ extern "C" int moc_abmil_backward(const float* x, int64_t ldx, int k_in, int64_t
     if (rc != MOC_OK) return rc;
     return moc_linear_wgrad(g1, L, L, x, ldx, k_in, n_rows, d_wfc, k_in, 0, ws + p.off_wg, p.wg_bytes, stream);
 }
+
+// =================================================================================================================
+// Conch_CLIP_Ada and MIL_fc: the rows that carry gradient are few (the top-j rows of each class; the single
+// max-probability instance), so their backward is a handful of row kernels around the dense tensor-core layers.
+// =================================================================================================================
+namespace moc {
+
+// Conch_CLIP_Ada.forward (models/model_adapters.py:185-193) backwards, for "virtual rows" v = (row pooled for class
+// c_v): f = ratio * a2 + (1 - ratio) * x, fn = f / |f|, logit = fn . classifier[:, c];  given g_v = d(loss)/d(logit)
+// the gradient at the adapter output is  da2 = ratio * (cls_c - fn (fn . cls_c)) g_v / |f|  where a2 > 0 (its ReLU).
+// One warp per virtual row; x / a2 are the gathered rows [R][512].
+__global__ void __launch_bounds__(256)
+adapter_bwd_rows_kernel(const float* __restrict__ x, const float* __restrict__ a2, float ratio,
+                        const float* __restrict__ classifier /* [512][C] */, int C, const int32_t* __restrict__ cls_of_row,
+                        const float* __restrict__ g_of_row, int64_t n_rows, float* __restrict__ da2) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float keep = 1.0f - ratio;
+    for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < n_rows; row += (int64_t)gridDim.x * 8) {
+        const int c = cls_of_row[row];
+        const float g = g_of_row[row];
+        float f[16], av[16], w[16];
+        float ss = 0.f, dot = 0.f;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const int k = q * 32 + lane;
+            av[q] = a2[row * D + k];
+            f[q] = __fadd_rn(__fmul_rn(av[q], ratio), __fmul_rn(x[row * D + k], keep));
+            w[q] = __ldg(classifier + (size_t)k * C + c);
+            ss = fmaf(f[q], f[q], ss);
+        }
+        const float nrm = sqrtf(warp_sum(ss));
+        const float inv = 1.0f / nrm;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            f[q] *= inv;                      // fn
+            dot = fmaf(f[q], w[q], dot);
+        }
+        dot = warp_sum(dot);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const float df = (w[q] - f[q] * dot) * (g * inv);
+            da2[row * D + q * 32 + lane] = av[q] > 0.f ? ratio * df : 0.f;
+        }
+    }
+}
+
+// g[i] = ref[i] > 0 ? g[i] : 0   (ReLU backward on a small dense block)
+__global__ void mask_positive_kernel(float* __restrict__ g, const float* __restrict__ ref, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && !(ref[i] > 0.f)) g[i] = 0.f;
+}
+
+// MIL_fc (models/model_mil.py:30-51): only the selected instance carries gradient.  x [K0] its features, hid [H1] its
+// hidden activations (after ReLU), dtop [C] = d(loss)/d(top_instance logits).  Block j handles hidden unit j.
+__global__ void __launch_bounds__(128)
+mil_fc_backward_kernel(const float* __restrict__ x, int K0, const float* __restrict__ hid, int H1,
+                       const float* __restrict__ w_last /* [C][H1] */, int C, const float* __restrict__ dtop,
+                       float* __restrict__ d_w0 /* [H1][K0] */, float* __restrict__ d_b0, float* __restrict__ d_wl,
+                       float* __restrict__ d_bl) {
+    const int j = blockIdx.x;
+    const float h = hid[j];
+    float dh = 0.f;
+    for (int c = 0; c < C; ++c) dh = fmaf(dtop[c], w_last[(size_t)c * H1 + j], dh);
+    if (!(h > 0.f)) dh = 0.f;
+    for (int k = threadIdx.x; k < K0; k += blockDim.x) d_w0[(size_t)j * K0 + k] = dh * x[k];
+    if (threadIdx.x == 0) {
+        d_b0[j] = dh;
+        for (int c = 0; c < C; ++c) d_wl[(size_t)c * H1 + j] = dtop[c] * h;
+        if (j == 0)
+            for (int c = 0; c < C; ++c) d_bl[c] = dtop[c];
+    }
+}
+
+}  // namespace moc
+
+extern "C" int moc_transpose(const float* in, int rows, int cols, float* out, void* stream) {
+    MOC_CHECK_ARG(in && out && rows >= 1 && cols >= 1, "moc_transpose: bad arguments");
+    transpose_kernel<<<dim3((cols + 31) / 32, (rows + 31) / 32), dim3(32, 8), 0, (cudaStream_t)stream>>>(in, rows, cols, out);
+    MOC_LAUNCH_CHECK("transpose_kernel");
+    return MOC_OK;
+}
+
+extern "C" int moc_adapter_backward_rows(const float* x_rows, const float* a2_rows, float clip_ratio, const float* classifier,
+                                         int n_classes, const int32_t* cls_of_row, const float* g_of_row, int64_t n_rows,
+                                         float* da2, void* stream) {
+    MOC_CHECK_ARG(x_rows && a2_rows && classifier && cls_of_row && g_of_row && da2 && n_rows >= 0 && n_classes >= 1,
+                  "moc_adapter_backward_rows: bad arguments");
+    if (n_rows == 0) return MOC_OK;
+    int64_t blocks = (n_rows + 7) / 8;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    adapter_bwd_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x_rows, a2_rows, clip_ratio, classifier, n_classes,
+                                                                                 cls_of_row, g_of_row, n_rows, da2);
+    MOC_LAUNCH_CHECK("adapter_bwd_rows_kernel");
+    return MOC_OK;
+}
+
+extern "C" int moc_mask_positive(float* g, const float* ref, int64_t n, void* stream) {
+    MOC_CHECK_ARG(g && ref && n >= 0, "moc_mask_positive: bad arguments");
+    if (n == 0) return MOC_OK;
+    mask_positive_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(g, ref, n);
+    MOC_LAUNCH_CHECK("mask_positive_kernel");
+    return MOC_OK;
+}
+
+extern "C" int moc_mil_fc_backward(const float* x_row, int k_in, const float* hid_row, int width, const float* w_last,
+                                   int n_classes, const float* dtop, float* d_w0, float* d_b0, float* d_wl, float* d_bl,
+                                   void* stream) {
+    MOC_CHECK_ARG(x_row && hid_row && w_last && dtop && d_w0 && d_b0 && d_wl && d_bl, "moc_mil_fc_backward: null pointer");
+    MOC_CHECK_ARG(k_in >= 1 && width >= 1 && n_classes >= 1, "moc_mil_fc_backward: bad sizes");
+    mil_fc_backward_kernel<<<width, 128, 0, (cudaStream_t)stream>>>(x_row, k_in, hid_row, width, w_last, n_classes, dtop, d_w0,
+                                                                    d_b0, d_wl, d_bl);
+    MOC_LAUNCH_CHECK("mil_fc_backward_kernel");
+    return MOC_OK;
+}

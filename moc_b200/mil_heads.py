@@ -6,7 +6,8 @@ interchange), ``forward`` runs every dense layer on the tensor cores (``ops.line
 everything else in our row kernels.  ABMIL also trains: with gradients enabled its ``forward`` returns logits that
 carry a graph whose backward is ours (``ops.abmil_backward``: tcgen05 weight gradients, deterministic reductions),
 so the reference's ``loss.backward(); optimizer.step()`` loop (utils/core_utils.py:398-416) runs unchanged.  The
-other two heads are forward-only (``torch.no_grad``).
+other two heads train the same way; their gradient lives on a few rows only (the top-j rows of each class for
+``Conch_CLIP_Ada``, the one max-probability instance for ``MIL_fc``), which the backward gathers first.
 
 * ``Conch_CLIP_Ada``  models/model_adapters.py:148-215 - adapter MLP, residual blend, normalise, score, top-j mean
 * ``CLAM_SB``         models/model_clam.py:77-219 with ``instance_loss_fn=None`` (= ABMIL): gated attention pooling
@@ -64,6 +65,63 @@ class _AbmilFunction(torch.autograd.Function):
         return (None, d_wfc, d_bfc, d_wab[:d], d_bab[:d], d_wab[d:], d_bab[d:], d_wc.view(1, d), d_bc, d_wcls, d_bcls)
 
 
+
+class _ClipAdaFunction(torch.autograd.Function):
+    """pooled logits = Conch_CLIP_Ada.forward(feat; adapter weights) with the hand-written backward: only the top-j rows
+    of each class carry gradient, so the backward gathers those <= j*C rows and runs the adapter's two layers backwards
+    on them (row kernel + tensor-core weight gradients)."""
+
+    @staticmethod
+    def forward(ctx, feat, w_a, w_b, classifier, clip_ratio, topj):
+        a1 = ops.linear(feat, w_a, None, "relu")
+        a2 = ops.linear(a1, w_b, None, "relu")
+        planes = ops.adapter_scores(feat, a2, clip_ratio, classifier)          # [C, N]
+        pooled = _pool_topj_planes(planes, topj)
+        ctx.save_for_backward(feat, a1, a2, planes, w_b, classifier)
+        ctx.clip_ratio, ctx.topj = float(clip_ratio), int(topj)
+        return pooled
+
+    @staticmethod
+    def backward(ctx, dpooled):
+        feat, a1, a2, planes, w_b, classifier = ctx.saved_tensors
+        c, n = planes.shape
+        j = min(ctx.topj, n)
+        idx = ops.topj_sorted(planes.t(), j, largest=True)                       # int64 [j, C]: the pooled rows
+        rows = idx.t().reshape(-1)                                               # class after class
+        cls_of_row = torch.arange(c, device=feat.device, dtype=torch.int32).repeat_interleave(j)
+        g_of_row = (dpooled.reshape(-1).float() / j).repeat_interleave(j)
+        x_r, a1_r, a2_r = ops.take_rows(feat, rows, feat.size(1)), ops.take_rows(a1, rows, a1.size(1)), ops.take_rows(a2, rows, a2.size(1))
+        da2 = ops.adapter_backward_rows(x_r, a2_r, ctx.clip_ratio, classifier, cls_of_row, g_of_row)
+        d_wb = ops.linear_wgrad(da2, a1_r)                                       # [512, 128]
+        da1 = ops.mask_positive_(ops.linear(da2, ops.transpose(w_b), None, None).contiguous(), a1_r)
+        d_wa = ops.linear_wgrad(da1, x_r)                                        # [128, 512]
+        return None, d_wa, d_wb, None, None, None
+
+
+class _MilFcFunction(torch.autograd.Function):
+    """top_instance logits = MIL_fc(h; parameters): the gradient reaches the parameters through the one selected
+    instance only (models/model_mil.py:40-42)."""
+
+    @staticmethod
+    def forward(ctx, h, w0, b0, wl, bl):
+        hid = ops.linear(h, w0, b0, "relu")
+        logits = ops.linear(hid, wl, bl, None).contiguous()
+        y_probs = ops.row_softmax(logits)
+        top_idx = ops.topj_sorted(y_probs[:, 1], 1, largest=True).view(1,)
+        top_instance = ops.take_rows(logits, top_idx, logits.size(1))
+        hid_row = ops.take_rows(hid, top_idx, hid.size(1))
+        x_row = ops.take_rows(h, top_idx, h.size(1))
+        ctx.save_for_backward(x_row, hid_row, wl)
+        ctx.mark_non_differentiable(y_probs, top_idx, hid_row)
+        return top_instance, y_probs, top_idx, hid_row
+
+    @staticmethod
+    def backward(ctx, dtop, *unused):
+        x_row, hid_row, wl = ctx.saved_tensors
+        d_w0, d_b0, d_wl, d_bl = ops.mil_fc_backward(x_row, hid_row, wl, dtop.contiguous())
+        return None, d_w0, d_b0, d_wl, d_bl
+
+
 class Conch_CLIP_Ada(nn.Module):
     def __init__(self, c_in=512, reduction=4, num_classes=2, classifier_tensor=None, clip_ratio=0.1, topj=10):
         super().__init__()
@@ -87,12 +145,16 @@ class Conch_CLIP_Ada(nn.Module):
         with torch.no_grad():
             return _pool_topj_planes(logits.t().contiguous().float(), topj)
 
-    @torch.no_grad()
     def forward(self, feat):
-        a1 = ops.linear(feat, self.adapter[0].weight, None, "relu")
-        a2 = ops.linear(a1, self.adapter[2].weight, None, "relu")
-        planes = ops.adapter_scores(feat, a2, self.clip_ratio, self.classifier)
-        return _pool_topj_planes(planes, self.topj)
+        w_a, w_b = self.adapter[0].weight, self.adapter[2].weight
+        if torch.is_grad_enabled() and (w_a.requires_grad or w_b.requires_grad):
+            # adapter training: the pooled logits carry a graph whose backward is ours
+            return _ClipAdaFunction.apply(feat, w_a, w_b, self.classifier, self.clip_ratio, self.topj)
+        with torch.no_grad():
+            a1 = ops.linear(feat, w_a, None, "relu")
+            a2 = ops.linear(a1, w_b, None, "relu")
+            planes = ops.adapter_scores(feat, a2, self.clip_ratio, self.classifier)
+            return _pool_topj_planes(planes, self.topj)
 
     @torch.no_grad()
     def forward_disable_ada(self, feat):
@@ -210,19 +272,32 @@ class MIL_fc(nn.Module):
     def relocate(self):
         self.classifier.to(torch.device("cuda"))
 
-    @torch.no_grad()
     def forward(self, h, return_features=False):
         if self.top_k != 1:
             raise MocError(E_ARG, "MIL_fc: the reference's .view(1,) admits top_k=1 only (models/model_mil.py:40)")
+        if self.training and any(isinstance(m, nn.Dropout) for m in self.modules()):
+            raise MocError(E_ARG, "dropout in training mode is not implemented: build the model with dropout=False or call .eval()")
         l0, l1 = self.classifier[0], self.classifier[-1]
-        hid = ops.linear(h, l0.weight, l0.bias, "relu")
-        logits = ops.linear(hid, l1.weight, l1.bias, None).contiguous()
-        y_probs = ops.row_softmax(logits)
-        top_idx = ops.topj_sorted(y_probs[:, 1], 1, largest=True).view(1,)
-        top_instance = ops.take_rows(logits, top_idx, logits.size(1))
-        y_prob = ops.row_softmax(top_instance)
-        y_hat = ops.topj_sorted(top_instance.t().contiguous(), 1, largest=True).view(1, 1)
+        params = (l0.weight, l0.bias, l1.weight, l1.bias)
+        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            top_instance, y_probs, top_idx, hid_row = _MilFcFunction.apply(h, *params)
+        else:
+            with torch.no_grad():
+                top_instance, y_probs, top_idx, hid_row = _MilFcFunction.forward(_NoCtx(), h, *params)
+        with torch.no_grad():
+            y_prob = ops.row_softmax(top_instance.detach())
+            y_hat = ops.topj_sorted(top_instance.detach().t().contiguous(), 1, largest=True).view(1, 1)
         results = {}
         if return_features:
-            results["features"] = ops.take_rows(hid, top_idx, hid.size(1))
+            results["features"] = hid_row
         return top_instance, y_prob, y_hat, y_probs, results
+
+
+class _NoCtx:
+    """Stand-in for the autograd context when a Function's forward is used without a graph."""
+
+    def save_for_backward(self, *a):
+        pass
+
+    def mark_non_differentiable(self, *a):
+        pass

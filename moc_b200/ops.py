@@ -535,3 +535,53 @@ def abmil_backward(x: torch.Tensor, h1: torch.Tensor, ab: torch.Tensor, hidden: 
                                  d_wab.data_ptr(), d_bab.data_ptr(), d_wc.data_ptr(), d_bc.data_ptr(), d_wcls.data_ptr(),
                                  d_bcls.data_ptr(), ws.data_ptr(), ws_bytes, _stream()))
     return d_wfc, d_bfc, d_wab, d_bab, d_wc, d_bc, d_wcls, d_bcls
+
+
+def transpose(mat: torch.Tensor) -> torch.Tensor:
+    """Contiguous transpose of a [R,C] fp32 CUDA matrix (our kernel, not a strided view)."""
+    mat = _dev_f32(mat, "mat")
+    r, c = mat.shape
+    out = torch.empty(c, r, dtype=torch.float32, device=mat.device)
+    _count(1)
+    check(_lib.load().moc_transpose(mat.data_ptr(), r, c, out.data_ptr(), _stream()))
+    return out
+
+
+def adapter_backward_rows(x_rows: torch.Tensor, a2_rows: torch.Tensor, clip_ratio: float, classifier: torch.Tensor,
+                          cls_of_row: torch.Tensor, g_of_row: torch.Tensor) -> torch.Tensor:
+    """Gradient at the adapter output [R,512] of Conch_CLIP_Ada for R pooled (row, class) pairs."""
+    x_rows, a2_rows = _dev_f32(x_rows, "x_rows"), _dev_f32(a2_rows, "a2_rows")
+    cl = _dev_f32(classifier, "classifier")
+    r = x_rows.size(0)
+    out = torch.empty(r, D, dtype=torch.float32, device=x_rows.device)
+    cls_of_row = cls_of_row.to(device=x_rows.device, dtype=torch.int32).contiguous()
+    g_of_row = _dev_f32(g_of_row, "g_of_row")
+    _count(1)
+    check(_lib.load().moc_adapter_backward_rows(x_rows.data_ptr(), a2_rows.data_ptr(), float(clip_ratio), cl.data_ptr(),
+                                                cl.size(1), cls_of_row.data_ptr(), g_of_row.data_ptr(), r, out.data_ptr(),
+                                                _stream()))
+    return out
+
+
+def mask_positive_(g: torch.Tensor, ref: torch.Tensor) -> torch.Tensor:
+    """In place: g[i] = 0 where ref[i] <= 0 (ReLU backward)."""
+    assert g.is_contiguous() and ref.is_contiguous() and g.shape == ref.shape
+    _count(1)
+    check(_lib.load().moc_mask_positive(g.data_ptr(), ref.data_ptr(), g.numel(), _stream()))
+    return g
+
+
+def mil_fc_backward(x_row: torch.Tensor, hid_row: torch.Tensor, w_last: torch.Tensor, dtop: torch.Tensor):
+    """(d_w0 [H1,K0], d_b0 [H1], d_wl [C,H1], d_bl [C]) of MIL_fc from the gradient at the selected instance's logits."""
+    x_row, hid_row = _dev_f32(x_row, "x_row").reshape(-1), _dev_f32(hid_row, "hid_row").reshape(-1)
+    w_last, dtop = _dev_f32(w_last, "w_last"), _dev_f32(dtop, "dtop").reshape(-1)
+    k0, h1, c = x_row.numel(), hid_row.numel(), w_last.size(0)
+    dev = x_row.device
+    d_w0 = torch.empty(h1, k0, dtype=torch.float32, device=dev)
+    d_b0 = torch.empty(h1, dtype=torch.float32, device=dev)
+    d_wl = torch.empty(c, h1, dtype=torch.float32, device=dev)
+    d_bl = torch.empty(c, dtype=torch.float32, device=dev)
+    _count(1)
+    check(_lib.load().moc_mil_fc_backward(x_row.data_ptr(), k0, hid_row.data_ptr(), h1, w_last.data_ptr(), c, dtop.data_ptr(),
+                                          d_w0.data_ptr(), d_b0.data_ptr(), d_wl.data_ptr(), d_bl.data_ptr(), _stream()))
+    return d_w0, d_b0, d_wl, d_bl

@@ -167,9 +167,58 @@ def main_backward():
         print("wrote heads_abmil_bwd_c%d  loss %.6f" % (c, float(loss)))
 
 
+def main_backward_sparse():
+    """Training-step gradients of the two heads whose gradient lives on a few rows, through the reference's own modules
+    and torch autograd: Conch_CLIP_Ada (both bags of heads_clip_ada_c2/c3: fewer rows than topj, and more) and MIL_fc.
+    Parameters and inputs are rebuilt from the seeds of main() and checked against the stored forward goldens."""
+    assert ref_loader.available()
+    torch.set_num_threads(1)
+    _, mil, ada = import_reference_models()
+    for c, sizes, topj, seed in ((2, [37, 700], 50, 31), (3, [300], 10, 32)):
+        w, _ = synthetic.prompt_matrices(c)
+        torch.manual_seed(seed)
+        m = ada.Conch_CLIP_Ada(c_in=512, reduction=4, num_classes=c, classifier_tensor=w, clip_ratio=0.1, topj=topj).train()
+        fp16_exact(m)
+        stored = np.load(os.path.join(OUT, "heads_clip_ada_c%d.npz" % c))
+        out = {"n_bags": len(sizes)}
+        for i in range(len(sizes)):
+            x = torch.from_numpy(stored["feat_%d" % i]).float()
+            m.zero_grad()
+            logits = m.forward(x)
+            assert np.array_equal(logits.detach().numpy(), stored["forward_%d" % i])
+            label = torch.tensor([(i + 1) % c])
+            loss = torch.nn.functional.cross_entropy(logits * 56.3477, label)   # CONCH's logit scale (model_adapters.py:190)
+            loss.backward()
+            out["label_%d" % i], out["loss_%d" % i] = int(label), float(loss.detach())
+            for k, p_ in m.named_parameters():
+                out["grad_%d_%s" % (i, k)] = p_.grad.numpy().copy()
+        np.savez_compressed(os.path.join(OUT, "heads_clip_ada_bwd_c%d.npz" % c), **out)
+        print("wrote heads_clip_ada_bwd_c%d" % c)
+
+    torch.manual_seed(51)
+    m = mil.MIL_fc(size_arg="benchmark", dropout=False, n_classes=2, top_k=1).train()
+    fp16_exact(m)
+    stored = np.load(os.path.join(OUT, "heads_mil_fc.npz"))
+    out = {}
+    i = 1
+    x = torch.from_numpy(stored["feat_%d" % i]).float()
+    top, _, _, _, _ = m(x)
+    assert np.array_equal(top.detach().numpy(), stored["top_instance_%d" % i])
+    loss = torch.nn.functional.cross_entropy(top, torch.tensor([1]))
+    loss.backward()
+    out["bag"], out["label"], out["loss"] = i, 1, float(loss.detach())
+    for k, p_ in m.named_parameters():
+        out["grad_" + k] = p_.grad.numpy().copy()
+    np.savez_compressed(os.path.join(OUT, "heads_mil_fc_bwd.npz"), **out)
+    print("wrote heads_mil_fc_bwd")
+
+
 if __name__ == "__main__":
-    if "--backward" in sys.argv:
+    if "--backward-sparse" in sys.argv:
+        main_backward_sparse()
+    elif "--backward" in sys.argv:
         main_backward()
     else:
         main()
         main_backward()
+        main_backward_sparse()

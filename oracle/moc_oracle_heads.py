@@ -71,3 +71,23 @@ def abmil_loss_and_grads(sd: Dict[str, torch.Tensor], h: torch.Tensor, label: in
     loss = F.cross_entropy(logits, torch.tensor([int(label)]))
     grads = torch.autograd.grad(loss, [leaf[k] for k in names])
     return loss.detach(), dict(zip(names, grads))
+
+
+def clip_ada_loss_and_grads(sd: Dict[str, torch.Tensor], classifier: torch.Tensor, feat: torch.Tensor, clip_ratio: float,
+                            topj: int, label: int, logit_scale: float = 56.3477):
+    """Adapter training step of Conch_CLIP_Ada: loss = CE(logit_scale * forward(feat), label) (the logit scale of
+    models/model_adapters.py:190), gradients of the two adapter weights by torch autograd over the restated forward."""
+    leaf = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
+    loss = F.cross_entropy(clip_ada_forward(leaf, classifier, feat, clip_ratio, topj) * logit_scale, torch.tensor([int(label)]))
+    names = list(leaf)
+    grads = torch.autograd.grad(loss, [leaf[k] for k in names])
+    return loss.detach(), dict(zip(names, grads))
+
+
+def mil_fc_loss_and_grads(sd: Dict[str, torch.Tensor], h: torch.Tensor, label: int):
+    """MIL_fc training step as utils/core_utils.py:391-414 runs it: loss = CE(top_instance, label); autograd."""
+    leaf = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
+    loss = F.cross_entropy(mil_fc_forward(leaf, h)[0], torch.tensor([int(label)]))
+    names = list(leaf)
+    grads = torch.autograd.grad(loss, [leaf[k] for k in names])
+    return loss.detach(), dict(zip(names, grads))

@@ -225,3 +225,55 @@ def test_abmil_training_loop_vs_oracle():
             assert float(diff.max()) <= 8 * 2e-4 * 1.01, k
             if diff.numel() > 1000:
                 assert float((diff > 2e-5).float().mean()) < 1e-3, k
+
+
+@pytest.mark.parametrize("name", ["heads_clip_ada_c2", "heads_clip_ada_c3"])
+def test_conch_clip_ada_backward_golden(golden, name):
+    """Adapter training step (CE on the scaled pooled logits, loss.backward()) against torch autograd through the
+    reference's own Conch_CLIP_Ada: bags with fewer rows than topj and with more."""
+    import moc_b200
+    g, gb = golden(name), golden(name.replace("clip_ada", "clip_ada_bwd"))
+    sd, cl = _sd(g), T(g["classifier"])
+    m = moc_b200.Conch_CLIP_Ada(512, 4, int(g["C"]), cl.to(DEV), float(g["clip_ratio"]), int(g["topj"])).to(DEV).train()
+    m.load_state_dict(sd)
+    for i in range(int(gb["n_bags"])):
+        x = T(g["feat_%d" % i]).float().to(DEV)
+        m.zero_grad()
+        logits = m.forward(x)
+        assert logits.requires_grad
+        close(logits, g["forward_%d" % i])
+        loss = torch.nn.functional.cross_entropy(logits * 56.3477, torch.tensor([int(gb["label_%d" % i])], device=DEV))
+        assert abs(float(loss.detach()) - float(gb["loss_%d" % i])) < 2e-4 * max(1.0, float(gb["loss_%d" % i]))
+        loss.backward()
+        for k, p in m.named_parameters():
+            close_grad(p.grad, gb["grad_%d_%s" % (i, k)])
+    with torch.no_grad():
+        assert not m.forward(x).requires_grad
+
+
+def test_mil_fc_backward_golden(golden):
+    import moc_b200
+    g, gb = golden("heads_mil_fc"), golden("heads_mil_fc_bwd")
+    m = moc_b200.MIL_fc(size_arg="benchmark", n_classes=2, top_k=1).to(DEV).train()
+    m.load_state_dict(_sd(g))
+    i = int(gb["bag"])
+    x = T(g["feat_%d" % i]).float().to(DEV)
+    top, y_prob, y_hat, y_probs, _ = m(x)
+    assert top.requires_grad and not y_probs.requires_grad
+    close(top, g["top_instance_%d" % i])
+    loss = torch.nn.functional.cross_entropy(top, torch.tensor([int(gb["label"])], device=DEV))
+    assert abs(float(loss.detach()) - float(gb["loss"])) < 1e-5
+    loss.backward()
+    for k, p in m.named_parameters():
+        close_grad(p.grad, gb["grad_" + k])
+    # three SGD steps keep following the oracle
+    sd = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    opt = torch.optim.SGD(m.parameters(), lr=0.05)
+    for step in range(3):
+        oloss, ograds = H.mil_fc_loss_and_grads(sd, x.cpu(), 1)
+        opt.zero_grad()
+        loss = torch.nn.functional.cross_entropy(m(x)[0], torch.tensor([1], device=DEV))
+        assert abs(float(loss.detach()) - float(oloss)) < 1e-5
+        loss.backward()
+        opt.step()
+        sd = {k: sd[k] - 0.05 * ograds[k] for k in sd}

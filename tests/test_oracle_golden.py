@@ -198,6 +198,30 @@ def test_heads_abmil_backward(golden, name):
             assert (gr.reshape(-1)[::5] - ref).abs().max() <= 1e-6 * ref.abs().max() + 1e-12, k
 
 
+@pytest.mark.parametrize("name", ["heads_clip_ada_c2", "heads_clip_ada_c3"])
+def test_heads_clip_ada_backward(golden, name):
+    from oracle import moc_oracle_heads as H
+    g, gb = golden(name), golden(name.replace("clip_ada", "clip_ada_bwd"))
+    sd, cl = _sd(g), T(g["classifier"])
+    for i in range(int(gb["n_bags"])):
+        loss, grads = H.clip_ada_loss_and_grads(sd, cl, T(g["feat_%d" % i]).float(), float(g["clip_ratio"]), int(g["topj"]),
+                                                int(gb["label_%d" % i]))
+        assert abs(float(loss) - float(gb["loss_%d" % i])) < 1e-6
+        for k, gr in grads.items():
+            ref = T(gb["grad_%d_%s" % (i, k)])
+            assert (gr - ref).abs().max() <= 1e-6 * ref.abs().max() + 1e-12, (i, k)
+
+
+def test_heads_mil_fc_backward(golden):
+    from oracle import moc_oracle_heads as H
+    g, gb = golden("heads_mil_fc"), golden("heads_mil_fc_bwd")
+    loss, grads = H.mil_fc_loss_and_grads(_sd(g), T(g["feat_%d" % int(gb["bag"])]).float(), int(gb["label"]))
+    assert abs(float(loss) - float(gb["loss"])) < 1e-6
+    for k, gr in grads.items():
+        ref = T(gb["grad_" + k])
+        assert (gr - ref).abs().max() <= 1e-6 * ref.abs().max() + 1e-12, k
+
+
 def test_heads_mil_fc(golden):
     from oracle import moc_oracle_heads as H
     g = golden("heads_mil_fc")
