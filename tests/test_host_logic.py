@@ -204,3 +204,25 @@ def test_cli_summary_mode(tmp_path, capsys):
         b = open(os.path.join(ref, "summary_%d.csv" % shot)).read()
         assert a == b, shot
     assert not os.path.exists(os.path.join(ref, "summary_8.csv"))
+
+
+def test_bench_reference_arm_contract():
+    """bench.py --impl reference runs on the host alone (no GPU) and prints ONE JSON line with the contract's keys."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--slides", "3", "--patches", "500"], capture_output=True, text=True, timeout=300, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, "stdout must carry the JSON line only"
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "slides_per_sec" and d["unit"] == "slides/s"
+    assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["value"] > 0 and d["gpu_launches"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "slides/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # a non-zero rank under torchrun exits 0 without work and without output
+    r2 = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                        capture_output=True, text=True, timeout=120, cwd=root, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
+    assert r2.returncode == 0 and r2.stdout.strip() == ""
