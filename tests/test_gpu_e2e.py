@@ -159,3 +159,34 @@ def test_cli_on_h5_dataset_directory(tmp_path):
     best = json.load(open(os.path.join(res, "best_results_shot_2_fold_0.json")))
     assert set(best) >= {"zero_shot_test", "best_val", "test_at_best_val", "test_acc_at_best_val", "best_epoch", "best_model_path"}
     assert os.path.exists(os.path.join(res, "best_model_shot_2_fold_0.pt"))
+
+
+def test_bench_json_contract():
+    """bench.py on a small workload: one JSON line with the driver's keys, a live roofline for the streaming kernel,
+    an end-to-end number with its copy volumes, a CPU baseline, kernel launches counted."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--slides", "24", "--patches", "6000", "--steps", "3",
+                        "--warmup", "3", "--cpu-seconds", "1", "--e2e-steps", "2", "--e2e-host-slides", "8"],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert k in d, k
+    assert d["metric"] == "slides_per_sec" and d["n_gpus"] == 1 and d["steps"] == 3 and d["scaling"] == "weak"
+    assert d["dtype"] == "f32" and d["data"] == "synthetic" and "workload" in d["config"] and d["vs_baseline"] is None
+    rf = d["roofline"]
+    assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and rf["achieved"] > 0 and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9
+    assert rf["algorithmic_bytes_per_launch"] == 24 * 6000 * 2048
+    e = d["e2e"]
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] == 24 * 6000 * 2048 and e["d2h_bytes_per_step"] == 24 * 2 * 4
+    assert e["value"] < d["value"], "the end-to-end number includes the host-to-device copies"
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] > 0
+    assert d["gpu_launches"] >= 3 * 6 and set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
