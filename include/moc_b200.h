@@ -93,6 +93,11 @@ int moc_collapse_prompt_bank(const float* bank, const int32_t* class_offsets, in
  * L2-normalises each row first (models/model_adapters.py:188; off in MOC). */
 int moc_score_keys(const float* feat, int64_t n_rows, const float* packed, int n_classes, int n_ext,
                    int normalize, float* keys, int64_t key_stride, void* stream);
+/* Same, on at most max_ctas persistent CTAs (0 = the default: 132 on a 148-SM B200, where the streaming kernel reads
+ * HBM fastest: 6.85 TB/s against 6.44 TB/s with one CTA on every SM).  A smaller number leaves SMs free for kernels
+ * running on another stream.  Ignored by the wide-prompt-set kernels. */
+int moc_score_keys_ex(const float* feat, int64_t n_rows, const float* packed, int n_classes, int n_ext,
+                      int normalize, float* keys, int64_t key_stride, int max_ctas, void* stream);
 
 /* ---- a2 for wide prompt sets: the same contract on the tensor cores ---------
  * With more than ~10 prompt columns (EBRAINS-30: 30 classes + 4 background)

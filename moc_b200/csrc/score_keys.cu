@@ -15,6 +15,7 @@
 // Measured on B200 (16.4 GB, C=2): 6.2-6.3 TB/s; the same ring with no compute and no stores reads 7.45 TB/s,
 // dropping only the 28 B/patch key stores gives 6.65 TB/s (any DRAM write mixed into the read stream costs
 // ~5 %, independent of store cache policy, locality or wave size), dropping 3/4 of the FMAs gives 6.55 TB/s.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace moc {
@@ -436,9 +437,24 @@ __global__ void __launch_bounds__(D) collapse_bank_kernel(const float* __restric
     w_out[(size_t)k * n_classes + c] = m / block_norm(m);
 }
 
+// The pure streaming kernel reads HBM fastest with somewhat fewer CTAs than SMs: on the 148-SM B200, 108..132
+// persistent CTAs read 6.74-6.81 TB/s, 134..148 only 6.33-6.42 TB/s (the step is sharp between 132 and 134).
+static int64_t stream_cta_cap() {
+    static int64_t cached = 0;
+    if (cached == 0) {
+        const int n = sm_count();
+        cached = n == 148 ? 132 : n;
+        if (const char* e = getenv("MOC_SCORE_CTAS")) {   // developer override for A/B runs
+            const int v = atoi(e);
+            if (v > 0 && v <= n) cached = v;
+        }
+    }
+    return cached;
+}
+
 template <int NC, bool NORM>
 static int launch_regw(const float* feat, int64_t n_rows, const float* packed, int C, float* keys,
-                       int64_t key_stride, cudaStream_t st) {
+                       int64_t key_stride, int max_ctas, cudaStream_t st) {
     constexpr int NV = NC + (NORM ? 1 : 0);
     constexpr int SLD = (NV % 2 == 0) ? NV + 1 : NV;
     constexpr size_t smem = (size_t)SK_WARPS * SK_STAGES * STAGE_BYTES + SK_WARPS * SK_STAGES * 8 +
@@ -447,7 +463,8 @@ static int launch_regw(const float* feat, int64_t n_rows, const float* packed, i
                                   (int)smem));
     const int64_t n_sg = (n_rows + SG_ROWS - 1) / SG_ROWS;
     int64_t ctas = (n_sg + SK_WARPS - 1) / SK_WARPS;
-    if (ctas > sm_count()) ctas = sm_count();
+    const int64_t cap = max_ctas > 0 && max_ctas < stream_cta_cap() ? max_ctas : stream_cta_cap();
+    if (ctas > cap) ctas = cap;
     score_keys_regw_kernel<NC, NORM><<<(unsigned)ctas, SK_WARPS * 32, smem, st>>>(feat, n_rows, packed, C, keys,
                                                                                 key_stride);
     MOC_LAUNCH_CHECK("score_keys_regw_kernel");
@@ -512,6 +529,11 @@ extern "C" int moc_collapse_prompt_bank(const float* bank, const int32_t* class_
 
 extern "C" int moc_score_keys(const float* feat, int64_t n_rows, const float* packed, int n_classes, int n_ext,
                               int normalize, float* keys, int64_t key_stride, void* stream) {
+    return moc_score_keys_ex(feat, n_rows, packed, n_classes, n_ext, normalize, keys, key_stride, 0, stream);
+}
+
+extern "C" int moc_score_keys_ex(const float* feat, int64_t n_rows, const float* packed, int n_classes, int n_ext,
+                                 int normalize, float* keys, int64_t key_stride, int max_ctas, void* stream) {
     MOC_CHECK_ARG(feat && packed && keys, "moc_score_keys: null pointer");
     MOC_CHECK_ARG(n_rows >= 0 && key_stride >= n_rows, "moc_score_keys: bad n_rows / key_stride");
     MOC_CHECK_SHAPE(n_classes >= 2 && n_ext > n_classes && n_ext <= MOC_MAX_COLS,
@@ -521,8 +543,8 @@ extern "C" int moc_score_keys(const float* feat, int64_t n_rows, const float* pa
     cudaStream_t st = (cudaStream_t)stream;
 #define MOC_REGW(NCV)                                                                                  \
     case NCV:                                                                                          \
-        return normalize ? launch_regw<NCV, true>(feat, n_rows, packed, n_classes, keys, key_stride, st) \
-                         : launch_regw<NCV, false>(feat, n_rows, packed, n_classes, keys, key_stride, st);
+        return normalize ? launch_regw<NCV, true>(feat, n_rows, packed, n_classes, keys, key_stride, max_ctas, st) \
+                         : launch_regw<NCV, false>(feat, n_rows, packed, n_classes, keys, key_stride, max_ctas, st);
     switch (n_ext) {
         MOC_REGW(3)
         MOC_REGW(4)

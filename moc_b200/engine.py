@@ -66,12 +66,12 @@ class MocEngine:
         r0, r1 = store.offsets_h[lo], store.offsets_h[hi]
         return self._score(store.feat[r0:r1])
 
-    def _score(self, feat: torch.Tensor) -> torch.Tensor:
+    def _score(self, feat: torch.Tensor, out: Optional[torch.Tensor] = None, max_ctas: int = 0) -> torch.Tensor:
         if self.score_events is None:
-            return ops.score_keys(feat, self.prompts, self.normalize)
+            return ops.score_keys(feat, self.prompts, self.normalize, out=out, max_ctas=max_ctas)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        k = ops.score_keys(feat, self.prompts, self.normalize)
+        k = ops.score_keys(feat, self.prompts, self.normalize, out=out, max_ctas=max_ctas)
         b.record()
         self.score_events.append((a, b, feat.size(0)))
         return k

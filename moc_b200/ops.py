@@ -111,8 +111,9 @@ def num_key_planes(n_classes: int) -> int:
 
 
 def score_keys(feat: torch.Tensor, prompts: Prompts, normalize: bool = False,
-               out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """keys [2C+3, R] (plane-major) for R rows of feat [R,512]."""
+               out: Optional[torch.Tensor] = None, max_ctas: int = 0) -> torch.Tensor:
+    """keys [2C+3, R] (plane-major) for R rows of feat [R,512].  ``max_ctas`` (streaming kernel only) leaves SMs free
+    for kernels running on another stream; 0 = the kernel's own best (132 of 148)."""
     feat = _dev_f32(feat, "feat")
     if feat.dim() != 2 or feat.size(1) != D:
         raise MocError(_lib.E_SHAPE, "feat must be [rows,512], got %s" % (tuple(feat.shape),))
@@ -125,9 +126,9 @@ def score_keys(feat: torch.Tensor, prompts: Prompts, normalize: bool = False,
                                             prompts.n_ext, int(bool(normalize)), out.data_ptr(), out.stride(0),
                                             _stream()))
     else:
-        check(_lib.load().moc_score_keys(feat.data_ptr(), r, prompts.packed.data_ptr(), prompts.n_classes,
-                                         prompts.n_ext, int(bool(normalize)), out.data_ptr(), out.stride(0),
-                                         _stream()))
+        check(_lib.load().moc_score_keys_ex(feat.data_ptr(), r, prompts.packed.data_ptr(), prompts.n_classes,
+                                            prompts.n_ext, int(bool(normalize)), out.data_ptr(), out.stride(0),
+                                            int(max_ctas), _stream()))
     return out
 
 
