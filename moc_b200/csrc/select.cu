@@ -345,7 +345,7 @@ __device__ int count_kept(const uint8_t* __restrict__ mk, int n, SelShared& sh) 
 
 // grid (n_slides, 2C+2): one selection of one slide per CTA; marks the chosen rows in the global bitmap.
 template <bool HAS_MASK>
-__global__ void __launch_bounds__(SEL_THREADS)
+__global__ void __launch_bounds__(SEL_THREADS, 3)   // 40 registers: three CTAs per SM (two: -20 %; four: worse at C = 30)
 select_mark_kernel(const float* __restrict__ keys, int64_t key_stride, const int64_t* __restrict__ offsets, int C,
                    int topj, unsigned discard_mask, const uint8_t* __restrict__ row_mask,
                    unsigned int* __restrict__ bitmap) {
