@@ -322,7 +322,11 @@ def run_ours(a):
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": rows_per_launch * 2048, "avg_launch_ms": avg_ms,
                 "launches_timed": len(score_ms), "share_of_step": avg_ms * len(score_ms) / a.steps / ms_step,
-                "frac_of_8TBps_nominal": achieved / 8000.0}
+                "frac_of_8TBps_nominal": achieved / 8000.0,
+                "note": "peak is the driver-measured COPY bandwidth (read + write); a read-only bulk-copy ring with no "
+                        "compute reads 7.3-7.4 TB/s on this part (tools/probe_stream.cu), so this read-mostly kernel "
+                        "can exceed 1.0 of it; frac_of_read_only_7400 is the stricter figure",
+                "frac_of_read_only_7400": achieved / 7400.0}
 
     # ---- end to end from pinned host memory -------------------------------------------------------------
     e2e = None
