@@ -273,7 +273,9 @@ extern "C" int moc_abmil_backward(const float* x, int64_t ldx, int k_in, int64_t
 
     abmil_bwd_prep_kernel<<<1, 1024, 0, st>>>(a_raw, n_rows, pooled, L, w_cls, n_classes, dlogits, dM, scal, d_wcls, d_bcls);
     MOC_LAUNCH_CHECK("abmil_bwd_prep_kernel");
-    const size_t smem = (size_t)AB_WARPS * (3 * Dh + 1) * sizeof(float);
+    const size_t smem = (size_t)AB_WARPS * (3 * Dh + 1) * sizeof(float);   // 36 KB at Dh = 384, 49 KB at the 512 maximum
+    MOC_CUDA(cudaFuncSetAttribute(abmil_bwd_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)((size_t)AB_WARPS * (3 * 32 * AB_MAXI + 1) * sizeof(float))));
     abmil_bwd_rows_kernel<<<p.blocks_rows, AB_THREADS, smem, st>>>(h1, ldh, L, ab, ldab, Dh, a_raw, wc, dM, scal, n_rows,
                                                                    p.rpb_rows, dZ, pr, part);
     MOC_LAUNCH_CHECK("abmil_bwd_rows_kernel");

@@ -277,3 +277,31 @@ def test_mil_fc_backward_golden(golden):
         loss.backward()
         opt.step()
         sd = {k: sd[k] - 0.05 * ograds[k] for k in sd}
+
+
+@pytest.mark.parametrize("size_arg,n,c", [("small", 777, 3), ("big", 1300, 2), ("benchmark", 65, 2)])
+def test_abmil_backward_other_sizes(size_arg, n, c):
+    """The other CLAM size presets (1024- and 384-wide inputs, 256-wide attention) through forward + backward against
+    torch autograd over the oracle's forward."""
+    import moc_b200
+    torch.manual_seed(21)
+    m = moc_b200.CLAM_SB(size_arg=size_arg, n_classes=c, instance_loss_fn=None)
+    with torch.no_grad():
+        for p in m.parameters():
+            if p.dim() == 1:
+                p.copy_(0.05 * torch.randn(p.shape))
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    x = torch.randn(n, m.size_dict[size_arg][0]) * 0.3
+    oloss, ograds = H.abmil_loss_and_grads(sd, x, c - 1)
+    m = m.to(DEV).train()
+    logits = m(x.to(DEV))[0]
+    loss = torch.nn.functional.cross_entropy(logits, torch.tensor([c - 1], device=DEV))
+    assert abs(float(loss.detach()) - float(oloss)) < 1e-4 * max(1.0, abs(float(oloss)))
+    loss.backward()
+    for k, p in m.named_parameters():
+        if k.startswith("instance_classifiers"):
+            continue
+        if k.endswith("attention_c.bias"):
+            assert abs(float(p.grad.reshape(-1)[0])) < 1e-6
+            continue
+        close_grad(p.grad, ograds[k])
