@@ -1,4 +1,4 @@
-"""Developer micro-benchmark: forward time of the secondary MIL heads on one resident bag, with the oracle's
+"""Developer micro-benchmark (lives under tests/ because it times the CPU oracle beside the kernels): forward time of the secondary MIL heads on one resident bag, with the oracle's
 CPU time beside it (torch fp32, all host cores)."""
 import os
 import sys

@@ -8,7 +8,7 @@ for wl in cfg3 cfg4 cfg5; do
   python bench.py --workload $wl --steps 10 --warmup 3 --cpu-seconds 8 > gpurun_out/${TAG}_bench_${wl}.json 2>> gpurun_out/${TAG}_bench.err
 done
 KREGEX='regex:score_keys|select_mark|compact_kernel|head_rows|pool_final|cross_entropy|head_tc_prep|head_f16_prep'
-python tools/kbench_heads.py > gpurun_out/${TAG}_heads.log 2>&1
+python tests/kbench_heads.py > gpurun_out/${TAG}_heads.log 2>&1
 SMALL="--slides 200 --steps 2 --warmup 3 --no-cpu-baseline --no-e2e"
 python bench.py $SMALL > gpurun_out/plain2.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KREGEX" -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py $SMALL > gpurun_out/ncu_l.log 2>&1
@@ -17,7 +17,7 @@ ncu --set full --clock-control none --import-source on -k regex:head_rows_f16 -s
 ncu --set full --clock-control none --import-source on -k regex:head_rows_tc -s 3 -c 1 -o gpurun_out/${TAG}_head_tc -f python bench.py --workload cfg4 --slides 80 --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_htc.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:select_mark -s 3 -c 1 -o gpurun_out/${TAG}_select -f python bench.py $SMALL > gpurun_out/ncu_sel.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:score_keys_tc -s 3 -c 1 -o gpurun_out/${TAG}_score_tc -f python bench.py --workload cfg4 --slides 80 --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_stc.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:wgrad_tc -s 2 -c 1 -o gpurun_out/${TAG}_wgrad -f python tools/kbench_heads.py > gpurun_out/ncu_wg.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:wgrad_tc -s 2 -c 1 -o gpurun_out/${TAG}_wgrad -f python tests/kbench_heads.py > gpurun_out/ncu_wg.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:pool_final -s 3 -c 1 -o gpurun_out/${TAG}_pool -f python bench.py $SMALL > gpurun_out/ncu_p.log 2>&1
 for f in gpurun_out/${TAG}_bench_*.json; do python -c "
 import json,sys
