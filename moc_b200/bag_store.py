@@ -91,11 +91,13 @@ class RaggedBagStore:
 
     @staticmethod
     def from_h5_dir(data_dir: str, slide_ids: Sequence[str], labels: Sequence[int], device="cuda",
-                    return_coords: bool = False):
+                    return_coords: bool = False, workers: int = 8):
         """CLAM-style ``h5_files/<slide_id>.h5`` bags (datasets/dataset_generic.py:424-430), parsed by the native
-        reader (moc_b200/h5bag.py; no h5py) straight into pinned staging buffers and copied to the device while the
-        next file is being read.  ``return_coords`` also returns the per-slide ``coords`` arrays (host, numpy)."""
+        reader (moc_b200/h5bag.py; no h5py).  ``workers`` threads read files ahead into a ring of pinned staging
+        buffers (the reader is C code called through ctypes, so the GIL is released) while the main thread issues the
+        host-to-device copies in slide order.  ``return_coords`` also returns the per-slide ``coords`` (host, numpy)."""
         import os
+        from concurrent.futures import ThreadPoolExecutor
         from .h5bag import H5File
         paths = [os.path.join(data_dir, "h5_files", "%s.h5" % s) for s in slide_ids]
         files = [H5File(p) for p in paths]
@@ -106,26 +108,43 @@ class RaggedBagStore:
                 if len(d.shape) != 2 or d.shape[1] != D:
                     raise ValueError("%s: 'features' has shape %s, expected [N,%d]" % (p, d.shape, D))
                 offs.append(offs[-1] + d.shape[0])
+            n = len(sets)
             feat = torch.empty(offs[-1], D, dtype=torch.float32, device=device)
             use_pin = torch.device(device).type == "cuda"
             max_rows = max([d.shape[0] for d in sets] + [1])
-            stage = [torch.empty(max_rows, D, dtype=torch.float32, pin_memory=use_pin) for _ in range(2 if use_pin else 1)]
-            ev = [None, None]
-            for i, d in enumerate(sets):
-                n = d.shape[0]
-                if n == 0:
-                    continue
-                k = i % len(stage)
-                if ev[k] is not None:
-                    ev[k].synchronize()
+            workers = max(1, min(int(workers), n))
+            ring = min(n, workers + 2) if n else 1
+            stage = [torch.empty(max_rows, D, dtype=torch.float32, pin_memory=use_pin) for _ in range(ring)]
+            copied = [None] * ring           # event after the H2D copy that last read the slot
+
+            def read(i, k):
+                d = sets[i]
+                rows = d.shape[0]
+                if rows == 0:
+                    return
                 if d.dtype == np.float32:
-                    d.read_into(stage[k].data_ptr(), n * D * 4)
+                    d.read_into(stage[k].data_ptr(), rows * D * 4)
                 else:       # float16 / float64 feature files: convert on the host
-                    stage[k][:n].copy_(torch.from_numpy(d[:].astype(np.float32)))
-                feat[offs[i]:offs[i + 1]].copy_(stage[k][:n], non_blocking=use_pin)
-                if use_pin:
-                    ev[k] = torch.cuda.Event()
-                    ev[k].record()
+                    stage[k][:rows].copy_(torch.from_numpy(d[:].astype(np.float32)))
+
+            with ThreadPoolExecutor(max_workers=workers) as pool:
+                pending = {}
+                nxt = 0
+                for i in range(n):
+                    while nxt < n and nxt < i + ring:
+                        k = nxt % ring
+                        if copied[k] is not None:
+                            copied[k].synchronize()      # the slot's previous bag has left for the device
+                            copied[k] = None
+                        pending[nxt] = pool.submit(read, nxt, k)
+                        nxt += 1
+                    pending.pop(i).result()
+                    k, rows = i % ring, sets[i].shape[0]
+                    if rows:
+                        feat[offs[i]:offs[i + 1]].copy_(stage[k][:rows], non_blocking=use_pin)
+                        if use_pin:
+                            copied[k] = torch.cuda.Event()
+                            copied[k].record()
             if use_pin:
                 torch.cuda.current_stream().synchronize()
             store = RaggedBagStore(feat, offs, labels, slide_ids)
