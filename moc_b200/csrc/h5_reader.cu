@@ -368,6 +368,7 @@ extern "C" int moc_h5_open(const char* path, void** handle) {
     }
     void* m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
     close(fd);
+    if (m != MAP_FAILED) madvise(m, (size_t)st.st_size, MADV_WILLNEED);   // start read-ahead of the whole bag now
     if (m == MAP_FAILED) {
         set_error("moc_h5_open: mmap of '%s' failed", path);
         return MOC_E_ARG;
