@@ -140,3 +140,19 @@ def test_store_from_h5_dir(tmp_path):
     for i in range(3):
         assert torch.equal(store.bag(i), torch.from_numpy(bags[i][0]))
         np.testing.assert_array_equal(coords[i], bags[i][1])
+
+
+@pytest.mark.parametrize("workers", [1, 2, 5])
+def test_store_from_h5_dir_ring_reuse(tmp_path, workers):
+    """More bags than staging slots: the read-ahead ring is reused and every bag still lands in its own rows."""
+    os.makedirs(tmp_path / "h5_files")
+    ids, want = [], []
+    for i in range(17):
+        feats, coords = _bag([3, 120, 0, 64, 700][i % 5] + i, seed=100 + i)
+        write_h5(str(tmp_path / "h5_files" / ("s%02d.h5" % i)), {"features": feats, "coords": coords})
+        ids.append("s%02d" % i)
+        want.append(feats)
+    store = RaggedBagStore.from_h5_dir(str(tmp_path), ids, list(range(17)), device="cpu", workers=workers)
+    assert len(store) == 17 and store.total_rows == sum(w.shape[0] for w in want)
+    for i in range(17):
+        assert torch.equal(store.bag(i), torch.from_numpy(want[i])), i
