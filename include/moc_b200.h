@@ -95,7 +95,8 @@ int moc_score_keys(const float* feat, int64_t n_rows, const float* packed, int n
                    int normalize, float* keys, int64_t key_stride, void* stream);
 /* Same, on at most max_ctas persistent CTAs (0 = the default: 132 on a 148-SM B200, where the streaming kernel reads
  * HBM fastest: 6.85 TB/s against 6.44 TB/s with one CTA on every SM).  A smaller number leaves SMs free for kernels
- * running on another stream.  Ignored by the wide-prompt-set kernels. */
+ * running on another stream; the best count differs slightly between individual GPUs (132 on most, 136 on some), which
+ * MocEngine calibrates once per process.  Ignored by the wide-prompt-set kernels. */
 int moc_score_keys_ex(const float* feat, int64_t n_rows, const float* packed, int n_classes, int n_ext,
                       int normalize, float* keys, int64_t key_stride, int max_ctas, void* stream);
 

@@ -463,7 +463,7 @@ static int launch_regw(const float* feat, int64_t n_rows, const float* packed, i
                                   (int)smem));
     const int64_t n_sg = (n_rows + SG_ROWS - 1) / SG_ROWS;
     int64_t ctas = (n_sg + SK_WARPS - 1) / SK_WARPS;
-    const int64_t cap = max_ctas > 0 && max_ctas < stream_cta_cap() ? max_ctas : stream_cta_cap();
+    const int64_t cap = max_ctas > 0 ? (max_ctas < sm_count() ? max_ctas : sm_count()) : stream_cta_cap();
     if (ctas > cap) ctas = cap;
     score_keys_regw_kernel<NC, NORM><<<(unsigned)ctas, SK_WARPS * 32, smem, st>>>(feat, n_rows, packed, C, keys,
                                                                                 key_stride);

@@ -66,7 +66,42 @@ class MocEngine:
         r0, r1 = store.offsets_h[lo], store.offsets_h[hi]
         return self._score(store.feat[r0:r1])
 
+    # The streaming kernel's best CTA count is a property of the individual GPU (132 on most B200s, 136 on some, DESIGN
+    # section 4).  The first large scoring call of a process times a few candidates on the caller's own data - the
+    # results are identical whatever the count - and every later call on that device uses the winner.
+    _TUNED_CTAS: Dict[int, int] = {}
+    _TUNE_CANDIDATES = (132, 128, 136, 124, 140)
+    _TUNE_MIN_ROWS = 4_000_000
+
+    def _tuned_ctas(self, feat: torch.Tensor) -> int:
+        import os
+        dev = feat.device.index if feat.device.index is not None else torch.cuda.current_device()
+        got = MocEngine._TUNED_CTAS.get(dev)
+        if got is not None:
+            return got
+        if (self.prompts.tc is not None or feat.size(0) < self._TUNE_MIN_ROWS
+                or os.environ.get("MOC_SCORE_AUTOTUNE", "1") == "0"
+                or torch.cuda.get_device_properties(dev).multi_processor_count != 148):
+            return 0                                   # the kernel's built-in default; try again on a larger call
+        scratch = torch.empty(ops.num_key_planes(self.n_classes), feat.size(0), dtype=torch.float32, device=feat.device)
+        best = {c: float("inf") for c in self._TUNE_CANDIDATES}
+        for _ in range(3):                             # interleaved rounds, minimum per candidate
+            for c in self._TUNE_CANDIDATES:
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                ops.score_keys(feat, self.prompts, self.normalize, out=scratch, max_ctas=c)
+                b.record()
+                b.synchronize()
+                best[c] = min(best[c], a.elapsed_time(b))
+        winner = min(best, key=best.get)
+        if best[winner] > 0.995 * best[132]:           # not clearly better than the default: keep the default
+            winner = 132
+        MocEngine._TUNED_CTAS[dev] = winner
+        return winner
+
     def _score(self, feat: torch.Tensor, out: Optional[torch.Tensor] = None, max_ctas: int = 0) -> torch.Tensor:
+        if max_ctas == 0:
+            max_ctas = self._tuned_ctas(feat)
         if self.score_events is None:
             return ops.score_keys(feat, self.prompts, self.normalize, out=out, max_ctas=max_ctas)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -198,3 +198,27 @@ def test_cached_scores_are_bit_identical(golden):
     # waves: force several small waves and compare with the single-wave result
     s = M.MocEngine(loops.zeroshot_weights, loops.zeroshot_weights_ext, j, k, max_wave_rows=300)
     assert torch.equal(la, s.eval_logits(store, model.head_params()))
+
+
+def test_score_cta_calibration_changes_nothing_but_speed(monkeypatch):
+    """MocEngine times a few CTA counts for the streaming kernel on its first large call and keeps the fastest for the
+    device; keys are bit-identical for every count, with the calibration on or off."""
+    import moc_b200
+    from moc_b200 import ops, synthetic
+    from moc_b200.engine import MocEngine
+    c = 2
+    w, we = synthetic.prompt_matrices(c, device=DEV)
+    store = moc_b200.RaggedBagStore.synthetic([3000] * 40, c, we, cohort_seed=5, device=DEV)
+    ref = ops.score_keys(store.feat, ops.Prompts.pack(w, we))
+    for cap in (1, 7, 100, 124, 132, 148, 1000):
+        assert torch.equal(ops.score_keys(store.feat, ops.Prompts.pack(w, we), max_ctas=cap), ref), cap
+    monkeypatch.setattr(MocEngine, "_TUNE_MIN_ROWS", 100_000)
+    monkeypatch.setattr(MocEngine, "_TUNED_CTAS", {})
+    eng = MocEngine(w, we, 400, 10)
+    assert torch.equal(eng.keys_for(store), ref)
+    dev = torch.cuda.current_device()
+    if torch.cuda.get_device_properties(dev).multi_processor_count == 148:
+        assert MocEngine._TUNED_CTAS.get(dev) in MocEngine._TUNE_CANDIDATES
+    monkeypatch.setenv("MOC_SCORE_AUTOTUNE", "0")
+    monkeypatch.setattr(MocEngine, "_TUNED_CTAS", {})
+    assert torch.equal(eng.keys_for(store), ref) and MocEngine._TUNED_CTAS == {}
