@@ -73,7 +73,7 @@ class MocEngine:
     _TUNE_CANDIDATES = (132, 128, 136, 124, 140)
     _TUNE_MIN_ROWS = 4_000_000
 
-    def _tuned_ctas(self, feat: torch.Tensor) -> int:
+    def _tuned_ctas(self, feat: torch.Tensor, scratch: torch.Tensor) -> int:
         import os
         dev = feat.device.index if feat.device.index is not None else torch.cuda.current_device()
         got = MocEngine._TUNED_CTAS.get(dev)
@@ -83,7 +83,6 @@ class MocEngine:
                 or os.environ.get("MOC_SCORE_AUTOTUNE", "1") == "0"
                 or torch.cuda.get_device_properties(dev).multi_processor_count != 148):
             return 0                                   # the kernel's built-in default; try again on a larger call
-        scratch = torch.empty(ops.num_key_planes(self.n_classes), feat.size(0), dtype=torch.float32, device=feat.device)
         best = {c: float("inf") for c in self._TUNE_CANDIDATES}
         for _ in range(3):                             # interleaved rounds, minimum per candidate
             for c in self._TUNE_CANDIDATES:
@@ -101,7 +100,9 @@ class MocEngine:
 
     def _score(self, feat: torch.Tensor, out: Optional[torch.Tensor] = None, max_ctas: int = 0) -> torch.Tensor:
         if max_ctas == 0:
-            max_ctas = self._tuned_ctas(feat)
+            if out is None:     # the calibration launches write the same keys into the buffer the real launch fills
+                out = torch.empty(ops.num_key_planes(self.n_classes), feat.size(0), dtype=torch.float32, device=feat.device)
+            max_ctas = self._tuned_ctas(feat, out)
         if self.score_events is None:
             return ops.score_keys(feat, self.prompts, self.normalize, out=out, max_ctas=max_ctas)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
