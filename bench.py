@@ -3,22 +3,28 @@
 
     python bench.py --gpus 1 --steps 20 --warmup 3
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
-    python bench.py --impl reference            # the reference algorithm on the host cores
+    python bench.py --impl reference            # the reference's own evaluation() on the host cores
+    torchrun ... bench.py --gpus N --scaling strong --workload cfg5     # one fixed cohort, LPT-sharded over N GPUs
 
 Metric (BASELINE.json): slides/s - with patches/s and the streaming kernel's HBM GB/s beside it - on
 configs[1]: NSCLC-shaped (C=2, 4 normal-tissue prompts), 1000 slides x 20 000 patches per GPU, J=400, K=10.
 One *step* is one evaluation pass of the hot path over every slide of the split: score all patches, make the
 four top-J selections and their union, gate + combine the selected patches, pool to bag logits, cross-entropy.
-Per-GPU work is fixed as N grows (slides are sharded, "weak" scaling); with N>1 every step ends with the
-all-gather of the bag logits, the one exchange the evaluation loop has.
+Default ("weak"): per-GPU work is fixed as N grows (every rank holds its own `slides` bags); with N>1 every step
+ends with the all-gather of the bag logits, the one exchange the evaluation loop has, and after the timed region
+rank 0 recomputes a sample of the other ranks' slides alone (`shard_check`).  `--scaling strong`: ONE cohort of
+`slides` bags is partitioned over the ranks with moc_b200.dist.Shard (LPT on patch count), every step gathers
+with Shard.gather and computes loss / predictions on the gathered split, as the sharded loops do.
 
 `value`  : bags resident in HBM when the timed region starts (CUDA events, max over ranks).
 `e2e`    : the same pass through MocEngine.eval_logits_host with the bags in pinned HOST memory - every
            step copies all its features host->device (double-buffered on a copy stream) and reads the logits
-           back device->host.
+           back device->host.  `h2d_ceiling_GBps` beside it: the same copies with no compute, all ranks at once.
 `roofline`: the streaming score+keys kernel; algorithmic bytes = 2048 B per patch, timed live with CUDA events
            on its stream inside the timed region, against the measured HBM copy bandwidth.
-`cpu_baseline`: the oracle port of the reference (torch fp32 on all host cores) on a bounded sample.
+`cpu_baseline` / `--impl reference`: the reference's own `evaluation()` (main_moc.py:462-520, lifted unmodified from
+           the staged copy in oracle/_ref, kind "reference"; the oracle port, kind "port", only if that copy is missing)
+           with torch fp32 on all host cores, on a bounded sample of the workload's bags.
 """
 from __future__ import annotations
 
@@ -64,6 +70,9 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: `slides` bags per GPU; strong: `slides` bags in total, LPT-sharded over the GPUs")
+    ap.add_argument("--numa-bind", type=int, default=1, help="bind each rank to its GPU's NUMA node before pinning host memory")
     a = ap.parse_args()
     wl = WORKLOADS[a.workload]
     a.n_classes = wl["n_classes"]
@@ -166,81 +175,112 @@ def sample_sizes(sizes, n):
     return [srt[(2 * i + 1) * len(srt) // (2 * n)] for i in range(n)]
 
 
-def cpu_reference_pass(n_classes, sizes, seconds, threads):
-    """The oracle port of the reference's evaluation() on host cores: returns (slides/s, slides timed, passes)."""
-    from moc_b200 import synthetic
-    from oracle import moc_oracle as O
-    torch.set_num_threads(threads)
-    w, we = synthetic.prompt_matrices(n_classes)
-    bags, labels = synthetic.make_cohort(len(sizes), sizes, n_classes, cohort_seed=99)
-    prm = O.SenetParams.init(0)
-    with torch.no_grad():
-        for x in bags[:2]:  # warm-up
-            O.slide_eval_logits(prm, x, w, we, n_classes, TOPJ, TOPK)
+class CpuArm:
+    """The reference's CPU implementation of one evaluation pass over a bounded sample of the workload's bags.
+
+    kind "reference": `evaluation(model, loader, device, args)` exactly as main_moc.py:462-520 defines it - with
+    `slide_process`, `senet`, the four index selectors and `topj_pooling` it calls - lifted unmodified from the copy
+    staged in oracle/_ref (oracle/ref_loader.py; nothing of ours on that path), run per pass over a loader that yields
+    the reference's (feats, label, coords, path) tuples from bags already in host RAM (no h5 / disk / worker cost).
+    kind "port": oracle/moc_oracle.py's restatement of the same loop, only when the staged copy is missing."""
+
+    def __init__(self, n_classes, sizes, threads):
+        import types
+        from moc_b200 import synthetic
+        from oracle import ref_loader
+        torch.set_num_threads(threads)
+        self.c, self.threads = n_classes, threads
+        self.w, self.we = synthetic.prompt_matrices(n_classes)
+        self.bags, self.labels = synthetic.make_cohort(len(sizes), sizes, n_classes, cohort_seed=99)
+        self.sizes = list(sizes)
+        g = torch.Generator().manual_seed(0)
+        w1 = (torch.rand(64, 512, generator=g) * 2 - 1) * 512 ** -0.5
+        b1 = (torch.rand(64, generator=g) * 2 - 1) * 512 ** -0.5
+        w2 = (torch.rand(4, 64, generator=g) * 2 - 1) * 0.125
+        b2 = (torch.rand(4, generator=g) * 2 - 1) * 0.125
+        # roc_auc_score needs every class among the sample's labels: the sample holds >= C slides (label = i mod C)
+        if ref_loader.available() and len(self.bags) >= n_classes and os.environ.get("MOC_BENCH_CPU_KIND", "") != "port":
+            self.kind = "reference"
+            ref = ref_loader.load()
+            ref.set_weights(self.w, self.we)
+            model = ref.senet(512, 4)
+            model.load_state_dict({"model.0.weight": w1, "model.0.bias": b1, "model.2.weight": w2, "model.2.bias": b2})
+            loader = ref_loader.RefLoader(ref_loader.RefDataset(self.bags, self.labels))
+            args = types.SimpleNamespace(disable_tqdm=True, n_classes=n_classes, topj=TOPJ, topk=TOPK,
+                                         discard_classifiers=[], pretrain="conch", ablation_study="none")
+            self._pass = lambda: ref.evaluation(model, loader, "cpu", args)
+            self.what = "the reference's evaluation() lifted unmodified from oracle/_ref (main_moc.py:462-520), torch fp32"
+        else:
+            from oracle import moc_oracle as O
+            self.kind = "port"
+            prm = O.SenetParams(w1, b1, w2, b2)
+
+            def run():
+                with torch.no_grad():
+                    for x, y in zip(self.bags, self.labels):
+                        float(O.cross_entropy(O.slide_eval_logits(prm, x, self.w, self.we, n_classes, TOPJ, TOPK), y))
+            self._pass = run
+            self.what = "oracle port of evaluation() (oracle/moc_oracle.py), torch fp32"
+
+    def run_for(self, seconds):
+        """Whole passes over the sample until `seconds` have elapsed: (slides, passes, elapsed)."""
         done, passes, t0 = 0, 0, time.perf_counter()
         while True:
-            for x, y in zip(bags, labels):
-                lg = O.slide_eval_logits(prm, x, w, we, n_classes, TOPJ, TOPK)
-                float(O.cross_entropy(lg, y))
-                done += 1
+            self._pass()
+            done += len(self.bags)
             passes += 1
             dt = time.perf_counter() - t0
             if dt >= seconds:
-                break
-    return done / dt, done, passes, dt
+                return done, passes, dt
+
+    def describe(self, done, passes, dt):
+        return ("%d distinct slides (%d..%d patches, spread over the workload's sizes) in host RAM, %d passes "
+                "(%d slides, %.1f s); %s" % (len(self.sizes), min(self.sizes), max(self.sizes), passes, done, dt, self.what))
+
+
+def make_config(a, world):
+    """The `config` object of the JSON line - the same keys and values from both arms, so the driver can compare them."""
+    mean = sum(a.sizes) / max(len(a.sizes), 1)
+    return {"workload": a.desc, "slides_per_gpu": a.slides if a.scaling == "weak" else None,
+            "slides_total": a.slides * world if a.scaling == "weak" else a.slides,
+            "patches_per_slide": a.patches if a.patches else "log-uniform 1000..100000 (mean %.0f)" % mean,
+            "n_classes": a.n_classes, "n_ext": a.n_classes + 4, "topj": TOPJ, "topk": TOPK,
+            "step": "one evaluation pass over every slide: score + select + gate/combine + pool + CE",
+            "l2": "inputs are %.1f GB per GPU, far larger than the 126 MB L2: no flush needed"
+                  % (mean * a.slides / (world if a.scaling == "strong" else 1) * 2048 / 1e9),
+            "sharding": ("single GPU" if world == 1 else
+                         "slides sharded over GPUs, logits all-gathered per step" if a.scaling == "weak" else
+                         "one cohort LPT-partitioned over GPUs (dist.Shard), Shard.gather per step")}
 
 
 def run_reference(a):
-    """--impl reference: the reference's CPU algorithm (oracle port, kind "port") on this box's host cores."""
+    """--impl reference: the reference's own CPU implementation of the pass on this box's host cores (CpuArm)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     threads = os.cpu_count() or 1
-    sizes = sample_sizes(a.sizes, 32)
-    n_slides = len(sizes)
-    N_CLASSES = a.n_classes
-    per_step = []
+    sizes = sample_sizes(a.sizes, max(32, a.n_classes))
+    arm = CpuArm(a.n_classes, sizes, threads)
     total = a.steps + a.warmup
-    budget = max(1.0, min(150.0, 150.0) / max(total, 1))
-    from moc_b200 import synthetic
-    from oracle import moc_oracle as O
-    torch.set_num_threads(threads)
-    w, we = synthetic.prompt_matrices(N_CLASSES)
-    bags, labels = synthetic.make_cohort(n_slides, sizes, N_CLASSES, cohort_seed=99)
-    prm = O.SenetParams.init(0)
+    budget = min(2.0, max(0.5, 150.0 / max(total, 1)))     # each step: whole passes over the sample for ~budget seconds
     mean_patches = sum(a.sizes) / len(a.sizes)
-
-    def step():
-        t0 = time.perf_counter()
-        n = 0
-        with torch.no_grad():
-            while True:
-                for x, y in zip(bags, labels):
-                    lg = O.slide_eval_logits(prm, x, w, we, N_CLASSES, TOPJ, TOPK)
-                    float(O.cross_entropy(lg, y))
-                    n += 1
-                if time.perf_counter() - t0 >= min(budget, 2.0):
-                    break
-        return n, time.perf_counter() - t0
-
     for _ in range(a.warmup):
-        step()
-    n_tot, t_tot = 0, 0.0
+        arm.run_for(budget)
+    n_tot, t_tot, p_tot = 0, 0.0, 0
     for _ in range(a.steps):
-        n, dt = step()
-        n_tot += n
-        t_tot += dt
-        per_step.append(dt / n)
+        n, passes, dt = arm.run_for(budget)
+        n_tot, t_tot, p_tot = n_tot + n, t_tot + dt, p_tot + passes
     value = n_tot / t_tot
-    sample = "%d distinct slides (%d..%d patches, spread over the workload's sizes) in host RAM, looped; %d slides " \
-             "timed over %d steps" % (n_slides, min(sizes), max(sizes), n_tot, a.steps)
+    cfg = make_config(a, max(world, a.gpus))
     line = {
         "impl": "reference", "metric": "slides_per_sec", "value": value, "unit": "slides/s", "n_gpus": a.gpus,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * t_tot / max(a.steps, 1),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": a.desc, "note": "reference algorithm (oracle port) on host cores; bounded sample"},
-        "patches_per_sec": value * mean_patches,
-        "cpu_baseline": {"value": value, "unit": "slides/s", "cores": threads, "kind": "port", "sample": sample},
+        "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": cfg, "patches_per_sec": value * mean_patches,
+        "note": "reference arm: host cores only, a bounded sample of the config's workload (cpu_baseline.sample)",
+        "cpu_baseline": {"value": value, "unit": "slides/s", "cores": threads, "kind": arm.kind,
+                         "sample": arm.describe(n_tot, p_tot, t_tot)},
         "e2e": {"value": value, "unit": "slides/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -249,10 +289,25 @@ def run_reference(a):
 
 
 # ------------------------------------------------------------------------------------------------
+def _store_for(ids, sizes, labels, n_classes, we, cohort_seed, dev):
+    """Slides `ids` of the cohort (`sizes`, `labels`, seed) as a resident store: slide i is the same bag whichever
+    rank builds it (its generator seed depends on the cohort seed and i only)."""
+    from moc_b200 import synthetic
+    from moc_b200.bag_store import RaggedBagStore
+    offs = [0]
+    for i in ids:
+        offs.append(offs[-1] + int(sizes[i]))
+    feat = torch.empty(offs[-1], 512, dtype=torch.float32, device=dev)
+    for k, i in enumerate(ids):
+        synthetic.make_bag(int(sizes[i]), labels[i], we, n_classes, synthetic.slide_seed(cohort_seed, i), device=dev,
+                           out=feat[offs[k]:offs[k + 1]])
+    return RaggedBagStore(feat, offs, [labels[i] for i in ids])
+
+
 def run_ours(a):
     from moc_b200 import ops, synthetic
-    from moc_b200.bag_store import HostBags, HostChunk, RaggedBagStore
-    from moc_b200.dist import barrier_max_ms, init_from_env
+    from moc_b200.bag_store import HostBags, HostChunk
+    from moc_b200.dist import Shard, barrier_max_ms, bind_to_gpu_numa_node, init_from_env
     from moc_b200.engine import MocEngine
     import torch.distributed as dist
 
@@ -262,10 +317,28 @@ def run_ours(a):
     dev = torch.device("cuda", local)
     if world != a.gpus and rank == 0:
         print("warning: --gpus %d but WORLD_SIZE=%d" % (a.gpus, world), file=sys.stderr)
+    # multi-GPU boxes are multi-socket: bind each rank to its GPU's NUMA node before any pinned allocation (the N=1 run
+    # keeps every core: its cpu_baseline leg must see the whole host)
+    numa = bind_to_gpu_numa_node(local) if (a.numa_bind and world > 1) else None
 
     N_CLASSES = a.n_classes
+    strong = a.scaling == "strong"
     w, we = synthetic.prompt_matrices(N_CLASSES, device=dev)
-    store = RaggedBagStore.synthetic(a.sizes, N_CLASSES, we, cohort_seed=1000 + rank, device=dev)
+    labels_all = [i % N_CLASSES for i in range(len(a.sizes))]
+    if strong:      # one cohort for the whole job, LPT-partitioned by patch count
+        shard = Shard(a.sizes, rank, world)
+        seed_of_rank = [1000] * world
+        need = sum(a.sizes[i] for i in shard.ids) * 2048
+        free = torch.cuda.mem_get_info(dev)[0]
+        if need > 0.9 * free:
+            raise SystemExit("--scaling strong: this rank's shard needs %.0f GB, %.0f GB free: use more GPUs or --slides"
+                             % (need / 1e9, free / 1e9))
+        ids = shard.ids
+    else:           # every rank holds its own `slides` bags (cohort seed 1000 + rank)
+        shard = None
+        seed_of_rank = [1000 + r for r in range(world)]
+        ids = list(range(len(a.sizes)))
+    store = _store_for(ids, a.sizes, labels_all, N_CLASSES, we, seed_of_rank[rank], dev)
     rows_per_gpu = store.total_rows
     eng = MocEngine(w, we, TOPJ, TOPK)
     g = torch.Generator().manual_seed(0)
@@ -273,12 +346,17 @@ def run_ours(a):
                          ((torch.rand(64, generator=g) * 2 - 1) * 512 ** -0.5).to(dev),
                          ((torch.rand(4, 64, generator=g) * 2 - 1) * 0.125).to(dev),
                          ((torch.rand(4, generator=g) * 2 - 1) * 0.125).to(dev))
-    gathered = [torch.empty(a.slides, N_CLASSES + 1, device=dev) for _ in range(world)] if world > 1 else None
+    n_local = len(store)
+    gathered = [torch.empty(n_local, N_CLASSES + 1, device=dev) for _ in range(world)] if world > 1 and not strong else None
 
     def step():
         logits = eng.eval_logits(store, prm)
+        if strong:      # the sharded loops' exchange (padded all-gather + scatter back into split order), then the
+            all_logits, all_labels = shard.gather(logits, store.labels)   # loss / predictions on the whole split
+            loss, _, pred = ops.cross_entropy(all_logits, all_labels, want_pred=True)
+            return all_logits, loss
         loss, _, pred = ops.cross_entropy(logits, store.labels, want_pred=True)
-        if world > 1:  # the evaluation loop's one exchange: every rank gets every shard's logits + labels
+        if world > 1:   # the evaluation loop's one exchange: every rank gets every shard's logits + labels
             buf = torch.cat([logits, store.labels.unsqueeze(1).float()], dim=1)
             dist.all_gather(gathered, buf)
         return logits, loss
@@ -303,13 +381,45 @@ def run_ours(a):
         dist.barrier()
     sampler.active = False
     launches = ops.LAUNCHES - launches0
-    ms_total = barrier_max_ms(e0.elapsed_time(e1), dev)
+    ms_local = e0.elapsed_time(e1)
+    ms_total = barrier_max_ms(ms_local, dev)
     score_ms = [x.elapsed_time(y) for x, y, _ in eng.score_events]
     score_rows = [r for _, _, r in eng.score_events]
     eng.score_events = None
     ms_step = ms_total / a.steps
-    slides_total = a.slides * world
+    slides_total = len(a.sizes) if strong else a.slides * world
+    rows_total = sum(a.sizes) if strong else rows_per_gpu * world
     value = slides_total / (ms_step * 1e-3)
+
+    # ---- multi-GPU correctness inside the bench: rank 0 recomputes slides other ranks own, alone ---------------
+    shard_check = None
+    if world > 1:
+        if strong:
+            full = logits                                         # [n_global, C] in split order, same on every rank
+            owner = {i: r for r, v in enumerate(shard.all_ids) for i in v}
+            pick = [v[k] for r, v in enumerate(shard.all_ids) if r != 0 for k in (0, len(v) // 2, len(v) - 1) if v][:12]
+            row_of = {i: i for i in pick}
+        else:
+            full = torch.cat([p_[:, :N_CLASSES] for p_ in gathered], dim=0)          # rank-major
+            pick_rk = [(r, k) for r in range(1, world) for k in (0, n_local // 2, n_local - 1)][:12]
+        if rank == 0:
+            worst, n_chk = 0.0, 0
+            if strong:
+                for i in pick:
+                    st1 = _store_for([i], a.sizes, labels_all, N_CLASSES, we, 1000, dev)
+                    alone = eng.eval_logits(st1, prm)
+                    worst = max(worst, float((alone[0] - full[row_of[i]]).abs().max()))
+                    n_chk += 1
+            else:
+                for r, k in pick_rk:
+                    st1 = _store_for([k], a.sizes, labels_all, N_CLASSES, we, seed_of_rank[r], dev)
+                    alone = eng.eval_logits(st1, prm)
+                    worst = max(worst, float((alone[0] - full[r * n_local + k]).abs().max()))
+                    n_chk += 1
+            shard_check = {"slides_checked": n_chk, "max_abs_diff": worst, "ok": bool(worst == 0.0),
+                           "how": "rank 0 regenerates slides owned by the other ranks and runs them alone; their bag "
+                                  "logits must equal the gathered rows bit for bit"}
+        dist.barrier()
 
     # ---- roofline of the streaming kernel (rank 0's launches) ----------------------------------------
     peak, peak_src = measured_peak()
@@ -321,7 +431,7 @@ def run_ours(a):
     roofline = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": rows_per_launch * 2048, "avg_launch_ms": avg_ms,
-                "launches_timed": len(score_ms), "share_of_step": avg_ms * len(score_ms) / a.steps / ms_step,
+                "launches_timed": len(score_ms), "share_of_step": avg_ms * len(score_ms) / a.steps / (ms_local / a.steps),
                 "frac_of_8TBps_nominal": achieved / 8000.0,
                 "note": "peak is the driver-measured COPY bandwidth (read + write); a read-only bulk-copy ring with no "
                         "compute reads 7.3-7.4 TB/s on this part (tools/probe_stream.cu), so this read-mostly kernel "
@@ -331,7 +441,7 @@ def run_ours(a):
     # ---- end to end from pinned host memory -------------------------------------------------------------
     e2e = None
     if not a.no_e2e:
-        n_host = min(a.e2e_host_slides, a.slides)
+        n_host = min(a.e2e_host_slides, n_local)
         pool_rows = 2_621_440 if world <= 4 else 1_310_720   # pinned pool per rank: ~5.4 GB, ~2.7 GB on an 8-GPU box
         while n_host > 1 and store.offsets_h[n_host] > pool_rows:
             n_host -= 1
@@ -344,7 +454,7 @@ def run_ours(a):
             pinned.copy_(store.feat[r0:r1])
             chunks.append(HostChunk(pinned, [v - r0 for v in store.offsets_h[lo:hi + 1]], store.labels_h[lo:hi], dev))
         seq, k = [], 0
-        remaining = a.slides
+        remaining = n_local
         while remaining > 0:  # the step's cohort: cycle through the pinned chunks until every slide is covered
             ch = chunks[k % len(chunks)]
             n = len(ch.labels_h)
@@ -354,27 +464,41 @@ def run_ours(a):
             remaining -= len(ch.labels_h)
             k += 1
         host = HostBags(seq, dev)
-        out_h = torch.empty(a.slides, N_CLASSES, dtype=torch.float32, pin_memory=True)
+        out_h = torch.empty(n_local, N_CLASSES, dtype=torch.float32, pin_memory=True)
 
         def e2e_step():
             lg = eng.eval_logits_host(host, prm)
             out_h.copy_(lg, non_blocking=True)
             torch.cuda.current_stream().synchronize()  # the caller holds the logits on the host
 
-        e2e_step()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(a.e2e_steps):
-            e2e_step()
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        dt = barrier_max_ms(dt * 1e3, dev) / 1e3
-        e2e = {"value": slides_total / (dt / a.e2e_steps), "unit": "slides/s", "steps": a.e2e_steps,
-               "h2d_bytes_per_step": host.h2d_bytes(), "d2h_bytes_per_step": a.slides * N_CLASSES * 4,
-               "ms_per_step": 1e3 * dt / a.e2e_steps, "h2d_GBps": host.h2d_bytes() / (dt / a.e2e_steps) / 1e9,
-               "host_pool": "%d distinct slides pinned, cycled to %d per step" % (n_host, a.slides),
+        def copies_only():   # the same pinned chunks through the same two staging buffers, no kernels: the H2D ceiling
+            with torch.cuda.stream(host.copy_stream):
+                for ci, ch in enumerate(host.chunks):
+                    host.staging[ci % 2][:ch.rows].copy_(ch.feat, non_blocking=True)
+            host.copy_stream.synchronize()
+
+        def timed(fn, reps):
+            fn()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                fn()
+            torch.cuda.synchronize()
+            return barrier_max_ms((time.perf_counter() - t0) * 1e3, dev) / 1e3 / reps
+
+        dt_copy = timed(copies_only, 2)
+        dt = timed(e2e_step, a.e2e_steps)
+        bytes_local = host.h2d_bytes()
+        e2e = {"value": slides_total / dt, "unit": "slides/s", "steps": a.e2e_steps,
+               "h2d_bytes_per_step": bytes_local, "d2h_bytes_per_step": n_local * N_CLASSES * 4,
+               "ms_per_step": 1e3 * dt, "h2d_GBps": bytes_local / dt / 1e9,
+               "h2d_ceiling_GBps": bytes_local / dt_copy / 1e9,
+               "h2d_ceiling_how": "the step's pinned chunks copied with cudaMemcpyAsync alone (no kernels), all %d ranks "
+                                  "at once, slowest rank" % world,
+               "numa_node": numa,
+               "host_pool": "%d distinct slides pinned, cycled to %d per step" % (n_host, n_local),
                "api": "MocEngine.eval_logits_host"}
         del host, seq, chunks
     sampler.stop_flag = True
@@ -383,30 +507,30 @@ def run_ours(a):
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        ss = sample_sizes(a.sizes, 32)
-        v, done, passes, dt = cpu_reference_pass(N_CLASSES, ss, a.cpu_seconds, threads)
-        cpu = {"value": v, "unit": "slides/s", "cores": threads, "kind": "port",
-               "sample": "%d distinct slides (%d..%d patches) in host RAM, looped %d times (%d slides, %.1f s); "
-                         "oracle port of evaluation(), torch fp32" % (len(ss), min(ss), max(ss), passes, done, dt)}
+        arm = CpuArm(N_CLASSES, sample_sizes(a.sizes, max(32, N_CLASSES)), threads)
+        arm.run_for(0.0)    # warm-up pass
+        done, passes, dt = arm.run_for(a.cpu_seconds)
+        cpu = {"value": done / dt, "unit": "slides/s", "cores": threads, "kind": arm.kind,
+               "sample": arm.describe(done, passes, dt)}
 
     if rank == 0:
         line = {
             "metric": "slides_per_sec", "value": value, "unit": "slides/s", "n_gpus": world, "steps": a.steps,
-            "warmup": max(a.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(a.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": a.scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": a.desc, "slides_per_gpu": a.slides,
-                       "patches_per_slide": a.patches if a.patches else "log-uniform 1000..100000 (mean %.0f)"
-                                            % (rows_per_gpu / a.slides),
-                       "n_classes": N_CLASSES, "n_ext": N_CLASSES + 4, "topj": TOPJ, "topk": TOPK,
-                       "step": "one evaluation pass over every slide: score + select + gate/combine + pool + CE",
-                       "l2": "inputs are %.1f GB per GPU, far larger than the 126 MB L2: no flush needed"
-                             % (store.nbytes() / 1e9),
-                       "sharding": "slides sharded over GPUs, logits all-gathered per step" if world > 1 else "single GPU"},
-            "patches_per_sec": rows_per_gpu * world / (ms_step * 1e-3),
-            "algorithmic_GBps_whole_step": rows_per_gpu * world * 2048 / (ms_step * 1e-3) / 1e9,
+            "config": make_config(a, world),
+            "patches_per_sec": rows_total / (ms_step * 1e-3),
+            "algorithmic_GBps_whole_step": rows_total * 2048 / (ms_step * 1e-3) / 1e9,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
             "clocks": sampler.summary(),
         }
+        if shard_check is not None:
+            line["shard_check"] = shard_check
+        if strong:
+            loads = [sum(a.sizes[i] for i in v) for v in shard.all_ids]
+            line["load_balance"] = {"rows_max": max(loads), "rows_min": min(loads),
+                                    "max_over_mean": max(loads) / (sum(loads) / len(loads)),
+                                    "slides_per_rank": [len(v) for v in shard.all_ids]}
         OUT.write(json.dumps(line) + "\n")
         OUT.flush()
     if world > 1:

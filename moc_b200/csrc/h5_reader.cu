@@ -17,6 +17,7 @@
 #include <unistd.h>
 
 #include <string>
+#include <unordered_set>
 #include <vector>
 
 #include "common.cuh"
@@ -128,6 +129,7 @@ int walk_object_header(Reader& r, uint64_t addr, F cb) {
             const uint8_t* d = r.at(block + pos + 8, size);
             if (!d && size) return fail("object header message outside the file");
             if (type == 0x0010) {
+                if (size < r.f.so + r.f.sl) return fail("truncated object header continuation message");
                 pending.push_back({Reader::le(d, r.f.so), Reader::le_raw(d + r.f.so, r.f.sl)});
             } else {
                 const int rc = cb(type, d, size);
@@ -297,9 +299,11 @@ int read_chunked(const H5File& f, const H5Dataset& ds, uint8_t* dst) {
     memset(dst, 0, n_elems(ds) * es);
     if (ds.chunk_btree == H5_UNDEF) return MOC_OK;  // nothing allocated yet
     std::vector<uint64_t> stack{ds.chunk_btree};
-    for (uint64_t guard = 0; !stack.empty() && guard < (1ull << 32); ++guard) {
+    std::unordered_set<uint64_t> visited;   // a node reached twice means a cyclic (corrupt) tree: fail, do not spin
+    while (!stack.empty()) {
         const uint64_t node = stack.back();
         stack.pop_back();
+        if (!visited.insert(node).second) return fail("chunk B-tree is cyclic (corrupt file)");
         const uint8_t* n = r.at(node, 8 + 2 * f.so);
         if (!n || memcmp(n, "TREE", 4) != 0 || n[4] != 1) return fail("chunk B-tree node not found");
         const int level = n[5], used = (int)Reader::le_raw(n + 6, 2);

@@ -397,7 +397,7 @@ compact_kernel(const unsigned int* __restrict__ bitmap, const int64_t* __restric
     __syncthreads();
     if (row1 > row0) {
         const int64_t w0 = row0 >> 5, w1 = (row1 - 1) >> 5;
-        const int64_t out0 = sel_base[slide];
+        const int64_t out0 = sel_base[slide], out_end = sel_base[slide + 1];
         for (int64_t wb = w0; wb <= w1; wb += CMP_THREADS) {
             const int64_t w = wb + tid;
             unsigned int bits = 0, kept = 0;
@@ -436,8 +436,10 @@ compact_kernel(const unsigned int* __restrict__ bitmap, const int64_t* __restric
             while (bits) {
                 const int b = __ffs(bits) - 1;
                 bits &= bits - 1;
-                sel_rows[pos] = (int32_t)((w << 5) + b);
-                sel_local[pos] = kept_before + __popc(kept & ((1u << b) - 1u));
+                if (pos < out_end) {   // a region smaller than the selection (a caller's stale layout) must not overrun
+                    sel_rows[pos] = (int32_t)((w << 5) + b);
+                    sel_local[pos] = kept_before + __popc(kept & ((1u << b) - 1u));
+                }
                 ++pos;
             }
             __syncthreads();
@@ -446,7 +448,8 @@ compact_kernel(const unsigned int* __restrict__ bitmap, const int64_t* __restric
         }
     }
     __syncthreads();
-    const int64_t count = (int64_t)(running & 0xffffffffull);
+    int64_t count = (int64_t)(running & 0xffffffffull);
+    if (count > sel_base[slide + 1] - sel_base[slide]) count = sel_base[slide + 1] - sel_base[slide];
     if (tid == 0) sel_count[slide] = (int32_t)count;
     // unused tail of this slide's region: -1, so consumers can walk regions without the counts
     for (int64_t p = sel_base[slide] + count + tid; p < sel_base[slide + 1]; p += CMP_THREADS) sel_rows[p] = -1;

@@ -180,11 +180,25 @@ class Generic_MIL_Dataset(Generic_WSI_Classification_Dataset):
         return torch.load(self._bag_path(slide_id)), label
 
     # ---- addition: the split as a GPU-resident ragged store ----------------------------------------------------
-    def to_store(self, device="cuda") -> RaggedBagStore:
-        """Every slide in manifest order, read once (native HDF5 reader or torch.load) into one buffer on ``device``.
-        With h5 bags the store's slide ids are the ``full_path`` strings the reference's loops see."""
+    def bag_sizes(self):
+        """Patch count of every slide in manifest order without reading the features (h5: dataset header only)."""
         ids = self.slide_data["slide_id"].astype(str).tolist()
-        labels = [int(self._label_of(r)) for r in range(len(ids))]
+        if self.use_h5:
+            from .h5bag import H5File
+            sizes = []
+            for s in ids:
+                with H5File(self._bag_path(s)) as f:
+                    sizes.append(int(f["features"].shape[0]))
+            return sizes
+        return [int(torch.load(self._bag_path(s), map_location="cpu").size(0)) for s in ids]
+
+    def to_store(self, device="cuda", rows=None) -> RaggedBagStore:
+        """The slides (all of them, or manifest positions ``rows`` - one rank's shard) in manifest order, read once
+        (native HDF5 reader or torch.load) into one buffer on ``device``.  With h5 bags the store's slide ids are the
+        ``full_path`` strings the reference's loops see."""
+        rows = range(self.real_len()) if rows is None else list(rows)
+        ids = [str(self.slide_data["slide_id"].iat[r]) for r in rows]
+        labels = [int(self._label_of(r)) for r in rows]
         if not self.use_h5:
             return RaggedBagStore.from_pt_dir(self.data_dir, ids, labels, device)
         st = RaggedBagStore.from_h5_dir(self.data_dir, ids, labels, device)

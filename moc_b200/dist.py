@@ -82,6 +82,58 @@ class Shard:
         return out, lab
 
 
+def bind_to_gpu_numa_node(local_rank: int) -> Optional[int]:
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off (read from sysfs), so that the pinned host
+    buffers it allocates afterwards are first-touched on that node and the H2D copies do not cross the socket link.
+    Returns the node, or None when the topology cannot be read (nothing is changed then)."""
+    try:
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+        dev_id = torch.cuda.get_device_properties(local_rank).pci_device_id
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0" % (dom, bus, dev_id)
+        node = int(open(os.path.join(path, "numa_node")).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
+def sync_seed(seed: Optional[int] = None, group=None) -> Optional[int]:
+    """Every rank seeds torch's CPU generator with the same value: rank 0's ``seed`` argument, or - when the run is
+    unseeded like the reference's - a fresh random one that rank 0 draws.  The gate's initial weights and the per-step
+    half masks (``torch.rand(N) > 0.5`` on the CPU default generator, main_moc.py:330) then come out identical on all
+    ranks, which is what makes replicated training bit-identical.  Single process: seeds only if ``seed`` is given."""
+    if not (dist.is_initialized() and dist.get_world_size(group) > 1):
+        if seed is not None:
+            torch.manual_seed(int(seed))
+        return seed
+    val = int(seed) if seed is not None else int.from_bytes(os.urandom(7), "little")
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else "cpu"
+    t = torch.tensor([val], dtype=torch.int64, device=dev)
+    dist.broadcast(t, src=0, group=group)
+    val = int(t.item())
+    torch.manual_seed(val)
+    return val
+
+
+def broadcast_parameters(module: torch.nn.Module, group=None) -> None:
+    """Rank 0's parameters and buffers overwrite every other rank's (in place)."""
+    if not (dist.is_initialized() and dist.get_world_size(group) > 1):
+        return
+    with torch.no_grad():
+        for t in list(module.parameters()) + list(module.buffers()):
+            dist.broadcast(t.data, src=0, group=group)
+
+
 def allreduce_sum(flat: torch.Tensor, group=None) -> torch.Tensor:
     """Sum of the flat gate gradient over ranks (data-parallel training mode; 132 KB, latency-bound)."""
     if dist.is_initialized() and dist.get_world_size(group) > 1:

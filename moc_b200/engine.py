@@ -14,6 +14,7 @@ again, like the reference.
 """
 from __future__ import annotations
 
+import weakref
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence
 
@@ -44,13 +45,23 @@ class MocEngine:
                  cache_scores: bool = False, max_wave_rows: int = 48 * 1024 * 1024):
         self.prompts = ops.Prompts.pack(zeroshot_weights, zeroshot_weights_ext)
         self.n_classes = self.prompts.n_classes
+        # slide_process never reads W_ext[:, :C] (only the background columns matter to it), but zs_evaluation with
+        # bottomk_irrel_classifier_pooling pools (feats @ W_ext)[:, :C] (main_moc.py:428-432,
+        # patch_selection_classifier.py:152-160).  In every shipped prompt file those columns equal W; when they do
+        # not, that pooling mode scores against a second packing whose class columns are W_ext[:, :C].
+        c = self.n_classes
+        self._prompts_ext_fg = None
+        if not torch.equal(zeroshot_weights_ext[:, :c].float(), zeroshot_weights.float()):
+            self._prompts_ext_fg = ops.Prompts.pack(zeroshot_weights_ext[:, :c].contiguous(), zeroshot_weights_ext)
         self.topj, self.topk = int(topj), int(topk)
         self.discard = tuple(discard_classifiers or ())
         self.normalize = bool(normalize)
         self.cache_scores = bool(cache_scores)
         self.max_wave_rows = int(max_wave_rows)
-        self._key_cache: Dict[int, torch.Tensor] = {}
-        self._layout_cache: Dict[tuple, tuple] = {}
+        # per-store state lives exactly as long as the store (or HostBags) object: weak keys, so a new store that
+        # happens to reuse a dead one's address can never see its key planes or selection layout
+        self._key_cache: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
+        self._layout_cache: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
         self.score_events = None  # when a list: (start, stop) CUDA events around every scoring launch
 
     # ---- scoring -------------------------------------------------------------------------------
@@ -58,10 +69,10 @@ class MocEngine:
         """Key planes [2C+3, rows] for slides [lo, hi) of the store (whole store when cached)."""
         hi = len(store) if hi is None else hi
         if self.cache_scores:
-            k = self._key_cache.get(id(store))
-            if k is None:
+            k = self._key_cache.get(store)
+            if k is None or k.size(1) != store.total_rows:
                 k = self._score(store.feat)
-                self._key_cache[id(store)] = k
+                self._key_cache[store] = k
             return k[:, store.offsets_h[lo]:store.offsets_h[hi]]
         r0, r1 = store.offsets_h[lo], store.offsets_h[hi]
         return self._score(store.feat[r0:r1])
@@ -116,7 +127,7 @@ class MocEngine:
         if store is None:
             self._key_cache.clear()
         else:
-            self._key_cache.pop(id(store), None)
+            self._key_cache.pop(store, None)
 
     def _waves(self, store: RaggedBagStore):
         """Split the store into runs of whole slides of at most max_wave_rows rows (key-plane memory bound)."""
@@ -129,16 +140,19 @@ class MocEngine:
             lo = hi
 
     def _layout(self, store: RaggedBagStore, lo: int, hi: int):
-        key = (id(store), lo, hi, self.topj)
-        hit = self._layout_cache.get(key)
-        if hit is None:
-            r0 = store.offsets_h[lo]
+        per_store = self._layout_cache.get(store)
+        if per_store is None:
+            per_store = self._layout_cache[store] = {}
+        key = (lo, hi, self.topj)
+        hit = per_store.get(key)
+        r0 = store.offsets_h[lo]
+        if hit is None or hit[1][-1] != store.offsets_h[hi] - r0:
             offs_h = [v - r0 for v in store.offsets_h[lo:hi + 1]]
             offs = (store.offsets[lo:hi + 1] - r0).contiguous()
             base_h = ops.selection_layout(offs_h, self.n_classes, self.topj)
             base = torch.tensor(base_h, dtype=torch.int64, device=store.device)
             hit = (offs, offs_h, base, base_h)
-            self._layout_cache[key] = hit
+            per_store[key] = hit
         return hit
 
     # ---- zero-shot -----------------------------------------------------------------------------
@@ -146,8 +160,12 @@ class MocEngine:
         c = self.n_classes
         sp0, ss, vp0, vs, small = POOLINGS[pooling](c)
         out = torch.empty(len(store), c, dtype=torch.float32, device=store.device)
+        ext_fg = self._prompts_ext_fg if pooling == "bottomk_irrel" else None
         for lo, hi in self._waves(store):
-            keys = self.keys_for(store, lo, hi)
+            if ext_fg is None:
+                keys = self.keys_for(store, lo, hi)
+            else:   # class planes of this pass = feats @ W_ext[:, :C]; the background sum is the same either way
+                keys = ops.score_keys(store.feat[store.offsets_h[lo]:store.offsets_h[hi]], ext_fg, self.normalize)
             offs, _, _, _ = self._layout(store, lo, hi)
             out[lo:hi] = ops.pool_topk(keys, offs, hi - lo, c, self.topk, sp0, ss, vp0, vs, small)
         return out
@@ -223,12 +241,14 @@ class MocEngine:
                 buf.copy_(ch.feat, non_blocking=True)
                 host.ready[b].record(copy)
             cur.wait_event(host.ready[b])
-            key = ("host", id(host), ci, self.topj)
-            lay = self._layout_cache.get(key)
+            per_host = self._layout_cache.get(host)
+            if per_host is None:
+                per_host = self._layout_cache[host] = {}
+            lay = per_host.get((ci, self.topj))
             if lay is None:
                 base_h = ops.selection_layout(ch.offsets_h, c, self.topj)
                 lay = (torch.tensor(base_h, dtype=torch.int64, device=dev), base_h)
-                self._layout_cache[key] = lay
+                per_host[(ci, self.topj)] = lay
             keys = self._score(buf)
             sel = ops.select_union(keys, ch.offsets, ch.offsets_h, c, self.topj, disc, None, lay[0], lay[1])
             ho = ops.head_forward(buf, keys, c, sel, params, act, self.topk)

@@ -40,7 +40,8 @@ def set_prompts(w: torch.Tensor, w_ext: torch.Tensor) -> None:
 def engine_for(args) -> MocEngine:
     if zeroshot_weights is None or zeroshot_weights_ext is None:
         raise _lib.MocError(_lib.E_ARG, "call moc_b200.loops.set_prompts(zeroshot_weights, zeroshot_weights_ext) first")
-    key = (zeroshot_weights.data_ptr(), zeroshot_weights_ext.data_ptr(), int(args.topj), int(args.topk),
+    key = (zeroshot_weights.data_ptr(), zeroshot_weights_ext.data_ptr(), zeroshot_weights._version,
+           zeroshot_weights_ext._version, int(args.topj), int(args.topk),
            tuple(getattr(args, "discard_classifiers", ()) or ()), bool(getattr(args, "cache_scores", False)))
     eng = _ENGINES.get(key)
     if eng is None:
@@ -82,7 +83,10 @@ def _optimizer_step(model, optimizer, flat_grads: torch.Tensor) -> None:
     views = ops.split_grads(flat_grads)
     plain_adam = (type(optimizer) is torch.optim.Adam and all(
         not g.get("amsgrad") and not g.get("maximize") and not g.get("capturable") and not g.get("fused")
-        and not g.get("differentiable") and not isinstance(g["lr"], torch.Tensor) for g in optimizer.param_groups))
+        and not g.get("differentiable") and not g.get("decoupled_weight_decay")
+        and not isinstance(g["lr"], torch.Tensor) for g in optimizer.param_groups)
+        and not getattr(optimizer, "_optimizer_step_pre_hooks", None)
+        and not getattr(optimizer, "_optimizer_step_post_hooks", None))
     if not plain_adam:
         for p, g in zip(params, views):
             p.grad = g.clone()

@@ -110,8 +110,9 @@ def summarize_results(summary_dir: str, shots=(1, 2, 4, 8), folds=(0, 1, 2, 3, 4
     print("end summary")
 
 
-def _real_stores(args, device):
+def _real_stores(args, device, rank=0, world=1):
     from .datasets import Generic_MIL_Dataset
+    from .dist import Shard
     n_classes, names, _, _ = DATASETS[args.dataset]
     if names:
         label_dict = {n: i for i, n in enumerate(names)}
@@ -124,20 +125,24 @@ def _real_stores(args, device):
     # h5_files/ as the reference's driver reads them (load_from_h5(True)); pt_files/ when only those exist
     use_h5 = os.path.isdir(os.path.join(args.data_dir, "h5_files"))
     splits = dataset.return_splits(from_id=False, csv_path=args.splits_csv, repeat_num=int(args.shot) * n_classes)
-    out = []
-    for sp in splits:
+    stores, shards = {}, {}
+    for key, sp in zip(("train", "val", "test"), splits):
         if sp is None:
             raise SystemExit("the split file %s leaves a split empty" % args.splits_csv)
         sp.load_full_path(True)
         sp.load_from_h5(use_h5)
-        out.append(sp.to_store(device))
-    return out
+        if world > 1 and key != "train":   # eval splits are slide-sharded (LPT on patch count); few-shot bags replicated
+            shards[key] = Shard(sp.bag_sizes(), rank, world)
+            stores[key] = sp.to_store(device, rows=shards[key].ids)
+        else:
+            stores[key] = sp.to_store(device)
+    return stores, shards
 
 
 def run(args):
     from . import loops, synthetic
     from .bag_store import BagDataset, BagLoader, RaggedBagStore
-    from .dist import Shard, init_from_env
+    from .dist import Shard, broadcast_parameters, init_from_env, sync_seed
     from .model import senet
 
     if getattr(args, "summary", False):      # no training, no GPU (main_moc.py:53-130)
@@ -178,8 +183,7 @@ def run(args):
             raise SystemExit("real data needs --data_dir --csv --splits_csv --weights --weights_ext (or use --synthetic)")
         w = torch.load(args.weights, map_location=device).float()
         w_ext = torch.load(args.weights_ext, map_location=device).float()
-        tr, va, te = _real_stores(args, device)
-        stores, shards = {"train": tr, "val": va, "test": te}, {}
+        stores, shards = _real_stores(args, device, rank, world)
 
     loops.set_prompts(w, w_ext)
     loaders = {}
@@ -189,9 +193,12 @@ def run(args):
             ds.shard = shards[key]
         loaders[key] = BagLoader(ds)
 
-    if args.seed is not None:
-        torch.manual_seed(args.seed)
+    # replicas must stay identical: one seed for all ranks (rank 0's --seed, or a random one it draws when the run is
+    # unseeded like the reference's) fixes the gate's initial weights and the per-step half masks everywhere; the
+    # parameters are broadcast as well, so nothing depends on every rank consuming its generator identically up to here
+    sync_seed(args.seed)
     model = senet(512, 4).to(device)
+    broadcast_parameters(model)
     optimizer = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4)
     import time
     torch.cuda.synchronize()

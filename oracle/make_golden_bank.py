@@ -63,7 +63,7 @@ def case(name, names_per_class, n_templates, seed, scale):
 
 
 if __name__ == "__main__":
-    assert ref_loader.available()
+    assert ref_loader.has_checkout()
     torch.set_num_threads(1)
     case("bank_rcc_ext", [3, 2, 4, 1, 1, 1, 1], 22, seed=21, scale=1.0)      # RCC-shaped: 3 classes + 4 background
     case("bank_stress", [3, 3, 3], 22, seed=22, scale=0.05)                   # >= 64 prompts per class

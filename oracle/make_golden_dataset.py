@@ -53,7 +53,7 @@ def load_reference_dataset_module():
 
 
 def main():
-    assert ref_loader.available()
+    assert ref_loader.has_checkout()
     from tests import dataset_fixture as fx
     mod = load_reference_dataset_module()
     out = {}

@@ -58,7 +58,7 @@ def fp16_exact(module):
 
 
 def main():
-    assert ref_loader.available()
+    assert ref_loader.has_checkout()
     torch.set_num_threads(1)
     clam, mil, ada = import_reference_models()
     out_all = {}
@@ -131,7 +131,7 @@ def main_backward():
     each heads_abmil_c*.npz configuration, rebuilt from the same seeds (checked against the stored parameters).
     Stored in heads_abmil_bwd_c*.npz: loss, every bias / small gradient in full, the three large matrices in full
     for C=2 and as every 5th element for C=3."""
-    assert ref_loader.available()
+    assert ref_loader.has_checkout()
     torch.set_num_threads(1)
     clam, _, _ = import_reference_models()
     for c, sizes, seed in ((2, [65, 900], 41), (3, [513], 42)):
@@ -171,7 +171,7 @@ def main_backward_sparse():
     """Training-step gradients of the two heads whose gradient lives on a few rows, through the reference's own modules
     and torch autograd: Conch_CLIP_Ada (both bags of heads_clip_ada_c2/c3: fewer rows than topj, and more) and MIL_fc.
     Parameters and inputs are rebuilt from the seeds of main() and checked against the stored forward goldens."""
-    assert ref_loader.available()
+    assert ref_loader.has_checkout()
     torch.set_num_threads(1)
     _, mil, ada = import_reference_models()
     for c, sizes, topj, seed in ((2, [37, 700], 50, 31), (3, [300], 10, 32)):

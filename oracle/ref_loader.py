@@ -1,8 +1,9 @@
 """Load the UNMODIFIED reference functions from the read-only checkout  --  TEST INFRASTRUCTURE.
 
-Used only in the build container (``/root/reference`` does not exist on the GPU
-box) by ``oracle/make_golden.py`` and by the ``pin`` tests that skip when the
-checkout is absent.  Nothing is copied: the two selector/pooling modules are
+Used by ``oracle/make_golden*.py`` and the comparison tests in the build container
+(read-only checkout at ``/root/reference``), and by ``bench.py``'s CPU legs on the GPU
+box, where the three files :func:`load` needs are found in git-ignored ``oracle/_ref/``
+(``oracle/stage_ref.py``).  The two selector/pooling modules are
 imported by path, and the functions of ``main_moc.py`` are lifted out of its AST
 because the script's module-level body (``main_moc.py:47``, ``:133-293``)
 parses the CLI and loads a CONCH checkpoint that is not available offline.
@@ -14,13 +15,23 @@ import importlib.util
 import os
 import types
 
-REFERENCE_ROOT = os.environ.get("MOC_REFERENCE_ROOT", "/root/reference")
+_CHECKOUT = os.environ.get("MOC_REFERENCE_ROOT", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")   # written by oracle/stage_ref.py
+# the read-only checkout in the build container; on the GPU box the handful of files staged next to this module
+REFERENCE_ROOT = _CHECKOUT if os.path.isfile(os.path.join(_CHECKOUT, "main_moc.py")) else _STAGED
 
 _LIFT = ("senet", "slide_process", "train", "zs_evaluation", "evaluation", "ablation_evaluation")
 
 
 def available() -> bool:
-    return os.path.isfile(os.path.join(REFERENCE_ROOT, "main_moc.py"))
+    """The functions :func:`load` lifts can be loaded (full checkout or the staged subset)."""
+    return all(os.path.isfile(os.path.join(REFERENCE_ROOT, rel)) for rel in
+               ("main_moc.py", "utils/patch_selection_classifier.py", "utils/patch_selection_classifier_index.py"))
+
+
+def has_checkout() -> bool:
+    """The whole read-only checkout is present (golden generation, loader / heads comparisons)."""
+    return REFERENCE_ROOT == _CHECKOUT and os.path.isdir(os.path.join(_CHECKOUT, "datasets"))
 
 
 def _import_by_path(name: str, rel: str) -> types.ModuleType:

@@ -45,6 +45,23 @@ def main():
     assert got_eval == ref_eval, (rank, got_eval, ref_eval)
     assert got_zs == ref_zs, (rank, got_zs, ref_zs)
     import torch.distributed as dist
+    # unseeded multi-GPU run (the reference never seeds): sync_seed + broadcast_parameters keep the replicas identical
+    # through a training epoch whose half masks come from each rank's own CPU generator
+    from moc_b200.dist import broadcast_parameters, sync_seed
+    torch.rand(rank * 5 + 1)                       # let the generators drift apart first
+    sync_seed(None)
+    model2 = M.senet(512, 4).to(dev)
+    broadcast_parameters(model2)
+    opt = torch.optim.Adam(model2.parameters(), lr=1e-3, weight_decay=1e-4)
+    train = M.BagLoader(M.BagDataset(store_for(list(range(6))), repeat_num=6))
+    M.train(model2, train, opt, dev, args)
+    flat = torch.cat([p.detach().flatten() for p in model2.parameters()])
+    parts = [torch.empty_like(flat) for _ in range(world)]
+    dist.all_gather(parts, flat)
+    assert all(torch.equal(parts[0], p) for p in parts), "replicas diverged during unseeded training"
+    got2 = M.evaluation(model2, part, dev, args)
+    ref2 = M.evaluation(model2, full, dev, args)
+    assert got2 == ref2, (rank, got2, ref2)
     dist.barrier()
     if rank == 0:
         print("DIST_OK " + json.dumps({"world": world, "eval": got_eval, "shard_sizes": [len(v) for v in sh.all_ids]}))

@@ -30,6 +30,46 @@ def assert_topj_set(got, ref, key, j, largest=True, rtol=RTOL, atol=ATOL):
     assert len(got) == len(ref)
 
 
+def selection_planes(c, discard=()):
+    """(key plane, largest?) of every top-J selection that enters the union (main_moc.py:341-352) in the key layout
+    [L_0..L_{C-1} | softmax_0.. | |top1-top2| | sum bg | max bg]."""
+    d = set(discard or ())
+    planes = []
+    if "topk" not in d:
+        planes += [(cc, True) for cc in range(c)]
+    if "delta_softmax" not in d:
+        planes += [(c + cc, True) for cc in range(c)]
+    if "delta_diff" not in d:
+        planes.append((2 * c, True))
+    if "bottomk" not in d:
+        planes.append((2 * c + 1, False))
+    return planes
+
+
+def assert_union_set(got, ref, okeys, c, j, discard=(), mask=None, rtol=RTOL, atol=ATOL):
+    """``selected_index`` as a set: identical to the reference's, except that a row may be swapped for another when
+    both sit within tolerance of the rank-j value of an active selection plane (torch.topk's tie order is
+    unspecified).  ``okeys`` are the oracle's key planes [2C+3, N] of the (masked) bag.  Fails otherwise.
+    Returns the rows common to both."""
+    got_s, ref_s = set(int(v) for v in got), set(int(v) for v in ref)
+    if got_s == ref_s:
+        return sorted(got_s)
+    okeys = np.asarray(okeys, dtype=np.float64)
+    if mask is not None:
+        okeys = okeys[:, np.asarray(mask, dtype=bool)]
+    n = okeys.shape[1]
+    jj = min(j, n)
+    thr = []
+    for plane, largest in selection_planes(c, discard):
+        srt = np.sort(okeys[plane])
+        thr.append((plane, srt[-jj] if largest else srt[jj - 1]))
+    for r in sorted(got_s ^ ref_s):
+        near = [abs(okeys[p_, r] - t) <= rtol * abs(t) + atol for p_, t in thr]
+        assert any(near), "row %d is in only one of the two selections and is at no selector's rank-%d threshold" % (r, jj)
+    assert abs(len(got_s) - len(ref_s)) <= len(thr), (len(got_s), len(ref_s))
+    return sorted(got_s & ref_s)
+
+
 def params_from_golden(g, prefix, device):
     from moc_b200.ops import HeadParams
     t = lambda k: torch.from_numpy(np.ascontiguousarray(g[prefix + k])).to(device)

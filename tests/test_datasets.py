@@ -43,7 +43,7 @@ def test_splits_match_the_reference_loader(tmp_path, repeat_num):
 
 def test_live_against_reference_checkout(tmp_path):
     from oracle import ref_loader
-    if not ref_loader.available():
+    if not ref_loader.has_checkout():
         pytest.skip("reference checkout not present (GPU box)")
     from oracle.make_golden_dataset import load_reference_dataset_module
     ref = load_reference_dataset_module()

@@ -6,7 +6,8 @@ import numpy as np
 import pytest
 import torch
 
-from tests.helpers import assert_topj_set, close
+from oracle import moc_oracle as O
+from tests.helpers import assert_topj_set, assert_union_set, close
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -33,22 +34,26 @@ def test_slide_process_golden(golden, name):
     model.to(DEV).eval()
     for i in range(int(g["n_slides"])):
         x = T(g["s%d_feat" % i]).float()  # host tensor: slide_process moves it, like the reference
+        ok = O.selection_keys(x, w.cpu(), we.cpu(), c)
+        okeys = np.concatenate([ok["logit"].T, ok["softmax"].T, ok["delta"][None], ok["bg_sum"][None], ok["bg_max"][None]], 0)
         for di, disc in enumerate(g["discards"]):
             disc = [d for d in str(disc).split("|") if d]
             q = "s%d_d%d_" % (i, di)
             r = slide_process(x, w, we, n_classes=c, topj=j, discard_classifiers=disc)
             assert isinstance(r["selected_index"], list)
-            if r["selected_index"] != g[q + "selected_index"].tolist():
-                assert len(set(r["selected_index"]) ^ set(g[q + "selected_index"].tolist())) <= 4
-                continue
+            ref_idx = g[q + "selected_index"].tolist()
+            common = assert_union_set(r["selected_index"], ref_idx, okeys, c, j, disc)
+            same = r["selected_index"] == ref_idx
+            gp = [r["selected_index"].index(v) for v in common]        # all rows unless a rank-J tie was swapped
+            rp = [ref_idx.index(v) for v in common]
             assert torch.equal(r["selected_feat"].cpu(), x[r["selected_index"]])
-            close(r["logits_top_classifier"], g[q + "plane_top"])
-            close(r["logits_delta_softmax_classifier"], g[q + "plane_dsoftmax"])
-            close(r["logits_delta_diff_classifier"], g[q + "plane_ddiff"])
-            close(r["logits_bottomk_irrel_classifier"], g[q + "plane_bottomk"])
+            close(r["logits_top_classifier"][gp], g[q + "plane_top"][rp])
+            close(r["logits_delta_softmax_classifier"][gp], g[q + "plane_dsoftmax"][rp])
+            close(r["logits_delta_diff_classifier"][gp], g[q + "plane_ddiff"][rp])
+            close(r["logits_bottomk_irrel_classifier"][gp], g[q + "plane_bottomk"][rp])
             with torch.no_grad():
                 gate = model(r["selected_feat"])
-            close(gate, g[q + "gate"], rtol=1e-4, atol=1e-6)
+            close(gate[gp], g[q + "gate"][rp], rtol=1e-4, atol=1e-6)
             # the reference's own eval-time combination written with torch ops on our tensors
             f = gate[:, 0:1] * r["logits_top_classifier"]
             if "delta_softmax" not in disc:
@@ -56,7 +61,10 @@ def test_slide_process_golden(golden, name):
             if "delta_diff" not in disc:
                 f = f + gate[:, 2:3] * r["logits_delta_diff_classifier"]
             f = f + gate[:, 3:4] * r["logits_bottomk_irrel_classifier"]
-            close(topj_pooling(f, [k])[1][k], g[q + "bag_logits"])
+            pooled = topj_pooling(f, [k])[1][k]
+            close(pooled, f.double().topk(min(k, f.size(0)), dim=0).values.mean(dim=0, keepdim=True))
+            if same:   # a swapped rank-J tie changes which rows are pooled: the golden holds for the identical selection
+                close(pooled, g[q + "bag_logits"])
 
 
 @pytest.mark.parametrize("name", ["slide_c2", "slide_c3", "slide_c30"])

@@ -10,6 +10,7 @@ import torch
 
 from moc_b200 import _lib, ops, synthetic
 from oracle import moc_oracle as O
+from tests.helpers import assert_union_set
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -117,7 +118,7 @@ def test_full_size_permutation_and_batch_independence():
     counts = sel.sel_count.cpu().tolist()
     # slide 1 alone
     x1 = feat[offs[1]:offs[2]].contiguous()
-    _, s1, o1 = _pipeline(x1, [0, 20000], w, we, c, prm)
+    k1, s1, o1 = _pipeline(x1, [0, 20000], w, we, c, prm)
     lo = sel.sel_base_h[1]
     assert int(s1.sel_count[0]) == counts[1]
     assert torch.equal(s1.sel_rows[:counts[1]], sel.sel_rows[lo:lo + counts[1]] - offs[1])
@@ -128,5 +129,5 @@ def test_full_size_permutation_and_batch_independence():
     _, sp, op = _pipeline(xp, [0, 20000], w, we, c, prm)
     got = set(perm[sp.sel_rows[:int(sp.sel_count[0])].long()].cpu().tolist())
     want = set(s1.sel_rows[:counts[1]].cpu().tolist())
-    assert len(got ^ want) <= 2, "permutation changed the selected set beyond threshold ties"
+    assert_union_set(got, want, k1.cpu().numpy(), c, J)   # only rank-J ties may move with the permutation
     assert (op.bag_logits - o1.bag_logits).abs().max().item() < 1e-6

@@ -127,6 +127,31 @@ def test_malformed_files_fail_loudly(tmp_path):
             d.read_into(buf.ctypes.data, buf.nbytes)
 
 
+def test_cyclic_chunk_tree_fails_instead_of_spinning(tmp_path):
+    """A corrupt file whose chunk B-tree points back at an inner node must be rejected, not walked forever."""
+    import struct
+    feats, coords = _bag(600, seed=11)
+    p = str(tmp_path / "cyc.h5")
+    write_h5(p, {"features": feats, "coords": coords}, chunk_fanout=8, batch=256)
+    blob = bytearray(open(p, "rb").read())
+    key_size = 8 + 8 * 3
+    patched = 0
+    pos = blob.find(b"TREE")
+    while pos >= 0:
+        ntype, level, used = struct.unpack_from("<BBH", blob, pos + 4)
+        if ntype == 1 and level >= 1 and used >= 2:      # inner chunk node: make its last child the node itself
+            child_at = pos + 8 + 16 + (used - 1) * (key_size + 8) + key_size
+            struct.pack_into("<Q", blob, child_at, pos)
+            patched += 1
+        pos = blob.find(b"TREE", pos + 4)
+    assert patched > 0
+    with open(p, "wb") as fh:
+        fh.write(bytes(blob))
+    with pytest.raises(_lib.MocError, match="cyclic"):
+        with H5File(p) as f:
+            f["features"][:]
+
+
 def test_store_from_h5_dir(tmp_path):
     """The loader surface: h5_files/<slide_id>.h5 -> ragged store (host tensors here; pinned + async on CUDA)."""
     os.makedirs(tmp_path / "h5_files")

@@ -134,6 +134,21 @@ flat = torch.full((33092,), float(rank + 1))
 allreduce_sum(flat)
 assert float(flat[0]) == sum(range(1, world + 1))
 assert barrier_max_ms(float(rank), "cpu") == float(world - 1)
+# unseeded replicas (main_moc.py never seeds): ranks whose generators have drifted apart must come out of
+# sync_seed() + broadcast_parameters() with identical gate weights and identical half masks
+from moc_b200.dist import broadcast_parameters, sync_seed
+from moc_b200.model import senet
+torch.rand(rank * 3 + 1)
+m_before = senet(512, 4)
+seed = sync_seed(None)
+m = senet(512, 4)
+broadcast_parameters(m_before)
+mask = (torch.rand(1000) > 0.5).float()
+flat = torch.cat([q.detach().flatten() for q in m.parameters()] + [q.detach().flatten() for q in m_before.parameters()] + [mask])
+parts = [torch.empty_like(flat) for _ in range(world)]
+dist.all_gather(parts, flat)
+assert all(torch.equal(parts[0], q) for q in parts), "replicas differ after sync_seed/broadcast_parameters"
+assert sync_seed(1234) == 1234
 dist.barrier()
 dist.destroy_process_group()
 print("rank %%d ok" %% rank)
@@ -223,7 +238,10 @@ def test_bench_reference_arm_contract():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "slides_per_sec" and d["unit"] == "slides/s"
     assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["value"] > 0 and d["gpu_launches"] == 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    from oracle import ref_loader
+    assert d["cpu_baseline"]["kind"] == ("reference" if ref_loader.available() else "port")
+    assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["config"]["n_classes"] == 2 and d["config"]["topj"] == 400 and "workload" in d["config"]
     assert d["e2e"] == {"value": d["value"], "unit": "slides/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     # a non-zero rank under torchrun exits 0 without work and without output
     r2 = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
