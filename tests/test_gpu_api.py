@@ -230,3 +230,37 @@ def test_score_cta_calibration_changes_nothing_but_speed(monkeypatch):
     monkeypatch.setenv("MOC_SCORE_AUTOTUNE", "0")
     monkeypatch.setattr(MocEngine, "_TUNED_CTAS", {})
     assert torch.equal(eng.keys_for(store), ref) and MocEngine._TUNED_CTAS == {}
+
+
+def test_ext_class_columns_differ_from_w(golden):
+    """zs_evaluation(pooling_func=bottomk_irrel_classifier_pooling) pools (feats @ W_ext)[:, :C] (main_moc.py:428-432):
+    with a W_ext whose class columns are not W the engine must score those columns, not reuse the W planes.  Golden
+    from the reference's own loops (oracle/make_golden_extfg.py)."""
+    import moc_b200 as M
+    from moc_b200 import loops
+    from moc_b200.engine import MocEngine
+    g = golden("zs_extfg")
+    c, j, k = int(g["C"]), int(g["J"]), int(g["K"])
+    w, we = T(g["W"]).to(DEV), T(g["W_ext"]).to(DEV)
+    loops.set_prompts(w, we)
+    args = _args(c, j, k)
+    store = M.RaggedBagStore.from_bags([T(g["feat_%d" % i]).float() for i in range(int(g["n_slides"]))],
+                                       g["labels"].tolist(), DEV)
+    ld = M.BagLoader(M.BagDataset(store))
+
+    def same(d, key, rtol=2e-5):
+        ref = g[key]
+        np.testing.assert_allclose(d["loss"], ref[0], rtol=rtol, err_msg=key)
+        assert d["acc"] == ref[1] and d["auc"] == ref[2], key
+
+    same(M.zs_evaluation(ld, DEV, args), "zs_topj")
+    same(M.zs_evaluation(ld, DEV, args, pooling_func=M.delta_softmax_classifier_pooling), "zs_dsoftmax")
+    same(M.zs_evaluation(ld, DEV, args, pooling_func=M.delta_diff_classifier_pooling), "zs_ddiff")
+    same(M.zs_evaluation(ld, DEV, args, pooling_func=M.bottomk_irrel_classifier_pooling), "zs_bottomk")
+    eng = MocEngine(w, we, j, k)
+    close(eng.zero_shot_logits(store, "bottomk_irrel"), g["bottomk_logits"])
+    assert not np.allclose(eng.zero_shot_logits(store, "topj").cpu().numpy(), g["bottomk_logits"], atol=1e-4)
+    model = M.senet(512, 4)
+    model.load_state_dict({kk[3:].replace("model_0_", "model.0.").replace("model_2_", "model.2."): T(v)
+                           for kk, v in g.items() if kk.startswith("sd_")})
+    same(M.evaluation(model.to(DEV), ld, DEV, args), "eval")

@@ -230,3 +230,20 @@ def test_heads_mil_fc(golden):
         top, y_prob, y_hat, y_probs = H.mil_fc_forward(sd, T(g["feat_%d" % i]).float())
         assert torch.equal(top, T(g["top_instance_%d" % i])) and torch.equal(y_prob, T(g["y_prob_%d" % i]))
         assert torch.equal(y_hat, T(g["y_hat_%d" % i])) and torch.equal(y_probs, T(g["y_probs_%d" % i]))
+
+
+def test_ext_class_columns_differ_from_w(golden):
+    """Prompt files whose W_ext[:, :C] is not W (tests/golden/zs_extfg.npz, the reference's own zs_evaluation /
+    evaluation): bottomk_irrel pooling reads (feats @ W_ext)[:, :C], everything else scores classes against W."""
+    g = golden("zs_extfg")
+    c, j, k = int(g["C"]), int(g["J"]), int(g["K"])
+    w, we = T(g["W"]), T(g["W_ext"])
+    assert not torch.equal(we[:, :c], w)
+    data = O.BagList([feat_of(g, "feat_%d" % i) for i in range(int(g["n_slides"]))], g["labels"].tolist())
+    ev = lambda d: np.asarray([d["loss"], d["acc"], d["auc"]])
+    for ours, key in (("topj", "zs_topj"), ("delta_softmax", "zs_dsoftmax"), ("delta_diff", "zs_ddiff"),
+                      ("bottomk_irrel", "zs_bottomk")):
+        np.testing.assert_allclose(ev(O.zs_evaluation(data, w, we, c, k, ours)), g[key], rtol=1e-6)
+    _, lg = O.zs_evaluation(data, w, we, c, k, "bottomk_irrel", return_logits=True)
+    np.testing.assert_array_equal(lg.numpy(), g["bottomk_logits"])
+    np.testing.assert_allclose(ev(O.evaluation(params_of(g, "sd_"), data, w, we, c, j, k)), g["eval"], rtol=1e-6)
