@@ -325,6 +325,11 @@ int moc_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
                   int64_t step, float lr, float beta1, float beta2, float eps, float weight_decay,
                   void* stream);
 
+/* dst[i] += src[i]: sums the gate gradients of the slides of one data-parallel micro-batch before the single
+ * all-reduce + Adam step (north_star's "small all-reduce of meta-optimizer gradients"; the reference's loop,
+ * main_moc.py:406-410, steps once per slide and has no such mode). */
+int moc_accumulate(float* dst, const float* src, int64_t n, void* stream);
+
 /* ---- a1: on-disk bags -------------------------------------------------------
  * Native reader for CLAM-style HDF5 bag files, replacing h5py.File(path)['features'][:] /
  * ['coords'][:] (datasets/dataset_generic.py:424-430) for the subset of the format those

@@ -81,6 +81,7 @@ SIGNATURES = {
     "moc_h5_dataset_info": (i32, [p, C.c_char_p, C.POINTER(i32), C.POINTER(i64), C.POINTER(i32), C.POINTER(i32)]),
     "moc_h5_read": (i32, [p, C.c_char_p, p, sz]),
     "moc_adam_step": (i32, [p, p, p, p, i64, i64, f32, f32, f32, f32, f32, p]),
+    "moc_accumulate": (i32, [p, p, i64, p]),
 }
 
 _lock = threading.Lock()

@@ -621,9 +621,23 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     p[i] = pi - step_size * __fdiv_rn(mi, denom);
 }
 
+// dst += src (gradient accumulation over the slides of a data-parallel micro-batch)
+__global__ void accumulate_kernel(float* __restrict__ dst, const float* __restrict__ src, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = __fadd_rn(dst[i], src[i]);
+}
+
 }  // namespace moc
 
 using namespace moc;
+
+extern "C" int moc_accumulate(float* dst, const float* src, int64_t n, void* stream) {
+    MOC_CHECK_ARG(dst && src && n >= 0, "moc_accumulate: bad arguments");
+    if (n == 0) return MOC_OK;
+    accumulate_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dst, src, n);
+    MOC_LAUNCH_CHECK("accumulate_kernel");
+    return MOC_OK;
+}
 
 extern "C" int moc_head_forward(const float* feat, const float* keys, int64_t key_stride, int n_classes,
                                 const int64_t* sel_base, const int32_t* sel_rows, const int32_t* sel_count,

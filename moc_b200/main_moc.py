@@ -48,6 +48,9 @@ def get_args(argv=None):
     p.add_argument("--epochs", type=int, default=25, help="the reference hard-codes 25 (main_moc.py:611)")
     p.add_argument("--seed", type=int, default=None, help="torch.manual_seed before model init (reference: unseeded)")
     p.add_argument("--cache_scores", action="store_true", help="score every bag once per run (bit-identical results)")
+    p.add_argument("--dp_microbatch", type=int, default=None,
+                   help="data-parallel training: sum the gate gradients of this many consecutive slides (spread over the "
+                        "ranks, one NCCL all-reduce) per Adam step; changes the trajectory, off by default")
     p.add_argument("--data_dir", type=str, default=None)
     p.add_argument("--csv", type=str, default=None)
     p.add_argument("--splits_csv", type=str, default=None)

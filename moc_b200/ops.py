@@ -302,6 +302,14 @@ def adam_step(params: torch.Tensor, grads: torch.Tensor, exp_avg: torch.Tensor, 
                                     params.numel(), int(step), lr, beta1, beta2, eps, weight_decay, _stream()))
 
 
+def accumulate_(dst: torch.Tensor, src: torch.Tensor) -> torch.Tensor:
+    """dst += src for two contiguous fp32 CUDA buffers of the same length (micro-batch gradient sum)."""
+    assert dst.is_cuda and src.is_cuda and dst.is_contiguous() and src.is_contiguous() and dst.numel() == src.numel()
+    _count(1)
+    check(_lib.load().moc_accumulate(dst.data_ptr(), src.data_ptr(), dst.numel(), _stream()))
+    return dst
+
+
 def gather_selected(feat: torch.Tensor, keys: torch.Tensor, n_classes: int, sel_rows: torch.Tensor, n_sel: int,
                     want_feat: bool = True, want_planes: bool = True):
     """Dense selected_feat [S,512] and the four [S,C] score planes of main_moc.py:355-366."""

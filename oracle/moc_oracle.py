@@ -379,19 +379,30 @@ class BagList:
 
 
 def train_epoch(p: SenetParams, st: AdamState, data: BagList, w, w_ext, n_classes, topj, topk,
-                discard_classifiers=(), masks: Optional[Iterable[torch.Tensor]] = None) -> List[float]:
-    """One pass of main_moc.py:378-410: one Adam step per (virtual) slide, half-masked."""
+                discard_classifiers=(), masks: Optional[Iterable[torch.Tensor]] = None,
+                dp_microbatch: Optional[int] = None) -> List[float]:
+    """One pass of main_moc.py:378-410: one Adam step per (virtual) slide, half-masked.
+
+    ``dp_microbatch=G`` is NOT the reference's semantics: it is the checker for the data-parallel training mode
+     - the gradients of G consecutive slides, all taken at the same parameters, are summed in
+    slide order and applied with one Adam step (a last, shorter micro-batch when G does not divide the epoch)."""
     losses = []
     masks = iter(masks) if masks is not None else None
     act = active_classifiers(discard_classifiers, "train")
+    g = int(dp_microbatch) if dp_microbatch else 1
+    acc, pending = None, 0
     for i in range(len(data)):
         feat, lbl = data[i]
         mk = next(masks) if masks is not None else None
         slide = slide_process(feat, w, w_ext, n_classes, topj, random_mask=True,
                               discard_classifiers=discard_classifiers, mask=mk)
         loss, _, grads = head_forward_backward(p, slide, lbl, topk, act)
-        adam_step(p, grads, st)
         losses.append(float(loss))
+        acc = grads if acc is None else [a + b for a, b in zip(acc, grads)]
+        pending += 1
+        if pending == g or i == len(data) - 1:
+            adam_step(p, acc, st)
+            acc, pending = None, 0
     return losses
 
 

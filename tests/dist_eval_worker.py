@@ -13,6 +13,14 @@ from moc_b200 import loops, synthetic  # noqa: E402
 from moc_b200.dist import Shard, init_from_env  # noqa: E402
 
 
+def _solo_dp(M, model, loader, opt, dev, args, masks):
+    """The same micro-batches accumulated by this process alone (a one-rank group for the collective)."""
+    import torch.distributed as dist
+    me = dist.get_rank()
+    groups = [dist.new_group(ranks=[r]) for r in range(dist.get_world_size())]   # every rank must create every group
+    return M.train(model, loader, opt, dev, args, masks=masks, dp_microbatch=4, group=groups[me])
+
+
 def main():
     rank, local, world = init_from_env("nccl")
     dev = torch.device("cuda", local)
@@ -62,6 +70,23 @@ def main():
     got2 = M.evaluation(model2, part, dev, args)
     ref2 = M.evaluation(model2, full, dev, args)
     assert got2 == ref2, (rank, got2, ref2)
+    # data-parallel training mode: micro-batches of 4 slides spread over the ranks, one all-reduce each; must equal
+    # the single-process accumulation of the same slides and leave all ranks with identical parameters
+    import copy
+    masks = [torch.rand(train.dataset.store.n_rows(k % 6), generator=torch.Generator().manual_seed(100 + k)) > 0.5
+             for k in range(6)]
+    m_dp, m_one = copy.deepcopy(model2), copy.deepcopy(model2)
+    o_dp = torch.optim.Adam(m_dp.parameters(), lr=1e-3, weight_decay=1e-4)
+    o_one = torch.optim.Adam(m_one.parameters(), lr=1e-3, weight_decay=1e-4)
+    l_dp = M.train(m_dp, train, o_dp, dev, args, masks=masks, dp_microbatch=4)
+    l_one = _solo_dp(M, m_one, train, o_one, dev, args, masks)
+    flat = torch.cat([p.detach().flatten() for p in m_dp.parameters()])
+    parts = [torch.empty_like(flat) for _ in range(world)]
+    dist.all_gather(parts, flat)
+    assert all(torch.equal(parts[0], p) for p in parts), "dp mode: replicas differ"
+    one = torch.cat([p.detach().flatten() for p in m_one.parameters()])
+    assert float((flat - one).abs().max()) < 1e-6, float((flat - one).abs().max())
+    assert float((l_dp - l_one).abs().max()) < 1e-6
     dist.barrier()
     if rank == 0:
         print("DIST_OK " + json.dumps({"world": world, "eval": got_eval, "shard_sizes": [len(v) for v in sh.all_ids]}))

@@ -264,3 +264,40 @@ def test_ext_class_columns_differ_from_w(golden):
     model.load_state_dict({kk[3:].replace("model_0_", "model.0.").replace("model_2_", "model.2."): T(v)
                            for kk, v in g.items() if kk.startswith("sd_")})
     same(M.evaluation(model.to(DEV), ld, DEV, args), "eval")
+
+
+@pytest.mark.parametrize("g_size", [2, 4, 6])
+def test_dp_microbatch_training_matches_oracle_variant(golden, g_size):
+    """train(..., dp_microbatch=G): gradients of G consecutive slides at common parameters, summed, one Adam step -
+    against oracle.train_epoch(dp_microbatch=G) on the same bags and masks (single rank: pure accumulation; the
+    multi-rank split of the same sum is covered by tests/dist_eval_worker.py)."""
+    import moc_b200 as M
+    from moc_b200 import loops
+    g = golden("loop_c2")
+    c, j, k = int(g["C"]), int(g["J"]), int(g["K"])
+    w, we = T(g["W"]), T(g["W_ext"])
+    bags = [T(g["train_feat_%d" % i]).float() for i in range(int(g["n_train"]))]
+    labels = g["train_labels"].tolist()
+    rep = int(g["repeat_num"])
+    masks = [T(g["mask_%d" % i]) for i in range(rep)]
+    oprm = O.SenetParams(*[T(g["sd0_" + n]).clone() for n in ("model_0_weight", "model_0_bias", "model_2_weight", "model_2_bias")])
+    st = O.AdamState()
+    ref_losses = O.train_epoch(oprm, st, O.BagList(bags, labels, repeat_num=rep), w, we, c, j, k, (), masks,
+                               dp_microbatch=g_size)
+    assert st.step == -(-rep // g_size)
+
+    loops.set_prompts(w.to(DEV), we.to(DEV))
+    model = M.senet(512, 4)
+    model.load_state_dict({kk[4:].replace("model_0_", "model.0.").replace("model_2_", "model.2."): T(v)
+                           for kk, v in g.items() if kk.startswith("sd0_")})
+    model.to(DEV)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4)
+    tr = M.BagLoader(M.BagDataset(M.RaggedBagStore.from_bags(bags, labels, DEV), repeat_num=rep))
+    losses = M.train(model, tr, opt, DEV, _args(c, j, k), masks=masks, dp_microbatch=g_size)
+    np.testing.assert_allclose(losses.cpu().numpy(), np.asarray(ref_losses), rtol=5e-5)
+    for got, ref in zip(model.parameters_in_order(), oprm.tensors()):
+        assert float((got.detach().cpu() - ref).abs().max()) < 2e-5
+    # and it is a different trajectory from the reference's one-step-per-slide loop
+    one = O.SenetParams(*[T(g["sd0_" + n]).clone() for n in ("model_0_weight", "model_0_bias", "model_2_weight", "model_2_bias")])
+    O.train_epoch(one, O.AdamState(), O.BagList(bags, labels, repeat_num=rep), w, we, c, j, k, (), masks)
+    assert float((one.w2 - oprm.w2).abs().max()) > 1e-5

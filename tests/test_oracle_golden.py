@@ -247,3 +247,32 @@ def test_ext_class_columns_differ_from_w(golden):
     _, lg = O.zs_evaluation(data, w, we, c, k, "bottomk_irrel", return_logits=True)
     np.testing.assert_array_equal(lg.numpy(), g["bottomk_logits"])
     np.testing.assert_allclose(ev(O.evaluation(params_of(g, "sd_"), data, w, we, c, j, k)), g["eval"], rtol=1e-6)
+
+
+def test_dp_microbatch_variant_of_the_oracle(golden):
+    """The checker of the data-parallel training mode: G=1 is the reference's loop; G >= epoch length is one Adam step
+    on the sum of all per-slide gradients taken at the initial parameters."""
+    g = golden("loop_c2")
+    c, j, k = int(g["C"]), int(g["J"]), int(g["K"])
+    w, we = T(g["W"]), T(g["W_ext"])
+    rep = int(g["repeat_num"])
+    data = O.BagList([feat_of(g, "train_feat_%d" % i) for i in range(int(g["n_train"]))], g["train_labels"].tolist(),
+                     repeat_num=rep)
+    masks = [T(g["mask_%d" % i]) for i in range(rep)]
+    a, b = params_of(g, "sd0_"), params_of(g, "sd0_")
+    la = O.train_epoch(a, O.AdamState(), data, w, we, c, j, k, (), masks)
+    lb = O.train_epoch(b, O.AdamState(), data, w, we, c, j, k, (), masks, dp_microbatch=1)
+    assert la == lb and all(torch.equal(x, y) for x, y in zip(a.tensors(), b.tensors()))
+    p0, whole = params_of(g, "sd0_"), params_of(g, "sd0_")
+    st = O.AdamState()
+    lw = O.train_epoch(whole, st, data, w, we, c, j, k, (), masks, dp_microbatch=100)
+    assert st.step == 1
+    total, losses = None, []
+    for i in range(rep):
+        feat, lbl = data[i]
+        slide = O.slide_process(feat, w, we, c, j, mask=masks[i])
+        loss, _, grads = O.head_forward_backward(p0, slide, lbl, k)
+        losses.append(float(loss))
+        total = grads if total is None else [x + y for x, y in zip(total, grads)]
+    O.adam_step(p0, total, O.AdamState())
+    assert lw == losses and all(torch.equal(x, y) for x, y in zip(p0.tensors(), whole.tensors()))
