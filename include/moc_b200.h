@@ -55,6 +55,9 @@ extern "C" {
 #define MOC_CLS_DELTA_DIFF 4u
 #define MOC_CLS_BOTTOMK 8u
 #define MOC_CLS_ALL 15u
+/* OR-ed into active_mask (moc_head_forward) / flags (moc_senet_forward): run the gate MLP on the 3xTF32 kernel, which
+ * has no |x| limit, whatever the class count.  Callers set it to redo a pass whose domain flag came back non-zero. */
+#define MOC_HEAD_WIDE_DOMAIN 0x100u
 
 const char* moc_last_error(void);
 int moc_version(void);
@@ -173,6 +176,12 @@ int moc_col_prefix_mean(const float* vals, int64_t ld, int n_cols, int j, float*
  * pool_pos [n_slides,C,topk] (positions inside the slide's selected list,
  * -1 padded), all indexed through sel_base/sel_count. gate may be null. */
 size_t moc_head_forward_workspace_bytes(void);
+/* Byte offset, inside that workspace, of an int32 "domain flag": the FP16x3 gate kernel ORs 1 into it when a gate
+ * pre-activation came out non-finite (a feature with |x| >= 4094, or a non-finite one).  It is never cleared by the
+ * library: the caller zeroes it before a pass and, at a point where it synchronises anyway, reads it and repeats the
+ * pass with MOC_HEAD_WIDE_DOMAIN when it is set.  The reference (fp32 matmul, main_moc.py:303) is finite for any
+ * finite feature, so the repeat restores parity for inputs outside the fast kernel's range. */
+size_t moc_head_domain_flag_offset(void);
 int moc_head_forward(const float* feat, const float* keys, int64_t key_stride, int n_classes,
                      const int64_t* sel_base, const int32_t* sel_rows, const int32_t* sel_count,
                      int n_slides, int64_t sel_capacity_total,
@@ -206,7 +215,8 @@ int moc_gather_selected(const float* feat, const float* keys, int64_t key_stride
  * gate = sigmoid(W2 relu(W1 x + b1) + b2) and, for autograd, the parameter
  * gradient given d(loss)/d(gate) [n_rows,4] (rows whose gradient is all-zero are skipped). */
 int moc_senet_forward(const float* x, int64_t n_rows, const float* w1, const float* b1, const float* w2,
-                      const float* b2, float* gate, void* workspace, size_t workspace_bytes, void* stream);
+                      const float* b2, float* gate, unsigned flags, void* workspace, size_t workspace_bytes,
+                      void* stream);
 size_t moc_senet_backward_workspace_bytes(int64_t n_rows);
 int moc_senet_backward(const float* x, int64_t n_rows, const float* dgate, const float* w1, const float* b1,
                        const float* w2, const float* b2, float* grads, void* workspace, size_t workspace_bytes,

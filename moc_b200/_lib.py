@@ -13,6 +13,7 @@ LIB_PATH = os.environ.get("MOC_B200_LIB", os.path.join(PKG, "libmoc_b200.so"))  
 
 OK, E_ARG, E_SHAPE, E_WORKSPACE, E_CUDA = 0, -1, -2, -3, -4
 CLS_TOPK, CLS_DELTA_SOFTMAX, CLS_DELTA_DIFF, CLS_BOTTOMK, CLS_ALL = 1, 2, 4, 8, 15
+HEAD_WIDE_DOMAIN = 0x100   # MOC_HEAD_WIDE_DOMAIN: force the range-free 3xTF32 gate kernel
 NUM_PARAMS = 64 * 512 + 64 + 4 * 64 + 4
 MAX_COLS = 64
 
@@ -50,6 +51,7 @@ SIGNATURES = {
     "moc_take_rows": (i32, [p, i64, p, i64, i32, p, p]),
     "moc_col_prefix_mean": (i32, [p, i64, i32, i32, p, p]),
     "moc_head_forward_workspace_bytes": (sz, []),
+    "moc_head_domain_flag_offset": (sz, []),
     "moc_head_forward": (i32, [p, p, i64, i32, p, p, p, i32, i64, p, p, p, p, u32, i32, p, p, p, p, p, sz, p]),
     "moc_ablation_forward": (i32, [p, i64, i32, p, p, p, i32, i64, i32, i32, p, p, p]),
     "moc_pool_topk": (i32, [p, i64, p, i32, i32, i32, i32, i32, i32, i32, i32, p, p]),
@@ -64,7 +66,7 @@ SIGNATURES = {
     "moc_head_backward_workspace_bytes": (sz, [i32, i32, i32]),
     "moc_head_backward": (i32, [p, p, i64, i32, p, p, p, i32, p, p, p, p, u32, i32, p, p, p, p, sz, p]),
     "moc_gather_selected": (i32, [p, p, i64, i32, p, i64, p, p, p, p, p, p]),
-    "moc_senet_forward": (i32, [p, i64, p, p, p, p, p, p, sz, p]),
+    "moc_senet_forward": (i32, [p, i64, p, p, p, p, p, u32, p, sz, p]),
     "moc_senet_backward_workspace_bytes": (sz, [i64]),
     "moc_senet_backward": (i32, [p, i64, p, p, p, p, p, p, p, sz, p]),
     "moc_linear_wgrad_workspace_bytes": (sz, [i64, i32, i32]),

@@ -25,7 +25,8 @@ int launch_head_rows_tc(const float* feat, const float* keys, int64_t key_stride
 size_t head_f16_workspace_bytes();
 int launch_head_rows_f16(const float* feat, const float* keys, int64_t key_stride, int C, const int32_t* sel_rows,
                          int64_t n_slots, const float* w1, const float* b1, const float* w2, const float* b2,
-                         unsigned active_mask, float* gate, float* final_scores, void* workspace, cudaStream_t st);
+                         unsigned active_mask, float* gate, float* final_scores, void* workspace, int* domain_flag,
+                         cudaStream_t st);
 
 // MOC_HEAD_IMPL = auto (default: FP16x3 up to 8 classes, 3xTF32 beyond - see head_f16.cu) | f16 | tf32 | simt.  The
 // 3xTF32 and CUDA-core kernels also serve as in-tree cross-checks of the FP16x3 path and for features outside its
@@ -39,18 +40,23 @@ static int head_impl() {
     return cached;
 }
 static bool use_simt_head() { return head_impl() == 2; }
-static size_t head_ws_bytes() {
+static size_t head_img_bytes() {
     const size_t a = head_tc_workspace_bytes(), b = head_f16_workspace_bytes();
-    return a > b ? a : b;
+    return ((a > b ? a : b) + 15) & ~(size_t)15;
 }
+// workspace = [ W1 image of whichever kernel runs | int32 domain flag (+ padding) ]
+static size_t head_ws_bytes() { return head_img_bytes() + 16; }
 static int launch_head_rows_mma(const float* feat, const float* keys, int64_t key_stride, int C, const int32_t* sel_rows,
                                 int64_t n_slots, const float* w1, const float* b1, const float* w2, const float* b2,
                                 unsigned active_mask, float* gate, float* final_scores, void* workspace, cudaStream_t st) {
     const int impl = head_impl();
-    return (impl == 1 || (impl == 3 && C > 8)) ? launch_head_rows_tc(feat, keys, key_stride, C, sel_rows, n_slots, w1, b1, w2, b2, active_mask,
-                                                  gate, final_scores, workspace, st)
-                            : launch_head_rows_f16(feat, keys, key_stride, C, sel_rows, n_slots, w1, b1, w2, b2, active_mask,
-                                                   gate, final_scores, workspace, st);
+    const bool wide = (active_mask & MOC_HEAD_WIDE_DOMAIN) != 0;   // the caller asks for the range-free kernel
+    int* flag = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(workspace) + head_img_bytes());
+    return (impl == 1 || wide || (impl == 3 && C > 8))
+               ? launch_head_rows_tc(feat, keys, key_stride, C, sel_rows, n_slots, w1, b1, w2, b2, active_mask, gate,
+                                     final_scores, workspace, st)
+               : launch_head_rows_f16(feat, keys, key_stride, C, sel_rows, n_slots, w1, b1, w2, b2, active_mask, gate,
+                                      final_scores, workspace, flag, st);
 }
 
 constexpr int H = MOC_HIDDEN;  // 64
@@ -751,9 +757,11 @@ extern "C" int moc_gather_selected(const float* feat, const float* keys, int64_t
 }
 
 extern "C" size_t moc_head_forward_workspace_bytes(void) { return head_ws_bytes(); }
+extern "C" size_t moc_head_domain_flag_offset(void) { return head_img_bytes(); }
 
 extern "C" int moc_senet_forward(const float* x, int64_t n_rows, const float* w1, const float* b1, const float* w2,
-                                 const float* b2, float* gate, void* workspace, size_t workspace_bytes, void* stream) {
+                                 const float* b2, float* gate, unsigned flags, void* workspace, size_t workspace_bytes,
+                                 void* stream) {
     MOC_CHECK_ARG(x && w1 && b1 && w2 && b2 && gate && n_rows >= 0, "moc_senet_forward: bad arguments");
     MOC_CHECK_SHAPE(n_rows < (1ll << 31), "moc_senet_forward: too many rows");
     if (n_rows == 0) return MOC_OK;
@@ -762,7 +770,7 @@ extern "C" int moc_senet_forward(const float* x, int64_t n_rows, const float* w1
             set_error("moc_senet_forward: workspace %zu B < required %zu B", workspace_bytes, head_ws_bytes());
             return MOC_E_WORKSPACE;
         }
-        return launch_head_rows_mma(x, nullptr, 0, 0, nullptr, n_rows, w1, b1, w2, b2, 0u, gate, nullptr, workspace,
+        return launch_head_rows_mma(x, nullptr, 0, 0, nullptr, n_rows, w1, b1, w2, b2, flags & MOC_HEAD_WIDE_DOMAIN, gate, nullptr, workspace,
                                    (cudaStream_t)stream);
     }
     const size_t smem = (size_t)(H + HR_TM) * HR_LD * sizeof(float);

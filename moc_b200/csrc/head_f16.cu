@@ -175,7 +175,8 @@ __global__ void __launch_bounds__(HF_THREADS, 1)
 head_rows_f16_kernel(const float* __restrict__ feat, const float* __restrict__ keys, int64_t key_stride, int C,
                      const int32_t* __restrict__ sel_rows, int64_t n_slots, const unsigned char* __restrict__ img,
                      const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
-                     unsigned active_mask, float* __restrict__ gate, float* __restrict__ final_scores) {
+                     unsigned active_mask, float* __restrict__ gate, float* __restrict__ final_scores,
+                     int* __restrict__ domain_flag) {
     extern __shared__ unsigned char hf_smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[HF_STAGES], empty_bar[HF_STAGES], tfull_bar[2], tempty_bar[2], b_bar;
     __shared__ uint32_t tmem_base_s;
@@ -367,6 +368,9 @@ head_rows_f16_kernel(const float* __restrict__ feat, const float* __restrict__ k
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);  // accumulator is in registers: MMA may reuse it
             if (++acc == 2) { acc = 0; acc_parity ^= 1u; }
             if (row < 0) continue;
+            // a feature outside the FP16 split's range (|x| >= 4094) or a non-finite one turns the pre-activations
+            // non-finite: raise the caller's flag so the pass can be redone on the range-free 3xTF32 kernel
+            if (domain_flag != nullptr && !(fabsf(z[0] + z[1] + z[2] + z[3]) <= 3.0e38f)) atomicOr(domain_flag, 1);
             float g[HF_G];
 #pragma unroll
             for (int m = 0; m < HF_G; ++m) g[m] = sigmoidf_exact(z[m] + b2s[m]);
@@ -409,7 +413,8 @@ size_t head_f16_workspace_bytes() { return (size_t)HF_BIMG_BYTES + sizeof(HeadF1
 
 int launch_head_rows_f16(const float* feat, const float* keys, int64_t key_stride, int C, const int32_t* sel_rows,
                          int64_t n_slots, const float* w1, const float* b1, const float* w2, const float* b2,
-                         unsigned active_mask, float* gate, float* final_scores, void* workspace, cudaStream_t st) {
+                         unsigned active_mask, float* gate, float* final_scores, void* workspace, int* domain_flag,
+                         cudaStream_t st) {
     unsigned char* img = reinterpret_cast<unsigned char*>(workspace);
     head_f16_prep_kernel<<<1, 1024, 0, st>>>(w1, img);
     MOC_LAUNCH_CHECK("head_f16_prep_kernel");
@@ -417,7 +422,7 @@ int launch_head_rows_f16(const float* feat, const float* keys, int64_t key_strid
     const int64_t n_tiles = (n_slots + HF_M - 1) / HF_M;
     const int grid = (int)(n_tiles < sm_count() ? n_tiles : sm_count());
     head_rows_f16_kernel<<<grid, HF_THREADS, HF_SMEM, st>>>(feat, keys, key_stride, C, sel_rows, n_slots, img, b1, w2, b2,
-                                                           active_mask, gate, final_scores);
+                                                           active_mask, gate, final_scores, domain_flag);
     MOC_LAUNCH_CHECK("head_rows_f16_kernel");
     return MOC_OK;
 }

@@ -63,19 +63,45 @@ class MocEngine:
         self._key_cache: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
         self._layout_cache: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
         self.score_events = None  # when a list: (start, stop) CUDA events around every scoring launch
+        # stores whose features left the fast kernels' range (|x| >= 4094 for the FP16x3 gate MLP, >= 65504 for the
+        # tensor-core scoring of wide prompt sets): found by a flag-checked pass, they are served by the range-free
+        # kernels from then on (3xTF32 gate, fp32 CUDA-core scoring) - the reference is finite for any finite feature
+        self._wide_stores: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
 
     # ---- scoring -------------------------------------------------------------------------------
-    def keys_for(self, store: RaggedBagStore, lo: int = 0, hi: Optional[int] = None) -> torch.Tensor:
-        """Key planes [2C+3, rows] for slides [lo, hi) of the store (whole store when cached)."""
+    def keys_for(self, store: RaggedBagStore, lo: int = 0, hi: Optional[int] = None, wide: bool = False) -> torch.Tensor:
+        """Key planes [2C+3, rows] for slides [lo, hi) of the store (whole store when cached).  ``wide``: score on the
+        fp32 CUDA-core kernel (only differs for wide prompt sets, whose tensor-core kernel has an |x| limit)."""
         hi = len(store) if hi is None else hi
+        wide = bool(wide and self.prompts.tc is not None)
         if self.cache_scores:
-            k = self._key_cache.get(store)
-            if k is None or k.size(1) != store.total_rows:
-                k = self._score(store.feat)
-                self._key_cache[store] = k
-            return k[:, store.offsets_h[lo]:store.offsets_h[hi]]
+            hit = self._key_cache.get(store)
+            if hit is None or hit[0].size(1) != store.total_rows or (wide and not hit[1]):
+                k = ops.score_keys(store.feat, self.prompts, self.normalize, wide=True) if wide else self._score(store.feat)
+                hit = self._key_cache[store] = (k, wide)
+            return hit[0][:, store.offsets_h[lo]:store.offsets_h[hi]]
         r0, r1 = store.offsets_h[lo], store.offsets_h[hi]
+        if wide:
+            return ops.score_keys(store.feat[r0:r1], self.prompts, self.normalize, wide=True)
         return self._score(store.feat[r0:r1])
+
+    # ---- out-of-range features ---------------------------------------------------------------------
+    def _arm_flags(self, device):
+        ws = ops.head_workspace(device)
+        ws.clear_flag()
+        if self.prompts.tc_flag is not None:
+            self.prompts.tc_flag.zero_()
+        return ws
+
+    def _flags_raised(self, ws) -> bool:
+        """One or two 4-byte reads (synchronises): did a fast kernel meet a feature outside its range?"""
+        bad = ws.overflowed()
+        if self.prompts.tc_flag is not None:
+            bad = bool(int(self.prompts.tc_flag.item()) != 0) or bad
+        return bad
+
+    def is_wide(self, store) -> bool:
+        return bool(self._wide_stores.get(store, False))
 
     # The streaming kernel's best CTA count is a property of the individual GPU (132 on most B200s, 136 on some, DESIGN
     # section 4).  The first large scoring call of a process times a few candidates on the caller's own data - the
@@ -156,62 +182,103 @@ class MocEngine:
         return hit
 
     # ---- zero-shot -----------------------------------------------------------------------------
-    def zero_shot_logits(self, store: RaggedBagStore, pooling: str = "topj") -> torch.Tensor:
+    def zero_shot_logits(self, store: RaggedBagStore, pooling: str = "topj", check_domain: bool = False) -> torch.Tensor:
+        """``check_domain``: see :meth:`eval_logits` (here only the tensor-core scoring of wide prompt sets can overflow)."""
         c = self.n_classes
         sp0, ss, vp0, vs, small = POOLINGS[pooling](c)
         out = torch.empty(len(store), c, dtype=torch.float32, device=store.device)
         ext_fg = self._prompts_ext_fg if pooling == "bottomk_irrel" else None
+        wide = self.is_wide(store)
+        armed = check_domain and not wide and self.prompts.tc is not None
+        if armed:
+            ws = self._arm_flags(store.device)
+            if ext_fg is not None and ext_fg.tc_flag is not None:
+                ext_fg.tc_flag.zero_()
         for lo, hi in self._waves(store):
             if ext_fg is None:
-                keys = self.keys_for(store, lo, hi)
+                keys = self.keys_for(store, lo, hi, wide)
             else:   # class planes of this pass = feats @ W_ext[:, :C]; the background sum is the same either way
-                keys = ops.score_keys(store.feat[store.offsets_h[lo]:store.offsets_h[hi]], ext_fg, self.normalize)
+                keys = ops.score_keys(store.feat[store.offsets_h[lo]:store.offsets_h[hi]], ext_fg, self.normalize, wide=wide)
             offs, _, _, _ = self._layout(store, lo, hi)
             out[lo:hi] = ops.pool_topk(keys, offs, hi - lo, c, self.topk, sp0, ss, vp0, vs, small)
+        if armed:
+            bad = self._flags_raised(ws) or (ext_fg is not None and ext_fg.tc_flag is not None and int(ext_fg.tc_flag.item()) != 0)
+            if bad:
+                self._wide_stores[store] = True
+                return self.zero_shot_logits(store, pooling)
         return out
 
     # ---- evaluation ----------------------------------------------------------------------------
     def eval_logits(self, store: RaggedBagStore, params: ops.HeadParams, mode: str = "eval",
-                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """Bag logits [n_slides, C] of every slide in the store under the current gate parameters."""
+                    out: Optional[torch.Tensor] = None, check_domain: bool = False) -> torch.Tensor:
+        """Bag logits [n_slides, C] of every slide in the store under the current gate parameters.
+
+        ``check_domain=True`` (what the loops pass; they read the logits back right afterwards): the fast kernels'
+        overflow flags are cleared before the pass and read after it (a host sync); if one is raised the store is
+        marked and the pass repeated on the range-free kernels, which then serve every later pass over that store."""
         c = self.n_classes
         if out is None:
             out = torch.empty(len(store), c, dtype=torch.float32, device=store.device)
         disc = _lib.discard_bits(self.discard)
         act = _lib.active_bits(self.discard, mode)
+        wide = self.is_wide(store)
+        armed = check_domain and not wide
+        if armed:
+            ws = self._arm_flags(store.device)
         for lo, hi in self._waves(store):
-            keys = self.keys_for(store, lo, hi)
+            keys = self.keys_for(store, lo, hi, wide)
             offs, offs_h, base, base_h = self._layout(store, lo, hi)
             feat = store.feat[store.offsets_h[lo]:store.offsets_h[hi]]
             sel = ops.select_union(keys, offs, offs_h, c, self.topj, disc, None, base, base_h)
-            ho = ops.head_forward(feat, keys, c, sel, params, act, self.topk)
+            ho = ops.head_forward(feat, keys, c, sel, params, act, self.topk, wide=wide)
             out[lo:hi] = ho.bag_logits
+        if armed:
+            if self._flags_raised(ws):
+                self._wide_stores[store] = True
+                return self.eval_logits(store, params, mode, out)
+            self._wide_stores.setdefault(store, False)
         return out
 
-    def ablation_logits(self, store: RaggedBagStore, how: str) -> torch.Tensor:
+    def ablation_logits(self, store: RaggedBagStore, how: str, check_domain: bool = False) -> torch.Tensor:
         """Un-gated avg / sum / max of the four planes (ablation_evaluation, main_moc.py:523-582)."""
         c = self.n_classes
         out = torch.empty(len(store), c, dtype=torch.float32, device=store.device)
+        wide = self.is_wide(store)
+        armed = check_domain and not wide and self.prompts.tc is not None
+        if armed:
+            ws = self._arm_flags(store.device)
         for lo, hi in self._waves(store):
-            keys = self.keys_for(store, lo, hi)
+            keys = self.keys_for(store, lo, hi, wide)
             offs, offs_h, base, base_h = self._layout(store, lo, hi)
             feat = store.feat[store.offsets_h[lo]:store.offsets_h[hi]]
             sel = ops.select_union(keys, offs, offs_h, c, self.topj, 0, None, base, base_h)
             out[lo:hi] = ops.ablation_pool(keys, c, sel, how, self.topk)
             del feat
+        if armed and self._flags_raised(ws):
+            self._wide_stores[store] = True
+            return self.ablation_logits(store, how)
         return out
+
+    def ensure_domain(self, store: RaggedBagStore, params: ops.HeadParams) -> bool:
+        """Decide, once per store, whether its features fit the fast kernels' range: one flag-checked evaluation pass
+        over it (the few-shot training bags are a few dozen slides).  Every unmasked row is gated by that pass, and a
+        masked training step only ever gates a subset of them.  Returns True when the range-free kernels are needed."""
+        if store not in self._wide_stores:
+            self.eval_logits(store, params, "train", check_domain=True)
+        return self.is_wide(store)
 
     # ---- training ------------------------------------------------------------------------------
     def train_step(self, store: RaggedBagStore, slide: int, label_dev: torch.Tensor, params: ops.HeadParams,
                    row_mask: Optional[torch.Tensor], grads_out: torch.Tensor) -> StepOut:
         """Forward + CE + backward of one (masked) slide; fills ``grads_out`` (flat, 33 092 floats)."""
         c = self.n_classes
-        keys = self.keys_for(store, slide, slide + 1)
+        wide = self.is_wide(store)      # decided once per store by ensure_domain(): a step has no sync to poll a flag at
+        keys = self.keys_for(store, slide, slide + 1, wide)
         offs, offs_h, base, base_h = self._layout(store, slide, slide + 1)
         feat = store.bag(slide)
         sel = ops.select_union(keys, offs, offs_h, c, self.topj, _lib.discard_bits(self.discard), row_mask, base, base_h)
         act = _lib.active_bits(self.discard, "train")
-        ho = ops.head_forward(feat, keys, c, sel, params, act, self.topk)
+        ho = ops.head_forward(feat, keys, c, sel, params, act, self.topk, wide=wide)
         loss, dl, _ = ops.cross_entropy(ho.bag_logits, label_dev, want_grad=True)
         ops.head_backward(feat, keys, c, sel, params, act, self.topk, ho.pool_pos, dl, out=grads_out)
         return StepOut(loss, ho.bag_logits, sel.sel_count)

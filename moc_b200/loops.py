@@ -125,6 +125,7 @@ def train(model, train_loader, optimizer, device, args, masks: Optional[Iterable
     store = _store_of(train_loader, device)
     ds = train_loader.dataset
     masks = iter(masks) if masks is not None else None
+    eng.ensure_domain(store, model.head_params())   # once per store: features outside the fast kernels' range?
     g = dp_microbatch if dp_microbatch is not None else getattr(args, "dp_microbatch", None)
     n_steps = len(ds)
     if not g or int(g) <= 1:
@@ -206,7 +207,7 @@ def zs_evaluation(loader, device, args, pooling_func=topj_pooling):
     name = _POOL_NAMES.get(pooling_func)
     if name is None:
         raise _lib.MocError(_lib.E_ARG, "pooling_func must be one of the four pooling functions of moc_b200.pooling")
-    logits = eng.zero_shot_logits(store, name)
+    logits = eng.zero_shot_logits(store, name, check_domain=True)
     ds.repeat_num = set_len
     logits, labels = _gathered(ds, logits, store.labels)
     loss_vec, _, pred = ops.cross_entropy(logits, labels, want_pred=True)
@@ -221,7 +222,7 @@ def evaluation(model, loader, device, args):
     store = _store_of(loader, device)
     real_len, set_len = ds.real_len(), len(ds)
     ds.repeat_num = real_len
-    logits = eng.eval_logits(store, model.head_params(), "eval")
+    logits = eng.eval_logits(store, model.head_params(), "eval", check_domain=True)
     ds.repeat_num = set_len
     logits, labels = _gathered(ds, logits, store.labels)
     loss_vec, _, pred = ops.cross_entropy(logits, labels, want_pred=True)
@@ -235,7 +236,7 @@ def ablation_evaluation(loader, device, args):
     store = _store_of(loader, device)
     real_len, set_len = ds.real_len(), len(ds)
     ds.repeat_num = real_len
-    logits = eng.ablation_logits(store, args.ablation_study)
+    logits = eng.ablation_logits(store, args.ablation_study, check_domain=True)
     ds.repeat_num = set_len
     logits, labels = _gathered(ds, logits, store.labels)
     loss_vec, _, pred = ops.cross_entropy(logits, labels, want_pred=True)

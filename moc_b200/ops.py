@@ -111,9 +111,15 @@ def num_key_planes(n_classes: int) -> int:
 
 
 def score_keys(feat: torch.Tensor, prompts: Prompts, normalize: bool = False,
-               out: Optional[torch.Tensor] = None, max_ctas: int = 0) -> torch.Tensor:
+               out: Optional[torch.Tensor] = None, max_ctas: int = 0, wide: bool = False,
+               check_domain: bool = False) -> torch.Tensor:
     """keys [2C+3, R] (plane-major) for R rows of feat [R,512].  ``max_ctas`` (streaming kernel only) leaves SMs free
-    for kernels running on another stream; 0 = the kernel's own best (132 of 148)."""
+    for kernels running on another stream; 0 = the kernel's own best (132 of 148).
+
+    Wide prompt sets are scored on the tensor cores with FP16x3 operands, which overflow for |x| >= 65504 (the fp32
+    reference does not).  ``wide=True`` scores on the fp32 CUDA-core kernel instead (no range limit);
+    ``check_domain=True`` reads the kernel's overflow flag after the launch (one host sync) and repeats the launch
+    that way when it is set - for callers that synchronise right afterwards anyway (slide_process)."""
     feat = _dev_f32(feat, "feat")
     if feat.dim() != 2 or feat.size(1) != D:
         raise MocError(_lib.E_SHAPE, "feat must be [rows,512], got %s" % (tuple(feat.shape),))
@@ -121,10 +127,14 @@ def score_keys(feat: torch.Tensor, prompts: Prompts, normalize: bool = False,
     if out is None:
         out = torch.empty(num_key_planes(prompts.n_classes), r, device=feat.device, dtype=torch.float32)
     _count(1)
-    if prompts.tc is not None and SCORE_IMPL != "simt":
+    if prompts.tc is not None and SCORE_IMPL != "simt" and not wide:
+        if check_domain:
+            prompts.tc_flag.zero_()
         check(_lib.load().moc_score_keys_tc(feat.data_ptr(), r, prompts.tc.data_ptr(), prompts.n_classes,
                                             prompts.n_ext, int(bool(normalize)), out.data_ptr(), out.stride(0),
                                             _stream()))
+        if check_domain and int(prompts.tc_flag.item()) != 0:
+            return score_keys(feat, prompts, normalize, out=out, max_ctas=max_ctas, wide=True)
     else:
         check(_lib.load().moc_score_keys_ex(feat.data_ptr(), r, prompts.packed.data_ptr(), prompts.n_classes,
                                             prompts.n_ext, int(bool(normalize)), out.data_ptr(), out.stride(0),
@@ -235,10 +245,47 @@ class HeadOut:
     bag_logits: torch.Tensor   # [n_slides, C]
     pool_pos: torch.Tensor     # int32 [n_slides, C, topk]
     gate: Optional[torch.Tensor]  # [capacity, 4]
+    domain_flag: Optional[torch.Tensor] = None   # int32 [1]: non-zero once the FP16x3 gate kernel left its |x| < 4094 range
+
+
+class HeadWorkspace:
+    """The gate kernels' scratch (their split / swizzled W1 image) plus the int32 domain flag the FP16x3 kernel raises
+    (include/moc_b200.h: moc_head_domain_flag_offset).  One per (device, stream); the flag is only ever cleared here,
+    by the caller."""
+
+    def __init__(self, device):
+        lib = _lib.load()
+        self.nbytes = lib.moc_head_forward_workspace_bytes()
+        self.buf = torch.zeros(self.nbytes, dtype=torch.uint8, device=device)
+        off = lib.moc_head_domain_flag_offset()
+        self.flag = self.buf[off:off + 4].view(torch.int32)
+
+    def clear_flag(self) -> None:
+        self.flag.zero_()
+
+    def overflowed(self) -> bool:
+        """Synchronises: call it where the results are read anyway."""
+        return int(self.flag.item()) != 0
+
+
+_HEAD_WS = {}
+
+
+def head_workspace(device) -> HeadWorkspace:
+    device = torch.device(device)
+    key = (device.index if device.index is not None else torch.cuda.current_device(), _stream())
+    ws = _HEAD_WS.get(key)
+    if ws is None:
+        if len(_HEAD_WS) > 64:
+            _HEAD_WS.clear()
+        ws = _HEAD_WS[key] = HeadWorkspace(device)
+    return ws
 
 
 def head_forward(feat: torch.Tensor, keys: torch.Tensor, n_classes: int, sel: Selection, params: HeadParams,
-                 active_mask: int, topk: int, want_gate: bool = False) -> HeadOut:
+                 active_mask: int, topk: int, want_gate: bool = False, wide: bool = False) -> HeadOut:
+    """Gate + combination + pooling of every selected row.  ``wide=True`` forces the range-free 3xTF32 gate kernel;
+    otherwise ``HeadOut.domain_flag`` tells (after a sync) whether the FP16x3 kernel met a feature outside its range."""
     dev = feat.device
     cap = max(sel.capacity, 1)
     final = torch.empty(cap, n_classes, dtype=torch.float32, device=dev)
@@ -246,16 +293,16 @@ def head_forward(feat: torch.Tensor, keys: torch.Tensor, n_classes: int, sel: Se
     bag = torch.empty(sel.n_slides, n_classes, dtype=torch.float32, device=dev)
     pos = torch.empty(sel.n_slides, n_classes, topk, dtype=torch.int32, device=dev)
     lib = _lib.load()
-    ws_bytes = lib.moc_head_forward_workspace_bytes()
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    ws = head_workspace(dev)
+    mask = int(active_mask) | (_lib.HEAD_WIDE_DOMAIN if wide else 0)
     _count(3)
     check(lib.moc_head_forward(feat.data_ptr(), keys.data_ptr(), keys.stride(0), n_classes,
                                        sel.sel_base.data_ptr(), sel.sel_rows.data_ptr(), sel.sel_count.data_ptr(),
                                        sel.n_slides, sel.capacity, params.w1.data_ptr(), params.b1.data_ptr(),
-                                       params.w2.data_ptr(), params.b2.data_ptr(), int(active_mask), int(topk),
-                                       _ptr(gate), final.data_ptr(), bag.data_ptr(), pos.data_ptr(), ws.data_ptr(),
-                                       ws_bytes, _stream()))
-    return HeadOut(final, bag, pos, gate)
+                                       params.w2.data_ptr(), params.b2.data_ptr(), mask, int(topk),
+                                       _ptr(gate), final.data_ptr(), bag.data_ptr(), pos.data_ptr(), ws.buf.data_ptr(),
+                                       ws.nbytes, _stream()))
+    return HeadOut(final, bag, pos, gate, ws.flag)
 
 
 def cross_entropy(bag_logits: torch.Tensor, labels: torch.Tensor, grad_scale: float = 1.0, want_grad: bool = False,
@@ -323,18 +370,31 @@ def gather_selected(feat: torch.Tensor, keys: torch.Tensor, n_classes: int, sel_
     return sf, planes
 
 
-def senet_forward(x: torch.Tensor, params: HeadParams) -> torch.Tensor:
+def senet_forward(x: torch.Tensor, params: HeadParams, wide: Optional[bool] = None) -> torch.Tensor:
+    """sigmoid(W2 relu(W1 x + b1) + b2) for a dense [rows,512] input.  ``wide=None`` (default): run the FP16x3 kernel,
+    read its domain flag (one host sync - this is the module-level API, whose callers synchronise per slide anyway) and
+    repeat on the range-free 3xTF32 kernel if a feature was outside |x| < 4094; True / False pick a kernel outright."""
     x = _dev_f32(x, "x")
     if x.dim() != 2 or x.size(1) != D:
         raise MocError(_lib.E_SHAPE, "senet input must be [rows,512], got %s" % (tuple(x.shape),))
     gate = torch.empty(x.size(0), GATES, dtype=torch.float32, device=x.device)
     lib = _lib.load()
-    ws_bytes = lib.moc_head_forward_workspace_bytes()
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
-    _count(2)
-    check(lib.moc_senet_forward(x.data_ptr(), x.size(0), params.w1.data_ptr(), params.b1.data_ptr(),
-                                params.w2.data_ptr(), params.b2.data_ptr(), gate.data_ptr(), ws.data_ptr(), ws_bytes,
-                                _stream()))
+    ws = head_workspace(x.device)
+
+    def run(flags):
+        _count(2)
+        check(lib.moc_senet_forward(x.data_ptr(), x.size(0), params.w1.data_ptr(), params.b1.data_ptr(),
+                                    params.w2.data_ptr(), params.b2.data_ptr(), gate.data_ptr(), flags, ws.buf.data_ptr(),
+                                    ws.nbytes, _stream()))
+
+    if wide:
+        run(_lib.HEAD_WIDE_DOMAIN)
+        return gate
+    if wide is None:
+        ws.clear_flag()
+    run(0)
+    if wide is None and x.size(0) > 0 and ws.overflowed():
+        run(_lib.HEAD_WIDE_DOMAIN)
     return gate
 
 

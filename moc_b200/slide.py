@@ -50,7 +50,7 @@ def slide_process(feat, zeroshot_weights, zeroshot_weights_ext, n_classes, topj=
     mask_d = mask.to(device) if mask is not None else None
 
     prompts = prompts_for(zeroshot_weights, zeroshot_weights_ext)
-    keys = ops.score_keys(feat, prompts)
+    keys = ops.score_keys(feat, prompts, check_domain=True)   # |x| >= 65504 with a wide prompt set: fp32 kernel instead
     offs_h = [0, n]
     offs = torch.tensor(offs_h, dtype=torch.int64, device=device)
     sel = ops.select_union(keys, offs, offs_h, n_classes, int(topj), _lib.discard_bits(discard_classifiers), mask_d)

@@ -443,8 +443,61 @@ def test_head_f16_domain():
     err32 = (g32.double() - g64).abs().max().item()
     assert (got.double() - g64).abs().max().item() <= 3 * err32 + 2e-6
     x[7, 3] = 5000.0
-    bad = ops.senet_forward(x.to(DEV), prm).cpu()
+    bad = ops.senet_forward(x.to(DEV), prm, wide=False).cpu()      # the fast kernel alone: loud, and it raises the flag
     assert not torch.isfinite(bad[7]).all() and torch.isfinite(bad[8:]).all()
+    assert ops.head_workspace(DEV).overflowed()
+    # default: the flag is polled and the launch repeated on the range-free 3xTF32 kernel - finite, like the reference
+    x[9, 100] = -1.0e5
+    g32, _ = O.senet_forward(oprm, x)
+    fixed = ops.senet_forward(x.to(DEV), prm).cpu()
+    assert torch.isfinite(fixed).all()
+    close(fixed, g32, rtol=1e-4, atol=2e-6)
+
+
+@pytest.mark.parametrize("c,big", [(2, 5000.0), (2, 1.0e5), (30, 5000.0), (30, 1.0e5)])
+def test_out_of_range_features_match_the_oracle(c, big):
+    """Features beyond the fast kernels' range (|x| >= 4094 for the FP16x3 gate MLP, >= 65504 for the tensor-core
+    scoring of wide prompt sets) are finite in the reference (fp32 matmul); the flag-checked passes of the engine and
+    slide_process must re-dispatch to the range-free kernels and return the oracle's finite values."""
+    from moc_b200 import RaggedBagStore, slide_process
+    from moc_b200.engine import MocEngine
+    from moc_b200 import synthetic
+    j, k = 100, 10
+    w, we = synthetic.prompt_matrices(c)
+    bags, labels = synthetic.make_cohort(3, [700, 900, 650], c, cohort_seed=31)
+    bags[1][5, 17] = big
+    bags[1][600, 300] = -big
+    oprm = O.SenetParams.init(3)
+    prm = ops_params(oprm)
+    eng = MocEngine(w.to(DEV), we.to(DEV), j, k)
+    store = RaggedBagStore.from_bags(bags, labels, DEV)
+    unchecked = eng.eval_logits(store, prm)
+    got = eng.eval_logits(store, prm, check_domain=True)
+    # 30 classes: 3xTF32 gate kernel (no limit) and FP16x3 scoring (limit 65504), so 5000 is still in range there
+    expect_wide = not (c == 30 and big < 65504)
+    assert eng.is_wide(store) == expect_wide and torch.isfinite(got).all()
+    assert torch.isfinite(unchecked[1]).all() != expect_wide          # the fast path alone is loud about it
+    for i, x in enumerate(bags):
+        ref = O.slide_eval_logits(oprm, x, w, we, c, j, k)
+        close(got[i:i + 1], ref, rtol=1e-3, atol=1e-5)
+    zs = eng.zero_shot_logits(RaggedBagStore.from_bags(bags, labels, DEV), check_domain=True)
+    for i, x in enumerate(bags):
+        close(zs[i:i + 1], O.topj_pooling(x @ w, [k])[1][k], rtol=1e-3, atol=1e-5)
+    # a fresh in-range store stays on the fast kernels
+    ok_store = RaggedBagStore.from_bags([bags[0], bags[2]], [0, 1], DEV)
+    eng.eval_logits(ok_store, prm, check_domain=True)
+    assert not eng.is_wide(ok_store)
+    # module-level API
+    r = slide_process(bags[1], w.to(DEV), we.to(DEV), n_classes=c, topj=j)
+    ref = O.slide_process(bags[1], w, we, c, j)
+    assert r["selected_index"] == ref["selected_index"]
+    close(r["logits_top_classifier"], ref["logits_top_classifier"], rtol=1e-3, atol=1e-4)
+    close(r["logits_bottomk_irrel_classifier"], ref["logits_bottomk_irrel_classifier"], rtol=1e-3, atol=1e-4)
+
+
+def ops_params(oprm):
+    from moc_b200 import ops
+    return ops.HeadParams(oprm.w1.to(DEV), oprm.b1.to(DEV), oprm.w2.to(DEV), oprm.b2.to(DEV))
 
 
 @pytest.mark.parametrize("name", ["bank_rcc_ext", "bank_stress"])
