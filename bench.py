@@ -48,6 +48,9 @@ WORKLOADS = {
                  desc="NSCLC 16-shot eval split: %d synthetic slides x %d CONCH-shaped patches (C=2, C_ext=6, J=400, K=10)"),
     "cfg3": dict(n_classes=3, slides=1000, patches=20000,
                  desc="RCC 3-class eval split: %d synthetic slides x %d patches (C=3, C_ext=7, J=400, K=10)"),
+    "cfg3bank": dict(n_classes=3, slides=1000, patches=20000, bank=64,
+                     desc="RCC 3-class with an UN-COLLAPSED prompt bank: %d synthetic slides x %d patches, 64 prompts per "
+                          "class kept as columns of the scoring contraction (C=3, 192 + 4 columns, J=400, K=10)"),
     "cfg4": dict(n_classes=30, slides=400, patches=50000,
                  desc="EBRAINS-30 eval shard: %d synthetic slides x %d patches (C=30, C_ext=34, J=400, K=10)"),
     "cfg5": dict(n_classes=2, slides=1000, patches=None,
@@ -76,6 +79,7 @@ def parse():
     a = ap.parse_args()
     wl = WORKLOADS[a.workload]
     a.n_classes = wl["n_classes"]
+    a.bank = wl.get("bank", 0)
     a.slides = a.slides or wl["slides"]
     if a.workload == "cfg5" and a.patches is None:
         from moc_b200 import synthetic
@@ -324,6 +328,11 @@ def run_ours(a):
     N_CLASSES = a.n_classes
     strong = a.scaling == "strong"
     w, we = synthetic.prompt_matrices(N_CLASSES, device=dev)
+    bank = None
+    if a.bank:      # configs[2]'s stress case: the class columns are what a bank of a.bank prompts per class collapses to
+        bank_t, w = synthetic.prompt_bank(N_CLASSES, a.bank, device=dev)
+        we = torch.cat([w, we[:, N_CLASSES:]], dim=1).contiguous()
+        bank = (bank_t.t().contiguous(), [a.bank] * N_CLASSES)
     labels_all = [i % N_CLASSES for i in range(len(a.sizes))]
     if strong:      # one cohort for the whole job, LPT-partitioned by patch count
         shard = Shard(a.sizes, rank, world)
@@ -340,7 +349,7 @@ def run_ours(a):
         ids = list(range(len(a.sizes)))
     store = _store_for(ids, a.sizes, labels_all, N_CLASSES, we, seed_of_rank[rank], dev)
     rows_per_gpu = store.total_rows
-    eng = MocEngine(w, we, TOPJ, TOPK)
+    eng = MocEngine(w, we, TOPJ, TOPK, prompt_bank=bank)
     g = torch.Generator().manual_seed(0)
     prm = ops.HeadParams(((torch.rand(64, 512, generator=g) * 2 - 1) * 512 ** -0.5).to(dev),
                          ((torch.rand(64, generator=g) * 2 - 1) * 512 ** -0.5).to(dev),
@@ -426,7 +435,8 @@ def run_ours(a):
     avg_ms = sum(score_ms) / len(score_ms)
     rows_per_launch = sum(score_rows) / len(score_rows)
     achieved = rows_per_launch * 2048 / (avg_ms * 1e-3) / 1e9
-    kernel = "score_keys_regw_kernel<%d>" % (N_CLASSES + 4) if eng.prompts.tc is None else "score_keys_tc_kernel"
+    kernel = ("score_bank_tc_kernel" if bank is not None else
+              "score_keys_regw_kernel<%d>" % (N_CLASSES + 4) if eng.prompts.tc is None else "score_keys_tc_kernel")
     traffic = ncu_traffic_bytes(kernel, rows_per_launch)
     roofline = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
@@ -437,6 +447,27 @@ def run_ours(a):
                         "compute reads 7.3-7.4 TB/s on this part (tools/probe_stream.cu), so this read-mostly kernel "
                         "can exceed 1.0 of it; frac_of_read_only_7400 is the stricter figure",
                 "frac_of_read_only_7400": achieved / 7400.0}
+
+    if bank is not None:
+        # ~100 FLOP per byte: this configuration is bound by the tensor pipe, not by HBM.  Algorithmic work = one
+        # product per (patch, column); the FP16x3 split executes three, on columns padded to a multiple of 16.
+        n_cols = eng.prompts.n_cols
+        flops = rows_per_launch * 2.0 * 512 * n_cols
+        tf = flops / (avg_ms * 1e-3) / 1e12
+        try:
+            mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            tpeak, tsrc = float(mp["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained: the kernel is timed inside a long step)"
+        except Exception:
+            tpeak, tsrc = 1400.0, "fallback (B200_PROFILING.md: ~1.4 PFLOP/s sustained)"
+        roofline = {"bound": "tensor", "kernel": kernel, "achieved": tf, "peak": tpeak, "unit": "TFLOP/s",
+                    "frac": tf / tpeak, "traffic": None, "peak_source": tsrc,
+                    "algorithmic_flops_per_launch": flops, "columns": n_cols, "avg_launch_ms": avg_ms,
+                    "launches_timed": len(score_ms),
+                    "share_of_step": avg_ms * len(score_ms) / a.steps / (ms_local / a.steps),
+                    "executed_TFLOPs": 3.0 * tf * ((n_cols + 15) // 16 * 16) / n_cols,
+                    "hbm_GBps_of_this_kernel": achieved,
+                    "note": "fp32-accurate scores need three FP16 products per algorithmic one (a0 b0 + a1 b0 + a0 b1): "
+                            "executed_TFLOPs is what the tensor pipe actually did"}
 
     # ---- end to end from pinned host memory -------------------------------------------------------------
     e2e = None

@@ -41,6 +41,8 @@ extern "C" {
 #define MOC_HIDDEN 64      /* senet hidden width            main_moc.py:302  */
 #define MOC_GATES 4        /* one gate per classifier       main_moc.py:315  */
 #define MOC_MAX_COLS 64    /* C + number of background prompts, this build   */
+#define MOC_BANK_MAX_CLASSES 8   /* un-collapsed prompt bank: classes ...        */
+#define MOC_BANK_MAX_COLS 256    /* ... and bank prompts + background prompts    */
 
 #define MOC_OK 0
 #define MOC_E_ARG (-1)        /* null pointer / negative size / bad flag      */
@@ -87,6 +89,23 @@ int moc_pack_prompts(const float* w, int n_classes, const float* w_ext, int n_ex
  * one scale, so a bank of any size costs nothing on the streaming path. */
 int moc_collapse_prompt_bank(const float* bank, const int32_t* class_offsets, int n_classes, float* w_out,
                              void* stream);
+
+/* The same bank kept UN-COLLAPSED on the scoring path (BASELINE.json configs[2], SURVEY.md section 8d: the dense
+ * contraction stress case): every prompt is a column of a tensor-core contraction (tcgen05 FP16x3, fp32-accurate),
+ * and the kernel's epilogue takes the per-class sum and rescales it by 1 / (P_c * ||mean_p normalise(w_p)||), which is
+ * exactly `feat @ w_out[:, c]` for the w_out moc_collapse_prompt_bank builds (utils/zeroshot_utils.py:38-44), so the
+ * keys equal moc_score_keys' on the collapsed matrix within the usual tolerance.
+ * bank / class_offsets as above (n_prompts = class_offsets[n_classes]); bg [n_bg][512] row-major are the background
+ * prompts (the columns C.. of zeroshot_weights_ext, transposed), used as given.  2 <= n_classes <=
+ * MOC_BANK_MAX_CLASSES, n_prompts + n_bg <= MOC_BANK_MAX_COLS.  image: moc_prompt_bank_tc_bytes() bytes, 16-byte
+ * aligned, built once per bank; an int32 flag at moc_prompt_bank_tc_flag_offset() is set when a score came out
+ * non-finite (|x| >= 65504 or non-finite features), like moc_prompts_tc_flag_offset.  keys as moc_score_keys. */
+size_t moc_prompt_bank_tc_bytes(int n_prompts, int n_bg);
+size_t moc_prompt_bank_tc_flag_offset(int n_prompts, int n_bg);
+int moc_prepare_prompt_bank_tc(const float* bank, const int32_t* class_offsets, int n_classes, int n_prompts,
+                               const float* bg, int n_bg, void* image, size_t image_bytes, void* stream);
+int moc_score_keys_bank_tc(const float* feat, int64_t n_rows, const void* image, int n_classes, int n_prompts,
+                           int n_bg, int normalize, float* keys, int64_t key_stride, void* stream);
 
 /* ---- a2 + selection keys: the streaming kernel ----------------------------
  * Replaces `feat @ zeroshot_weights`, `feat @ zeroshot_weights_ext`

@@ -37,6 +37,10 @@ SIGNATURES = {
     "moc_packed_cols": (i32, [i32, i32]),
     "moc_pack_prompts": (i32, [p, i32, p, i32, p, p]),
     "moc_collapse_prompt_bank": (i32, [p, p, i32, p, p]),
+    "moc_prompt_bank_tc_bytes": (sz, [i32, i32]),
+    "moc_prompt_bank_tc_flag_offset": (sz, [i32, i32]),
+    "moc_prepare_prompt_bank_tc": (i32, [p, p, i32, i32, p, i32, p, sz, p]),
+    "moc_score_keys_bank_tc": (i32, [p, i64, p, i32, i32, i32, i32, p, i64, p]),
     "moc_score_keys": (i32, [p, i64, p, i32, i32, i32, p, i64, p]),
     "moc_score_keys_ex": (i32, [p, i64, p, i32, i32, i32, p, i64, i32, p]),
     "moc_prompts_tc_bytes": (sz, [i32, i32]),

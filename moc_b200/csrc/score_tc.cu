@@ -459,6 +459,370 @@ score_keys_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const float* 
     }
 }
 
+// =====================================================================================================
+// Un-collapsed prompt BANK (BASELINE.json configs[2]: >= 64 prompts per class kept as W_bank [512, C*P]).
+//
+// The reference collapses a bank offline to one unit column per class (utils/zeroshot_utils.py:38-44: normalise every
+// prompt, mean over the class, renormalise) and scores against that.  Scoring is linear, so the class logit equals
+//     L_c = ( sum_{p in class c} x . w^_p ) / ( P_c * || mean_p w^_p || )            w^_p = prompt p, L2-normalised
+// This kernel keeps the bank un-collapsed: every prompt is a column of the tensor-core contraction (the dense
+// stress case of SURVEY.md section 8d: 2*512*(C*P + n_bg) FLOP per 2 KB patch, ~100 FLOP/B - tensor-bound, not
+// HBM-bound) and the group sum + the 1/(P_c ||mean||) rescale happen in the epilogue; keys come out in the usual
+// layout.  Same FP16x3 operand split, same producers as score_keys_tc_kernel.  Differences:
+//   * up to 256 columns: one tcgen05.mma of N = round16(columns); two TMEM accumulators of 256 columns each
+//   * the split prompt image ([b0 ; b1] per 64-wide K-block: 2 * N * 128 B, 52 KB at 196 columns) no longer fits
+//     shared memory for all eight K-blocks: a B-loader warp streams one K-block tile per bulk copy (UBLKCP, L2
+//     evict-last: all CTAs read the same 416 KB image) into a two-stage ring, in step with the A stages
+//   * epilogue: thread = patch; the accumulator is read 32 columns at a time; a chunk that lies inside one class
+//     (almost all do) is tree-summed and added to that class's sum, boundary chunks go element by element
+struct BankTail {                      // after the eight K-block tiles of the image
+    float scale, descale;              // same first 16 bytes as ScoreTcTail (score_tc_scale_kernel writes them)
+    int flag, pad;
+    int col_off[MOC_BANK_MAX_CLASSES + 1];   // first column of every class; col_off[C] = number of bank prompts
+    float cls_scale[MOC_BANK_MAX_CLASSES];   // 1 / (P_c * ||mean_p w^_p||)
+};
+
+struct BankGeom {
+    int n_cols;    // bank prompts + background prompts
+    int npa;       // columns rounded up to 16 = MMA width N = row of b1 inside a K-block tile
+    __host__ __device__ size_t tile_bytes() const { return (size_t)(2 * npa) * 128; }
+    __host__ __device__ size_t b_bytes() const { return (size_t)ST_NKB * tile_bytes(); }
+    __host__ __device__ size_t packed_offset() const { return (b_bytes() + sizeof(BankTail) + 255) & ~(size_t)255; }
+    __host__ __device__ size_t image_bytes() const { return packed_offset() + (size_t)n_cols * D * sizeof(float); }
+};
+__host__ __device__ inline BankGeom bank_geom(int n_prompts, int n_bg) {
+    BankGeom g;
+    g.n_cols = n_prompts + n_bg;
+    g.npa = (g.n_cols + 15) & ~15;
+    return g;
+}
+
+constexpr int SB_B_STAGES = 2;
+constexpr int SB_ACC_COLS = 256;
+constexpr int SB_WARP_B = ST_WARP_MMA + 1;          // 13: B loader
+constexpr int SB_THREADS = (SB_WARP_B + 1) * 32;    // 448
+
+// rows of the packed K-major matrix the image is built from: bank prompts L2-normalised (F.normalize, eps 1e-12),
+// background prompts as given.  One block of 512 threads per column.
+__global__ void __launch_bounds__(D) bank_pack_kernel(const float* __restrict__ bank, int n_prompts,
+                                                     const float* __restrict__ bg, int n_bg,
+                                                     float* __restrict__ packed) {
+    __shared__ float red[D / 32];
+    __shared__ float total;
+    const int col = blockIdx.x, k = threadIdx.x;
+    if (col >= n_prompts) {
+        packed[(size_t)col * D + k] = bg[(size_t)(col - n_prompts) * D + k];
+        return;
+    }
+    const float v = bank[(size_t)col * D + k];
+    const float s = warp_sum(v * v);
+    if ((k & 31) == 0) red[k >> 5] = s;
+    __syncthreads();
+    if (k == 0) {
+        float t = 0.f;
+        for (int w = 0; w < D / 32; ++w) t += red[w];
+        total = fmaxf(sqrtf(t), 1e-12f);
+    }
+    __syncthreads();
+    packed[(size_t)col * D + k] = v / total;
+}
+
+// One block of 512 threads per class: || mean of the class's normalised prompts ||, column range, rescale factor.
+__global__ void __launch_bounds__(D) bank_class_scale_kernel(const float* __restrict__ packed,
+                                                            const int32_t* __restrict__ class_offsets, int n_classes,
+                                                            BankTail* __restrict__ tail) {
+    __shared__ float red[D / 32];
+    const int c = blockIdx.x, k = threadIdx.x;
+    const int p0 = class_offsets[c], p1 = class_offsets[c + 1];
+    float acc = 0.f;
+    for (int p = p0; p < p1; ++p) acc += packed[(size_t)p * D + k];
+    const float m = acc / (float)(p1 - p0);
+    const float s = warp_sum(m * m);
+    if ((k & 31) == 0) red[k >> 5] = s;
+    __syncthreads();
+    if (k == 0) {
+        float t = 0.f;
+        for (int w = 0; w < D / 32; ++w) t += red[w];
+        tail->col_off[c] = p0;
+        if (c == n_classes - 1) tail->col_off[n_classes] = p1;
+        tail->cls_scale[c] = 1.0f / ((float)(p1 - p0) * sqrtf(t));
+    }
+}
+
+template <bool NORM>
+__global__ void __launch_bounds__(SB_THREADS, 1)
+score_bank_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const float* __restrict__ feat, int64_t n_rows,
+                     const unsigned char* __restrict__ image, int n_classes, BankGeom g, int ring_slots,
+                     float* __restrict__ keys, int64_t key_stride, BankTail* __restrict__ tail) {
+    extern __shared__ unsigned char sb_smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[ST_A_STAGES], empty_bar[ST_A_STAGES], tfull_bar[2], tempty_bar[2];
+    __shared__ __align__(8) uint64_t bfull_bar[SB_B_STAGES], bempty_bar[SB_B_STAGES];
+    __shared__ __align__(8) uint64_t raw_bar[ST_PROD_WARPS][ST_MAX_SLOTS];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ int col_off_s[MOC_BANK_MAX_CLASSES + 1];
+    __shared__ float cls_scale_s[MOC_BANK_MAX_CLASSES];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(sb_smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t tile_bytes = (uint32_t)g.tile_bytes();
+    unsigned char* bsm = smem;                                         // B ring: SB_B_STAGES K-block tiles
+    unsigned char* asm_ = smem + (size_t)SB_B_STAGES * tile_bytes;     // A stages (a0 | a1)
+    unsigned char* rawsm = asm_ + ST_A_STAGES * ST_STAGE_BYTES;        // per-warp raw fp32 rings
+    constexpr int tmem_cols = 2 * SB_ACC_COLS;                         // the whole tensor memory
+
+    if (tid <= n_classes) col_off_s[tid] = tail->col_off[tid];
+    if (tid < n_classes) cls_scale_s[tid] = tail->cls_scale[tid];
+    if (tid == 0) {
+        for (int s = 0; s < ST_A_STAGES; ++s) {
+            mbar_init(&full_bar[s], ST_PROD_WARPS);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < SB_B_STAGES; ++s) {
+            mbar_init(&bfull_bar[s], 1);
+            mbar_init(&bempty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tfull_bar[a], 1);
+            mbar_init(&tempty_bar[a], ST_EPI_WARPS);
+        }
+        for (int w = 0; w < ST_PROD_WARPS; ++w)
+            for (int s = 0; s < ring_slots; ++s) mbar_init(&raw_bar[w][s], 1);
+        fence_mbar_init();
+    }
+    if (warp == ST_WARP_MMA) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                     "r"((uint32_t)tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    st_fence_before();
+    __syncthreads();
+    st_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    const int64_t n_tiles = (n_rows + ST_M - 1) / ST_M;
+    const int64_t my_tiles = (int64_t)blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    if (warp >= ST_EPI_WARPS && warp < ST_WARP_MMA) {
+        // =============================== producers (as in score_keys_tc_kernel) ====================
+        const int pw = warp - ST_EPI_WARPS, rhalf = lane >> 4, q = lane & 15;
+        const uint64_t policy = l2_policy_evict_first();
+        const int64_t n_slots_total = my_tiles * ST_NKB * 2;
+        const uint32_t ring = smem_u32(rawsm) + (uint32_t)(pw * ring_slots * ST_SLOT_BYTES);
+        const uint32_t bars = smem_u32(&raw_bar[pw][0]);
+        int64_t i_tile = blockIdx.x, i_left = n_slots_total;
+        int i_sub = 0;
+        auto issue = [&](int pos) {
+            if (lane == 0) {
+                const int64_t row0 = i_tile * ST_M + pw * 16 + (i_sub & 1) * ST_SLOT_ROWS;
+                const uint32_t bar = bars + pos * 8;
+                mbar_arrive_expect_tx_a(bar, ST_SLOT_BYTES);
+                tma_load_2d(ring + pos * ST_SLOT_BYTES, &feat_map, (i_sub >> 1) * ST_KB, (int)row0, bar, policy);
+            }
+            if (++i_sub == 2 * ST_NKB) { i_sub = 0; i_tile += gridDim.x; }
+            --i_left;
+        };
+        for (int s = 0; s < ring_slots; ++s)
+            if (i_left > 0) issue(s);
+        uint32_t roff[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = pw * 16 + i * 2 + rhalf;
+            roff[i] = (uint32_t)(r * 128 + (((q >> 1) ^ (r & 7)) << 4) + ((q & 1) << 3));
+        }
+        const uint32_t a_base = smem_u32(asm_);
+        const uint32_t lds_off = (uint32_t)(rhalf * (ST_KB * 4) + q * 16);
+        int stage = 0, pos = 0;
+        uint32_t parity = 0, rparity = 0;
+        for (int64_t step = 0; step < my_tiles * ST_NKB; ++step) {
+            uint2 c0[8], c1[8];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                mbar_wait_a(bars + pos * 8, rparity);
+                const uint32_t sp = ring + pos * ST_SLOT_BYTES + lds_off;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) split4(lds128(sp + i * 2 * (ST_KB * 4)), c0[4 * j + i], c1[4 * j + i]);
+                __syncwarp();
+                if (i_left > 0) issue(pos);
+                if (++pos == ring_slots) { pos = 0; rparity ^= 1u; }
+            }
+            mbar_wait(&empty_bar[stage], parity ^ 1u);
+            const uint32_t a0 = a_base + stage * ST_STAGE_BYTES;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                sts64(a0 + roff[i], c0[i]);
+                sts64(a0 + ST_A_BYTES + roff[i], c1[i]);
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full_bar[stage]);
+            if (++stage == ST_A_STAGES) { stage = 0; parity ^= 1u; }
+        }
+    } else if (warp == SB_WARP_B) {
+        // =============================== B loader: one K-block tile of the image per step ===========
+        if (lane == 0) {
+            const uint64_t policy = l2_policy_evict_last();
+            int bs = 0;
+            uint32_t bparity = 0;
+            for (int64_t step = 0; step < my_tiles * ST_NKB; ++step) {
+                const int kb = (int)(step % ST_NKB);
+                mbar_wait(&bempty_bar[bs], bparity ^ 1u);
+                mbar_arrive_expect_tx(&bfull_bar[bs], tile_bytes);
+                for (uint32_t o = 0; o < tile_bytes; o += 16384u)      // 16 KB pieces, all counted on the one barrier
+                    bulk_g2s(bsm + (size_t)bs * tile_bytes + o, image + (size_t)kb * tile_bytes + o,
+                             tile_bytes - o < 16384u ? tile_bytes - o : 16384u, &bfull_bar[bs], policy);
+                if (++bs == SB_B_STAGES) { bs = 0; bparity ^= 1u; }
+            }
+        }
+    } else if (warp == ST_WARP_MMA) {
+        // =============================== MMA issuer ================================================
+        const uint32_t idesc = st_idesc_f16(g.npa);
+        const uint32_t b1_off = (uint32_t)g.npa * 128u;
+        int stage = 0, acc = 0, bs = 0;
+        uint32_t parity = 0, acc_parity = 0, bparity = 0;
+        for (int64_t t = 0; t < my_tiles; ++t) {
+            if (lane == 0) {
+                mbar_wait(&tempty_bar[acc], acc_parity ^ 1u);
+                st_fence_after();
+            }
+            __syncwarp();
+            const uint32_t tmem_d = tmem_base + acc * SB_ACC_COLS;
+            for (int kb = 0; kb < ST_NKB; ++kb) {
+                if (lane == 0) {
+                    mbar_wait(&full_bar[stage], parity);
+                    mbar_wait(&bfull_bar[bs], bparity);
+                    st_fence_after();
+                    const uint32_t a0 = smem_u32(asm_ + (size_t)stage * ST_STAGE_BYTES);
+                    const uint32_t a1 = a0 + ST_A_BYTES;
+                    const uint32_t bt = smem_u32(bsm + (size_t)bs * tile_bytes);
+#pragma unroll
+                    for (int ks = 0; ks < ST_KB / 16; ++ks) {
+                        const uint32_t o = ks * 32;
+                        const uint64_t da0 = st_desc_sw128(a0 + o), da1 = st_desc_sw128(a1 + o);
+                        const uint64_t db0 = st_desc_sw128(bt + o), db1 = st_desc_sw128(bt + b1_off + o);
+                        umma_f16(tmem_d, da0, db1, idesc, (kb | ks) != 0 ? 1u : 0u);
+                        umma_f16(tmem_d, da1, db0, idesc, 1u);
+                        umma_f16(tmem_d, da0, db0, idesc, 1u);
+                    }
+                    st_commit(&empty_bar[stage]);
+                    st_commit(&bempty_bar[bs]);
+                    if (kb == ST_NKB - 1) st_commit(&tfull_bar[acc]);
+                }
+                __syncwarp();
+                if (++stage == ST_A_STAGES) { stage = 0; parity ^= 1u; }
+                if (++bs == SB_B_STAGES) { bs = 0; bparity ^= 1u; }
+            }
+            if (++acc == 2) { acc = 0; acc_parity ^= 1u; }
+        }
+    } else {
+        // =============================== epilogue (warps 0-3): thread = patch ========================
+        const int C = n_classes;
+        const int n_bank = col_off_s[C], n_cols = g.n_cols;
+        const int n_chunks = (n_cols + 31) >> 5;
+        const float descale = tail->descale;
+        int acc = 0;
+        uint32_t acc_parity = 0;
+        bool bad = false;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int64_t row = tile * ST_M + warp * 32 + lane;
+            mbar_wait(&tfull_bar[acc], acc_parity);
+            st_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * SB_ACC_COLS;
+            float cs[MOC_BANK_MAX_CLASSES];
+#pragma unroll
+            for (int c = 0; c < MOC_BANK_MAX_CLASSES; ++c) cs[c] = 0.f;
+            float bsum = 0.f, bmax = -INFINITY, probe = 0.f;
+            int cls = 0;                                    // class of the current chunk's first column (warp-uniform)
+            for (int ch = 0; ch < n_chunks; ++ch) {
+                float d[32];
+                st_tmem_ld32(taddr + ch * 32, d);
+                const int c0 = ch * 32;
+                while (cls < C && c0 >= col_off_s[cls + 1]) ++cls;
+                if (cls < C && c0 + 32 <= col_off_s[cls + 1]) {
+                    // the whole chunk belongs to class `cls`: fixed-shape tree sum, one add into that class
+#pragma unroll
+                    for (int w = 16; w > 0; w >>= 1)
+#pragma unroll
+                        for (int e = 0; e < w; ++e) d[e] += d[e + w];
+                    probe = fmaf(d[0], 0.f, probe);
+#pragma unroll
+                    for (int c = 0; c < MOC_BANK_MAX_CLASSES; ++c)
+                        if (c == cls) cs[c] += d[0];
+                } else {
+                    // a chunk straddling class boundaries, the background columns or the padding
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) {
+                        const int col = c0 + e;
+                        const float x = d[e];
+                        if (col < n_bank) {
+                            probe = fmaf(x, 0.f, probe);
+#pragma unroll
+                            for (int c = 0; c < MOC_BANK_MAX_CLASSES; ++c)
+                                if (c < C && col >= col_off_s[c] && col < col_off_s[c + 1]) cs[c] += x;
+                        } else if (col < n_cols) {
+                            const float b = x * descale;
+                            probe = fmaf(b, 0.f, probe);
+                            bsum += b;
+                            bmax = fmaxf(bmax, b);
+                        }
+                    }
+                }
+            }
+            st_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (++acc == 2) { acc = 0; acc_parity ^= 1u; }
+            if (row >= n_rows) continue;
+            float inv = 1.0f;
+            if (NORM) {
+                const float4* xp = reinterpret_cast<const float4*>(feat + row * D);
+                float ss = 0.f;
+                for (int i = 0; i < D / 4; ++i) {
+                    const float4 t = __ldg(xp + i);
+                    ss = fmaf(t.x, t.x, ss); ss = fmaf(t.y, t.y, ss); ss = fmaf(t.z, t.z, ss); ss = fmaf(t.w, t.w, ss);
+                }
+                inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+                bsum *= inv;
+                bmax *= inv;
+            }
+            bad |= (probe != probe);
+            float m1 = -INFINITY, m2 = -INFINITY;
+            float* kp = keys + row;
+#pragma unroll
+            for (int c = 0; c < MOC_BANK_MAX_CLASSES; ++c) {
+                if (c < C) {
+                    const float l = cs[c] * descale * cls_scale_s[c] * inv;
+                    cs[c] = l;
+                    m2 = fmaxf(m2, fminf(m1, l));
+                    m1 = fmaxf(m1, l);
+                    kp[(int64_t)c * key_stride] = l;
+                }
+            }
+            float esum = 0.f;
+#pragma unroll
+            for (int c = 0; c < MOC_BANK_MAX_CLASSES; ++c) {
+                if (c < C) {
+                    cs[c] = expf(cs[c] - m1);
+                    esum += cs[c];
+                }
+            }
+            const float inv_sum = 1.0f / esum;
+#pragma unroll
+            for (int c = 0; c < MOC_BANK_MAX_CLASSES; ++c)
+                if (c < C) kp[(int64_t)(C + c) * key_stride] = cs[c] * inv_sum;
+            kp[(int64_t)(2 * C) * key_stride] = fabsf(m1 - m2);
+            kp[(int64_t)(2 * C + 1) * key_stride] = bsum;
+            kp[(int64_t)(2 * C + 2) * key_stride] = bmax;
+        }
+        if (bad) atomicExch(&tail->flag, 1);
+    }
+
+    st_fence_before();
+    __syncthreads();
+    if (warp == ST_WARP_MMA) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)tmem_cols)
+                     : "memory");
+    }
+}
+
 // feat viewed as a 2-D fp32 tensor [n_rows][512]; box = one raw slot (ST_SLOT_ROWS patches x ST_KB floats).
 static int make_feat_map(CUtensorMap* map, const float* feat, int64_t n_rows) {
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -514,9 +878,99 @@ static int launch_tc(const float* feat, int64_t n_rows, const unsigned char* pre
     return MOC_OK;
 }
 
+template <bool NORM>
+static int launch_bank(const float* feat, int64_t n_rows, const unsigned char* image, int C, const BankGeom& g, float* keys,
+                       int64_t key_stride, cudaStream_t st) {
+    const size_t budget = 227 * 1024 - 1024 - 2048;  // alignment slack, static shared memory
+    const size_t fixed = (size_t)SB_B_STAGES * g.tile_bytes() + (size_t)ST_A_STAGES * ST_STAGE_BYTES;
+    int ring_slots = fixed < budget ? (int)((budget - fixed) / ((size_t)ST_PROD_WARPS * ST_SLOT_BYTES)) : 0;
+    if (ring_slots > ST_MAX_SLOTS) ring_slots = ST_MAX_SLOTS;
+    MOC_CHECK_SHAPE(ring_slots >= 2, "moc_score_keys_bank_tc: %d columns do not fit the kernel's shared memory", g.n_cols);
+    const size_t smem = fixed + (size_t)ring_slots * ST_PROD_WARPS * ST_SLOT_BYTES + 1024;
+    MOC_CUDA(cudaFuncSetAttribute(score_bank_tc_kernel<NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t n_tiles = (n_rows + ST_M - 1) / ST_M;
+    const int grid = (int)(n_tiles < sm_count() ? n_tiles : sm_count());
+    BankTail* tail = reinterpret_cast<BankTail*>(const_cast<unsigned char*>(image) + g.b_bytes());
+    CUtensorMap map;
+    const int rc = make_feat_map(&map, feat, n_rows);
+    if (rc != MOC_OK) return rc;
+    score_bank_tc_kernel<NORM><<<grid, SB_THREADS, smem, st>>>(map, feat, n_rows, image, C, g, ring_slots, keys, key_stride,
+                                                              tail);
+    MOC_LAUNCH_CHECK("score_bank_tc_kernel");
+    return MOC_OK;
+}
+
+static int bank_args_ok(int n_classes, int n_prompts, int n_bg) {
+    MOC_CHECK_SHAPE(n_classes >= 2 && n_classes <= MOC_BANK_MAX_CLASSES,
+                    "prompt bank: 2..%d classes supported, got %d", MOC_BANK_MAX_CLASSES, n_classes);
+    MOC_CHECK_SHAPE(n_prompts >= n_classes && n_bg >= 1 && n_prompts + n_bg <= MOC_BANK_MAX_COLS,
+                    "prompt bank: need >= 1 prompt per class, >= 1 background prompt and at most %d columns in all, got "
+                    "%d + %d", MOC_BANK_MAX_COLS, n_prompts, n_bg);
+    return MOC_OK;
+}
+
 }  // namespace moc
 
 using namespace moc;
+
+extern "C" size_t moc_prompt_bank_tc_bytes(int n_prompts, int n_bg) {
+    if (n_prompts < 1 || n_bg < 1 || n_prompts + n_bg > MOC_BANK_MAX_COLS) return 0;
+    return bank_geom(n_prompts, n_bg).image_bytes();
+}
+
+extern "C" size_t moc_prompt_bank_tc_flag_offset(int n_prompts, int n_bg) {
+    return bank_geom(n_prompts, n_bg).b_bytes() + offsetof(BankTail, flag);
+}
+
+extern "C" int moc_prepare_prompt_bank_tc(const float* bank, const int32_t* class_offsets, int n_classes, int n_prompts,
+                                          const float* bg, int n_bg, void* image, size_t image_bytes, void* stream) {
+    MOC_CHECK_ARG(bank && class_offsets && bg && image, "moc_prepare_prompt_bank_tc: null pointer");
+    {
+        const int rc = bank_args_ok(n_classes, n_prompts, n_bg);
+        if (rc != MOC_OK) return rc;
+    }
+    MOC_CHECK_ARG((reinterpret_cast<uintptr_t>(image) & 15) == 0, "moc_prepare_prompt_bank_tc: image must be 16-byte aligned");
+    const BankGeom g = bank_geom(n_prompts, n_bg);
+    if (image_bytes < g.image_bytes()) {
+        set_error("moc_prepare_prompt_bank_tc: image needs %zu bytes, got %zu", g.image_bytes(), image_bytes);
+        return MOC_E_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned char* out = reinterpret_cast<unsigned char*>(image);
+    BankTail* tail = reinterpret_cast<BankTail*>(out + g.b_bytes());
+    float* packed = reinterpret_cast<float*>(out + g.packed_offset());
+    MOC_CUDA(cudaMemsetAsync(out, 0, g.packed_offset(), st));
+    bank_pack_kernel<<<g.n_cols, D, 0, st>>>(bank, n_prompts, bg, n_bg, packed);
+    MOC_LAUNCH_CHECK("bank_pack_kernel");
+    score_tc_scale_kernel<<<1, 1024, 0, st>>>(packed, g.n_cols * D, reinterpret_cast<ScoreTcTail*>(tail));
+    MOC_LAUNCH_CHECK("score_tc_scale_kernel");
+    ScoreTcGeom tg;                       // the tile layout of score_tc_prep_kernel with b1 at row npa
+    tg.npa = g.npa;
+    tg.n_wide = 2 * g.npa;
+    tg.n_narrow = g.npa;
+    score_tc_prep_kernel<<<(g.n_cols * (D / 4) + 255) / 256, 256, 0, st>>>(packed, g.n_cols, tg,
+                                                                         reinterpret_cast<const ScoreTcTail*>(tail), out);
+    MOC_LAUNCH_CHECK("score_tc_prep_kernel");
+    bank_class_scale_kernel<<<n_classes, D, 0, st>>>(packed, class_offsets, n_classes, tail);
+    MOC_LAUNCH_CHECK("bank_class_scale_kernel");
+    return MOC_OK;
+}
+
+extern "C" int moc_score_keys_bank_tc(const float* feat, int64_t n_rows, const void* image, int n_classes, int n_prompts,
+                                      int n_bg, int normalize, float* keys, int64_t key_stride, void* stream) {
+    MOC_CHECK_ARG(feat && image && keys, "moc_score_keys_bank_tc: null pointer");
+    MOC_CHECK_ARG(n_rows >= 0 && key_stride >= n_rows, "moc_score_keys_bank_tc: bad n_rows / key_stride");
+    {
+        const int rc = bank_args_ok(n_classes, n_prompts, n_bg);
+        if (rc != MOC_OK) return rc;
+    }
+    MOC_CHECK_ARG((reinterpret_cast<uintptr_t>(feat) & 15) == 0, "moc_score_keys_bank_tc: feat must be 16-byte aligned");
+    if (n_rows == 0) return MOC_OK;
+    const BankGeom g = bank_geom(n_prompts, n_bg);
+    const unsigned char* p = reinterpret_cast<const unsigned char*>(image);
+    return normalize ? launch_bank<true>(feat, n_rows, p, n_classes, g, keys, key_stride, (cudaStream_t)stream)
+                     : launch_bank<false>(feat, n_rows, p, n_classes, g, keys, key_stride, (cudaStream_t)stream);
+}
 
 extern "C" size_t moc_prompts_tc_bytes(int n_classes, int n_ext) {
     (void)n_classes;

@@ -42,8 +42,20 @@ class StepOut:
 class MocEngine:
     def __init__(self, zeroshot_weights: torch.Tensor, zeroshot_weights_ext: torch.Tensor, topj: int = 10,
                  topk: int = 10, discard_classifiers: Sequence[str] = (), normalize: bool = False,
-                 cache_scores: bool = False, max_wave_rows: int = 48 * 1024 * 1024):
-        self.prompts = ops.Prompts.pack(zeroshot_weights, zeroshot_weights_ext)
+                 cache_scores: bool = False, max_wave_rows: int = 48 * 1024 * 1024,
+                 prompt_bank: Optional[tuple] = None):
+        """``prompt_bank=(bank [n_prompts,512], prompts_per_class)`` keeps the class prompts UN-COLLAPSED on the scoring
+        path (ops.BankPrompts): ``zeroshot_weights`` must then be the matrix the bank collapses to (it is checked) and
+        every pass gives what it gives without the bank, within the scoring tolerance - the dense stress configuration
+        of BASELINE.json configs[2], not something the reference does at run time (it collapses offline)."""
+        if prompt_bank is None:
+            self.prompts = ops.Prompts.pack(zeroshot_weights, zeroshot_weights_ext)
+        else:
+            bank, counts = prompt_bank
+            self.prompts = ops.BankPrompts.pack(bank.to(zeroshot_weights.device), counts, zeroshot_weights_ext)
+            w_from_bank = self.prompts.collapsed.packed[:len(counts)].t()
+            if (w_from_bank - zeroshot_weights.float()).abs().max().item() > 1e-5:
+                raise _lib.MocError(_lib.E_ARG, "zeroshot_weights is not what the prompt bank collapses to")
         self.n_classes = self.prompts.n_classes
         # slide_process never reads W_ext[:, :C] (only the background columns matter to it), but zs_evaluation with
         # bottomk_irrel_classifier_pooling pools (feats @ W_ext)[:, :C] (main_moc.py:428-432,

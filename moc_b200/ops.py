@@ -106,11 +106,69 @@ def collapse_prompt_bank(bank: torch.Tensor, prompts_per_class: Sequence[int]) -
     return out
 
 
+@dataclass
+class BankPrompts:
+    """An UN-COLLAPSED prompt bank on the scoring path (BASELINE.json configs[2]): every prompt
+    of every class stays a column of the tensor-core contraction, the per-class mean and the 1/||mean|| rescale of
+    utils/zeroshot_utils.py:38-44 happen in the kernel's epilogue.  ``collapsed`` is the ordinary packing of the matrix
+    the reference would score against (``collapse_prompt_bank`` + the background columns): the range-free fallback
+    and the cross-check."""
+    image: torch.Tensor          # uint8: split / swizzled K-block tiles, tail, packed fp32 rows
+    n_classes: int
+    n_prompts: int
+    n_bg: int
+    collapsed: "Prompts"
+    tc_flag: Optional[torch.Tensor] = None
+
+    @property
+    def n_ext(self) -> int:
+        return self.n_classes + self.n_bg
+
+    @property
+    def n_cols(self) -> int:
+        return self.n_prompts + self.n_bg
+
+    @property
+    def tc(self):                # "has a tensor-core scoring path with an |x| limit" for the engine's domain logic
+        return self.image
+
+    @staticmethod
+    def pack(bank: torch.Tensor, prompts_per_class: Sequence[int], w_ext: torch.Tensor) -> "BankPrompts":
+        """bank [n_prompts,512] (class after class), prompts per class, and zeroshot_weights_ext [512, C+n_bg] whose
+        last n_bg columns are the background prompts (its first C columns are not scored, as in slide_process)."""
+        bank = _dev_f32(bank, "bank")
+        w_ext = _dev_f32(w_ext, "zeroshot_weights_ext")
+        counts = [int(c) for c in prompts_per_class]
+        c = len(counts)
+        if bank.dim() != 2 or bank.size(1) != D or sum(counts) != bank.size(0) or min(counts, default=0) < 1:
+            raise MocError(_lib.E_SHAPE, "bank must be [sum(prompts_per_class),512] with at least one prompt per class")
+        if w_ext.dim() != 2 or w_ext.size(0) != D or w_ext.size(1) <= c:
+            raise MocError(_lib.E_SHAPE, "zeroshot_weights_ext must be [512, C + n_bg] with n_bg >= 1")
+        n_bg = w_ext.size(1) - c
+        lib = _lib.load()
+        nb = lib.moc_prompt_bank_tc_bytes(bank.size(0), n_bg)
+        if nb == 0:
+            raise MocError(_lib.E_SHAPE, "prompt bank of %d + %d columns exceeds this build's limit" % (bank.size(0), n_bg))
+        offs = [0]
+        for n in counts:
+            offs.append(offs[-1] + n)
+        offs_d = torch.tensor(offs, dtype=torch.int32, device=bank.device)
+        bg = w_ext[:, c:].t().contiguous()
+        image = torch.empty(nb, dtype=torch.uint8, device=bank.device)
+        _count(4)
+        check(lib.moc_prepare_prompt_bank_tc(bank.data_ptr(), offs_d.data_ptr(), c, bank.size(0), bg.data_ptr(), n_bg,
+                                             image.data_ptr(), nb, _stream()))
+        off = lib.moc_prompt_bank_tc_flag_offset(bank.size(0), n_bg)
+        w = collapse_prompt_bank(bank, counts)
+        return BankPrompts(image, c, bank.size(0), n_bg, Prompts.pack(w, torch.cat([w, w_ext[:, c:]], dim=1).contiguous()),
+                           image[off:off + 4].view(torch.int32))
+
+
 def num_key_planes(n_classes: int) -> int:
     return 2 * n_classes + 3
 
 
-def score_keys(feat: torch.Tensor, prompts: Prompts, normalize: bool = False,
+def score_keys(feat: torch.Tensor, prompts, normalize: bool = False,
                out: Optional[torch.Tensor] = None, max_ctas: int = 0, wide: bool = False,
                check_domain: bool = False) -> torch.Tensor:
     """keys [2C+3, R] (plane-major) for R rows of feat [R,512].  ``max_ctas`` (streaming kernel only) leaves SMs free
@@ -127,6 +185,17 @@ def score_keys(feat: torch.Tensor, prompts: Prompts, normalize: bool = False,
     if out is None:
         out = torch.empty(num_key_planes(prompts.n_classes), r, device=feat.device, dtype=torch.float32)
     _count(1)
+    if isinstance(prompts, BankPrompts):
+        if wide:      # range-free: the collapsed matrix on the fp32 kernels (scoring is linear in the prompts)
+            return score_keys(feat, prompts.collapsed, normalize, out=out, max_ctas=max_ctas, wide=True)
+        if check_domain:
+            prompts.tc_flag.zero_()
+        check(_lib.load().moc_score_keys_bank_tc(feat.data_ptr(), r, prompts.image.data_ptr(), prompts.n_classes,
+                                                 prompts.n_prompts, prompts.n_bg, int(bool(normalize)), out.data_ptr(),
+                                                 out.stride(0), _stream()))
+        if check_domain and int(prompts.tc_flag.item()) != 0:
+            return score_keys(feat, prompts, normalize, out=out, max_ctas=max_ctas, wide=True)
+        return out
     if prompts.tc is not None and SCORE_IMPL != "simt" and not wide:
         if check_domain:
             prompts.tc_flag.zero_()
