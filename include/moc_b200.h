@@ -354,6 +354,14 @@ int moc_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
                   int64_t step, float lr, float beta1, float beta2, float eps, float weight_decay,
                   void* stream);
 
+/* The same update with the step count in DEVICE memory, for training steps captured into a CUDA graph (a graph
+ * replays fixed kernel arguments, so the bias corrections cannot be host scalars): moc_adam_prepare_dev adds 1 to
+ * *step (int64) and writes scalars[0] = lr / (1 - beta1^step), scalars[1] = sqrt(1 - beta2^step); moc_adam_apply_dev
+ * updates one parameter tensor with them.  One prepare, then one apply per tensor, per optimizer step. */
+int moc_adam_prepare_dev(int64_t* step, float* scalars, float lr, float beta1, float beta2, void* stream);
+int moc_adam_apply_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                       const float* scalars, float beta1, float beta2, float eps, float weight_decay, void* stream);
+
 /* dst[i] += src[i]: sums the gate gradients of the slides of one data-parallel micro-batch before the single
  * all-reduce + Adam step (north_star's "small all-reduce of meta-optimizer gradients"; the reference's loop,
  * main_moc.py:406-410, steps once per slide and has no such mode). */

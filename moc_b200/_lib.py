@@ -88,6 +88,8 @@ SIGNATURES = {
     "moc_h5_read": (i32, [p, C.c_char_p, p, sz]),
     "moc_adam_step": (i32, [p, p, p, p, i64, i64, f32, f32, f32, f32, f32, p]),
     "moc_accumulate": (i32, [p, p, i64, p]),
+    "moc_adam_prepare_dev": (i32, [p, p, f32, f32, f32, p]),
+    "moc_adam_apply_dev": (i32, [p, p, p, p, i64, p, f32, f32, f32, f32, p]),
 }
 
 _lock = threading.Lock()

@@ -627,6 +627,34 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     p[i] = pi - step_size * __fdiv_rn(mi, denom);
 }
 
+// Adam with the step counter in device memory, so that a captured CUDA graph of a training step can be replayed:
+// the prepare kernel advances the counter and derives the two bias-correction scalars (same double-precision
+// arithmetic as moc_adam_step does on the host), the apply kernel is adam_kernel reading them from memory.
+__global__ void adam_prepare_dev_kernel(int64_t* __restrict__ step, float* __restrict__ scalars, float lr, float beta1,
+                                        float beta2) {
+    const int64_t t = *step + 1;
+    *step = t;
+    const double bc1 = 1.0 - pow((double)beta1, (double)t);
+    const double bc2 = 1.0 - pow((double)beta2, (double)t);
+    scalars[0] = (float)((double)lr / bc1);
+    scalars[1] = (float)sqrt(bc2);
+}
+__global__ void adam_apply_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                      float* __restrict__ v, int64_t n, const float* __restrict__ scalars, float beta1,
+                                      float beta2, float eps, float wd) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float step_size = scalars[0], bc2_sqrt = scalars[1];
+    const float pi = p[i];
+    const float gi = __fmaf_rn(wd, pi, g[i]);
+    const float mi = __fmaf_rn(1.f - beta1, gi - m[i], m[i]);
+    const float vi = __fmaf_rn(__fmul_rn(gi, gi), 1.f - beta2, __fmul_rn(v[i], beta2));
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = __fadd_rn(__fdiv_rn(sqrtf(vi), bc2_sqrt), eps);
+    p[i] = pi - step_size * __fdiv_rn(mi, denom);
+}
+
 // dst += src (gradient accumulation over the slides of a data-parallel micro-batch)
 __global__ void accumulate_kernel(float* __restrict__ dst, const float* __restrict__ src, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -636,6 +664,24 @@ __global__ void accumulate_kernel(float* __restrict__ dst, const float* __restri
 }  // namespace moc
 
 using namespace moc;
+
+extern "C" int moc_adam_prepare_dev(int64_t* step, float* scalars, float lr, float beta1, float beta2, void* stream) {
+    MOC_CHECK_ARG(step && scalars, "moc_adam_prepare_dev: null pointer");
+    adam_prepare_dev_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step, scalars, lr, beta1, beta2);
+    MOC_LAUNCH_CHECK("adam_prepare_dev_kernel");
+    return MOC_OK;
+}
+
+extern "C" int moc_adam_apply_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                                  const float* scalars, float beta1, float beta2, float eps, float weight_decay,
+                                  void* stream) {
+    MOC_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && scalars && n >= 0, "moc_adam_apply_dev: bad arguments");
+    if (n == 0) return MOC_OK;
+    adam_apply_dev_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        params, grads, exp_avg, exp_avg_sq, n, scalars, beta1, beta2, eps, weight_decay);
+    MOC_LAUNCH_CHECK("adam_apply_dev_kernel");
+    return MOC_OK;
+}
 
 extern "C" int moc_accumulate(float* dst, const float* src, int64_t n, void* stream) {
     MOC_CHECK_ARG(dst && src && n >= 0, "moc_accumulate: bad arguments");

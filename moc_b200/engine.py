@@ -39,6 +39,65 @@ class StepOut:
     n_selected: torch.Tensor  # int32 [1] device
 
 
+class _TrainGraph:
+    """A captured training step of one slide: static input (mask), static outputs, and what keeps them alive."""
+    graph = mask_pinned = mask_dev = grads = head_ws = out = copied = None
+
+
+class AdamDev:
+    """torch.optim.Adam's state for the graph-captured training step: the optimizer's own exp_avg / exp_avg_sq tensors,
+    its hyper-parameters, and the step count mirrored in device memory (ops.adam_prepare_dev advances it inside the
+    graph).  ``count_host_step`` keeps the optimizer's host-side ``state['step']`` in line, so ``state_dict()`` and a
+    later eager ``optimizer.step()`` see the right count."""
+
+    def __init__(self, optimizer, params: List[torch.Tensor]):
+        self.optimizer, self.params = optimizer, params
+        group_of = {id(p): g for g in optimizer.param_groups for p in g["params"]}
+        self.groups = [group_of[id(p)] for p in params]
+        steps = set()
+        for p in params:
+            st = optimizer.state[p]
+            if len(st) == 0:
+                st["step"] = torch.tensor(0.0, dtype=torch.float32)
+                st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            steps.add(int(st["step"]))
+        if len(steps) != 1:
+            raise _lib.MocError(_lib.E_ARG, "the gate parameters have been stepped a different number of times")
+        g0 = self.groups[0]
+        if any((g["lr"], g["betas"]) != (g0["lr"], g0["betas"]) for g in self.groups):
+            raise _lib.MocError(_lib.E_ARG, "graph-captured Adam needs one lr / betas for all gate parameters")
+        dev = params[0].device
+        self.step_dev = torch.tensor([steps.pop()], dtype=torch.int64, device=dev)
+        self.scalars = torch.zeros(2, dtype=torch.float32, device=dev)
+
+    def key(self):
+        return (id(self.optimizer), self.step_dev.data_ptr()) + tuple(
+            (g["lr"], g["betas"], g["eps"], g["weight_decay"]) for g in self.groups)
+
+    def host_step(self) -> int:
+        return int(self.optimizer.state[self.params[0]]["step"])
+
+    def in_sync(self) -> bool:
+        """False once someone else stepped the optimizer (the device counter no longer matches)."""
+        return all(len(self.optimizer.state[p]) and int(self.optimizer.state[p]["step"]) == self._expected
+                   for p in self.params) if hasattr(self, "_expected") else True
+
+    def count_host_step(self) -> None:
+        for p in self.params:
+            self.optimizer.state[p]["step"] += 1
+        self._expected = self.host_step()
+
+    def apply(self, grad_views) -> None:
+        """prepare + one apply per tensor, on the current stream (captured into the step's graph)."""
+        g0 = self.groups[0]
+        ops.adam_prepare_dev(self.step_dev, self.scalars, g0["lr"], g0["betas"][0], g0["betas"][1])
+        for p, gv, grp in zip(self.params, grad_views, self.groups):
+            st = self.optimizer.state[p]
+            ops.adam_apply_dev(p.data, gv, st["exp_avg"], st["exp_avg_sq"], self.scalars, grp["betas"][0],
+                               grp["betas"][1], grp["eps"], grp["weight_decay"])
+
+
 class MocEngine:
     def __init__(self, zeroshot_weights: torch.Tensor, zeroshot_weights_ext: torch.Tensor, topj: int = 10,
                  topk: int = 10, discard_classifiers: Sequence[str] = (), normalize: bool = False,
@@ -79,6 +138,7 @@ class MocEngine:
         # tensor-core scoring of wide prompt sets): found by a flag-checked pass, they are served by the range-free
         # kernels from then on (3xTF32 gate, fp32 CUDA-core scoring) - the reference is finite for any finite feature
         self._wide_stores: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
+        self._graphs: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()   # store -> captured training steps
 
     # ---- scoring -------------------------------------------------------------------------------
     def keys_for(self, store: RaggedBagStore, lo: int = 0, hi: Optional[int] = None, wide: bool = False) -> torch.Tensor:
@@ -281,7 +341,7 @@ class MocEngine:
 
     # ---- training ------------------------------------------------------------------------------
     def train_step(self, store: RaggedBagStore, slide: int, label_dev: torch.Tensor, params: ops.HeadParams,
-                   row_mask: Optional[torch.Tensor], grads_out: torch.Tensor) -> StepOut:
+                   row_mask: Optional[torch.Tensor], grads_out: torch.Tensor, head_ws=None) -> StepOut:
         """Forward + CE + backward of one (masked) slide; fills ``grads_out`` (flat, 33 092 floats)."""
         c = self.n_classes
         wide = self.is_wide(store)      # decided once per store by ensure_domain(): a step has no sync to poll a flag at
@@ -290,10 +350,62 @@ class MocEngine:
         feat = store.bag(slide)
         sel = ops.select_union(keys, offs, offs_h, c, self.topj, _lib.discard_bits(self.discard), row_mask, base, base_h)
         act = _lib.active_bits(self.discard, "train")
-        ho = ops.head_forward(feat, keys, c, sel, params, act, self.topk, wide=wide)
+        ho = ops.head_forward(feat, keys, c, sel, params, act, self.topk, wide=wide, ws=head_ws)
         loss, dl, _ = ops.cross_entropy(ho.bag_logits, label_dev, want_grad=True)
         ops.head_backward(feat, keys, c, sel, params, act, self.topk, ho.pool_pos, dl, out=grads_out)
         return StepOut(loss, ho.bag_logits, sel.sel_count)
+
+    # ---- training step as a CUDA graph -------------------------------------------------------------
+    def train_step_graph(self, store: RaggedBagStore, slide: int, params: ops.HeadParams, adam: "AdamDev",
+                         row_mask_host: torch.Tensor) -> StepOut:
+        """One masked training step INCLUDING the Adam update, replayed from a CUDA graph.
+
+        The eager step is ~16 kernel launches, a dozen small allocations and a pageable mask copy: ~0.3 ms of host
+        time around ~0.1 ms of GPU work (main_moc.py:380-410 is one such step per few-shot slide, 25 epochs).  The
+        launch sequence of a slide depends only on its size, so it is captured once per (store, slide) - score,
+        select with the mask read from a device buffer, gate / combine / pool, CE, backward, Adam with its step counter
+        in device memory - and every later visit is one pinned H2D copy of the fresh half mask plus one graph launch.
+        Same kernels, same order, same arguments as :meth:`train_step` + ``ops.adam_step``: bit-identical results.
+        The returned tensors are the graph's static outputs: copy what must outlive the next replay."""
+        per_store = self._graphs.get(store)
+        if per_store is None:
+            per_store = self._graphs[store] = {}
+        key = (slide, params.w1.data_ptr(), params.b1.data_ptr(), params.w2.data_ptr(), params.b2.data_ptr(),
+               adam.key(), self.is_wide(store))
+        g = per_store.get(key)
+        if g is None:
+            g = per_store[key] = self._capture_train_step(store, slide, params, adam)
+        if g.copied is not None:
+            g.copied.synchronize()      # the host runs ahead of the GPU: the previous visit's mask must have left the pinned buffer
+        g.mask_pinned.copy_(row_mask_host.view(torch.uint8) if row_mask_host.dtype == torch.bool else row_mask_host)
+        g.mask_dev.copy_(g.mask_pinned, non_blocking=True)
+        if g.copied is None:
+            g.copied = torch.cuda.Event()
+        g.copied.record()
+        g.graph.replay()
+        adam.count_host_step()
+        return g.out
+
+    def _capture_train_step(self, store, slide, params, adam):
+        dev = store.device
+        n = store.n_rows(slide)
+        self._layout(store, slide, slide + 1)           # host-built layout tensors: not inside the capture
+        if self.cache_scores:
+            self.keys_for(store, slide, slide + 1, self.is_wide(store))
+        g = _TrainGraph()
+        g.mask_pinned = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+        g.mask_dev = torch.ones(n, dtype=torch.uint8, device=dev)
+        g.grads = torch.empty(ops.NUM_PARAMS, dtype=torch.float32, device=dev)
+        g.head_ws = ops.HeadWorkspace(dev)
+        label = store.labels[slide:slide + 1]
+        views = ops.split_grads(g.grads)
+        torch.cuda.current_stream().synchronize()
+        g.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g.graph):
+            out = self.train_step(store, slide, label, params, g.mask_dev, g.grads, head_ws=g.head_ws)
+            adam.apply(views)
+        g.out = out
+        return g
 
     # ---- host-resident bags (end-to-end path) ---------------------------------------------------
     def eval_logits_host(self, host: "HostBags", params: ops.HeadParams, out: Optional[torch.Tensor] = None

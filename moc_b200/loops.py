@@ -76,17 +76,34 @@ def _flat_params(model):
     return model.parameters_in_order() if hasattr(model, "parameters_in_order") else list(model.parameters())
 
 
-def _optimizer_step(model, optimizer, flat_grads: torch.Tensor) -> None:
-    """optimizer.step() on the flat gradient.  A plain torch.optim.Adam (what main_moc.py:316 builds) is
-    advanced by our Adam kernel directly on its own state tensors; anything else gets .grad and its own step()."""
-    params = _flat_params(model)
-    views = ops.split_grads(flat_grads)
-    plain_adam = (type(optimizer) is torch.optim.Adam and all(
+def _is_plain_adam(optimizer) -> bool:
+    """torch.optim.Adam exactly as main_moc.py:316 builds it (L2 weight decay in the gradient, no amsgrad / maximize /
+    capturable / fused / decoupled decay, python-float lr, no step hooks): what our Adam kernels implement."""
+    return (type(optimizer) is torch.optim.Adam and all(
         not g.get("amsgrad") and not g.get("maximize") and not g.get("capturable") and not g.get("fused")
         and not g.get("differentiable") and not g.get("decoupled_weight_decay")
         and not isinstance(g["lr"], torch.Tensor) for g in optimizer.param_groups)
         and not getattr(optimizer, "_optimizer_step_pre_hooks", None)
         and not getattr(optimizer, "_optimizer_step_post_hooks", None))
+
+
+def _adam_dev(model, optimizer):
+    """The optimizer's device-side mirror for graph-captured steps (one per optimizer, rebuilt if it was stepped
+    behind our back or its hyper-parameters changed)."""
+    from .engine import AdamDev
+    params = _flat_params(model)
+    ad = getattr(optimizer, "_moc_adam_dev", None)
+    if ad is None or not ad.in_sync() or [id(p) for p in ad.params] != [id(p) for p in params]:
+        ad = optimizer._moc_adam_dev = AdamDev(optimizer, params)
+    return ad
+
+
+def _optimizer_step(model, optimizer, flat_grads: torch.Tensor) -> None:
+    """optimizer.step() on the flat gradient.  A plain torch.optim.Adam (what main_moc.py:316 builds) is
+    advanced by our Adam kernel directly on its own state tensors; anything else gets .grad and its own step()."""
+    params = _flat_params(model)
+    views = ops.split_grads(flat_grads)
+    plain_adam = _is_plain_adam(optimizer)
     if not plain_adam:
         for p, g in zip(params, views):
             p.grad = g.clone()
@@ -130,11 +147,20 @@ def train(model, train_loader, optimizer, device, args, masks: Optional[Iterable
     n_steps = len(ds)
     if not g or int(g) <= 1:
         flat = torch.empty(ops.NUM_PARAMS, dtype=torch.float32, device=store.device)
+        # a plain Adam lets the whole step - forward, backward, update - replay from one CUDA graph per few-shot slide
+        use_graph = bool(getattr(args, "cuda_graph", True)) and _is_plain_adam(optimizer) and \
+            os.environ.get("MOC_TRAIN_GRAPH", "1") != "0"
+        adam = _adam_dev(model, optimizer) if use_graph else None
+        params = model.head_params()
         losses = []
         for k in range(n_steps):
             i = k % ds.real_len()
             n = store.n_rows(i)
             mask = next(masks) if masks is not None else (torch.rand(n) > 0.5)
+            if use_graph:
+                out = eng.train_step_graph(store, i, params, adam, mask)
+                losses.append(out.loss.clone())
+                continue
             out = eng.train_step(store, i, store.labels[i:i + 1], model.head_params(), mask.to(store.device), flat)
             _optimizer_step(model, optimizer, flat)
             losses.append(out.loss)

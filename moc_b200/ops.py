@@ -352,7 +352,8 @@ def head_workspace(device) -> HeadWorkspace:
 
 
 def head_forward(feat: torch.Tensor, keys: torch.Tensor, n_classes: int, sel: Selection, params: HeadParams,
-                 active_mask: int, topk: int, want_gate: bool = False, wide: bool = False) -> HeadOut:
+                 active_mask: int, topk: int, want_gate: bool = False, wide: bool = False,
+                 ws: Optional["HeadWorkspace"] = None) -> HeadOut:
     """Gate + combination + pooling of every selected row.  ``wide=True`` forces the range-free 3xTF32 gate kernel;
     otherwise ``HeadOut.domain_flag`` tells (after a sync) whether the FP16x3 kernel met a feature outside its range."""
     dev = feat.device
@@ -362,7 +363,8 @@ def head_forward(feat: torch.Tensor, keys: torch.Tensor, n_classes: int, sel: Se
     bag = torch.empty(sel.n_slides, n_classes, dtype=torch.float32, device=dev)
     pos = torch.empty(sel.n_slides, n_classes, topk, dtype=torch.int32, device=dev)
     lib = _lib.load()
-    ws = head_workspace(dev)
+    if ws is None:
+        ws = head_workspace(dev)
     mask = int(active_mask) | (_lib.HEAD_WIDE_DOMAIN if wide else 0)
     _count(3)
     check(lib.moc_head_forward(feat.data_ptr(), keys.data_ptr(), keys.stride(0), n_classes,
@@ -416,6 +418,19 @@ def adam_step(params: torch.Tensor, grads: torch.Tensor, exp_avg: torch.Tensor, 
     _count(1)
     check(_lib.load().moc_adam_step(params.data_ptr(), grads.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
                                     params.numel(), int(step), lr, beta1, beta2, eps, weight_decay, _stream()))
+
+
+def adam_prepare_dev(step_dev: torch.Tensor, scalars: torch.Tensor, lr: float, beta1: float, beta2: float) -> None:
+    """Advance the device step counter (int64 [1]) and derive the bias-correction scalars (float32 [2]) from it."""
+    _count(1)
+    check(_lib.load().moc_adam_prepare_dev(step_dev.data_ptr(), scalars.data_ptr(), lr, beta1, beta2, _stream()))
+
+
+def adam_apply_dev(params: torch.Tensor, grads: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor,
+                   scalars: torch.Tensor, beta1: float, beta2: float, eps: float, weight_decay: float) -> None:
+    _count(1)
+    check(_lib.load().moc_adam_apply_dev(params.data_ptr(), grads.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
+                                         params.numel(), scalars.data_ptr(), beta1, beta2, eps, weight_decay, _stream()))
 
 
 def accumulate_(dst: torch.Tensor, src: torch.Tensor) -> torch.Tensor:

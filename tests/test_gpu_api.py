@@ -301,3 +301,47 @@ def test_dp_microbatch_training_matches_oracle_variant(golden, g_size):
     one = O.SenetParams(*[T(g["sd0_" + n]).clone() for n in ("model_0_weight", "model_0_bias", "model_2_weight", "model_2_bias")])
     O.train_epoch(one, O.AdamState(), O.BagList(bags, labels, repeat_num=rep), w, we, c, j, k, (), masks)
     assert float((one.w2 - oprm.w2).abs().max()) > 1e-5
+
+
+def test_graph_captured_training_is_bit_identical_to_eager(golden):
+    """train() replays one CUDA graph per few-shot slide (forward + CE + backward + Adam with a device step counter);
+    the eager sequence of the same kernels must give bit-identical losses, parameters and optimizer state, also across
+    epochs, and the optimizer's host-side step count must follow."""
+    import copy
+    import moc_b200 as M
+    from moc_b200 import loops
+    g = golden("loop_c2")
+    c, j, k = int(g["C"]), int(g["J"]), int(g["K"])
+    loops.set_prompts(T(g["W"]).to(DEV), T(g["W_ext"]).to(DEV))
+    bags = [T(g["train_feat_%d" % i]).float() for i in range(int(g["n_train"]))]
+    rep = int(g["repeat_num"])
+    tr = M.BagLoader(M.BagDataset(M.RaggedBagStore.from_bags(bags, g["train_labels"].tolist(), DEV), repeat_num=rep))
+    masks = [T(g["mask_%d" % i]) for i in range(int(g["n_masks"]))]
+    model_g = M.senet(512, 4)
+    model_g.load_state_dict({kk[4:].replace("model_0_", "model.0.").replace("model_2_", "model.2."): T(v)
+                             for kk, v in g.items() if kk.startswith("sd0_")})
+    model_g.to(DEV)
+    model_e = copy.deepcopy(model_g)
+    opt_g = torch.optim.Adam(model_g.parameters(), lr=1e-3, weight_decay=1e-4)
+    opt_e = torch.optim.Adam(model_e.parameters(), lr=1e-3, weight_decay=1e-4)
+    a_g, a_e = _args(c, j, k), _args(c, j, k)
+    a_e.cuda_graph = False
+    for e in range(int(g["epochs"])):
+        mk = masks[e * rep:(e + 1) * rep]
+        lg = M.train(model_g, tr, opt_g, DEV, a_g, masks=mk)
+        le = M.train(model_e, tr, opt_e, DEV, a_e, masks=mk)
+        assert torch.equal(lg, le)
+        np.testing.assert_allclose(lg.cpu().numpy(), g["train_losses_e%d" % e], rtol=5e-5)
+        for pg, pe in zip(model_g.parameters(), model_e.parameters()):
+            assert torch.equal(pg, pe)
+            assert torch.equal(opt_g.state[pg]["exp_avg"], opt_e.state[pe]["exp_avg"])
+            assert torch.equal(opt_g.state[pg]["exp_avg_sq"], opt_e.state[pe]["exp_avg_sq"])
+            assert int(opt_g.state[pg]["step"]) == int(opt_e.state[pe]["step"]) == (e + 1) * rep
+    # an eager step in between (someone else stepping the optimizer) must not desynchronise the device counter
+    a_g.cuda_graph = False
+    M.train(model_g, tr, opt_g, DEV, a_g, masks=masks[:rep])
+    M.train(model_e, tr, opt_e, DEV, a_e, masks=masks[:rep])
+    a_g.cuda_graph = True
+    lg = M.train(model_g, tr, opt_g, DEV, a_g, masks=masks[:rep])
+    le = M.train(model_e, tr, opt_e, DEV, a_e, masks=masks[:rep])
+    assert torch.equal(lg, le) and all(torch.equal(pg, pe) for pg, pe in zip(model_g.parameters(), model_e.parameters()))

@@ -38,7 +38,11 @@ def main():
         model = M.senet(512, 4).to(dev)
         opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4)
         print("cache_scores =", cache)
-        t = timed("train epoch (32 steps)", lambda: M.train(model, tr, opt, dev, args))
+        args.cuda_graph = False
+        t = timed("train epoch (32 steps), eager", lambda: M.train(model, tr, opt, dev, args))
+        print("   -> %.3f ms per step" % (t * 1e3 / 32))
+        args.cuda_graph = True
+        t = timed("train epoch (32 steps), CUDA graph", lambda: M.train(model, tr, opt, dev, args))
         print("   -> %.3f ms per step" % (t * 1e3 / 32))
         timed("evaluation(train, 32 slides)", lambda: M.evaluation(model, tr, dev, args))
         timed("evaluation(val, 100 slides)", lambda: M.evaluation(model, va, dev, args))
