@@ -1,7 +1,7 @@
 // Host-to-device ceiling probe: bare cudaMemcpyAsync from pinned host memory on every visible GPU AT ONCE.
 //
 //   nvcc -O2 -std=c++17 -o tools/probe_h2d tools/probe_h2d.cu -lpthread
-//   tools/probe_h2d [MiB per copy = 1024] [copies = 8] [numa = 1]
+//   tools/probe_h2d [MiB per copy = 1024] [copies = 8] [numa = 1] [write_combined = 0]
 //
 // bench.py's `e2e` number is bound by these copies (55 GB/s per GPU alone; less per GPU when several copy at once on
 // this pool's boxes).  This program takes the framework out of the picture: one thread per GPU, one pinned buffer and
@@ -61,6 +61,7 @@ int main(int argc, char** argv) {
     const size_t mib = argc > 1 ? (size_t)atoll(argv[1]) : 1024;
     const int copies = argc > 2 ? atoi(argv[2]) : 8;
     const int numa = argc > 3 ? atoi(argv[3]) : 1;
+    const int wc = argc > 4 ? atoi(argv[4]) : 0;   // cudaHostAllocWriteCombined: not snooped during the DMA reads
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
         printf("{\"error\": \"no CUDA device\"}\n");
@@ -80,7 +81,7 @@ int main(int argc, char** argv) {
             void *h = nullptr, *g = nullptr;
             cudaStream_t st;
             cudaEvent_t e0, e1;
-            if (cudaHostAlloc(&h, bytes, cudaHostAllocDefault) != cudaSuccess || cudaMalloc(&g, bytes) != cudaSuccess) {
+            if (cudaHostAlloc(&h, bytes, wc ? cudaHostAllocWriteCombined : cudaHostAllocDefault) != cudaSuccess || cudaMalloc(&g, bytes) != cudaSuccess) {
                 ready++;
                 return;
             }
@@ -107,7 +108,7 @@ int main(int argc, char** argv) {
     go.store(true);
     for (auto& t : threads) t.join();
     double total = 0.0;
-    printf("{\"gpus\": %d, \"MiB_per_copy\": %zu, \"copies\": %d, \"numa_bind\": %d, \"per_gpu_GBps\": [", n, mib, copies, numa);
+    printf("{\"gpus\": %d, \"MiB_per_copy\": %zu, \"copies\": %d, \"numa_bind\": %d, \"write_combined\": %d, \"per_gpu_GBps\": [", n, mib, copies, numa, wc);
     for (int d = 0; d < n; ++d) {
         printf("%s%.2f", d ? ", " : "", gbps[d]);
         total += gbps[d];
