@@ -29,6 +29,7 @@
 //   warp 20     MMA issuer (one elected lane): 4 k-steps x 3 products of tcgen05.mma.kind::f16 M128 N64 K16
 // Three A stages of {a0 16K, a1 16K}; W1 image 8 x {b0 8K, b1 8K}; two TMEM accumulators.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -51,6 +52,7 @@ constexpr int HF_EPI_WARPS = 4, HF_PROD_WARPS = 16;  // 16 producer warps: 4 per
 constexpr int HF_WARP_MMA = HF_EPI_WARPS + HF_PROD_WARPS;  // 20
 constexpr int HF_THREADS = (HF_WARP_MMA + 1) * 32;         // 672
 constexpr int HF_TMEM_COLS = 128;
+constexpr int HF_DEFAULT_A_IN_TMEM = 0;   // 1 once head_rows_f16t_kernel is validated and faster on hardware
 constexpr size_t HF_SMEM = (size_t)HF_BIMG_BYTES + (size_t)HF_STAGES * HF_STAGE_BYTES + 1024;
 
 struct HeadF16Tail {   // after the W1 image in the workspace
@@ -409,6 +411,279 @@ head_rows_f16_kernel(const float* __restrict__ feat, const float* __restrict__ k
     }
 }
 
+// =====================================================================================================
+// Variant with the A operand in TENSOR MEMORY (MOC_HEAD_IMPL=f16t; the default once validated on hardware).
+//
+// What bounds head_rows_f16_kernel is memory-level parallelism, not request size: tools/probe_gather_kblock.cu gathers
+// the same sparse rows K-block by K-block at 4.5 TB/s with 64 KB of loads in flight per SM (what 16 producer warps x
+// two 64-byte register sets give: the kernel reaches 3.9) and at 6.5 TB/s with 128 KB.  The registers for deeper
+// prefetch went into the (row, 32-byte chunk) work split: 8 lanes shared one row piece so that their 16-byte stores
+// filled a swizzled shared-memory row.  With A read from tensor memory there is no shared-memory layout to serve: a
+// producer thread owns ONE ROW of the tile (its TMEM lane), loads 128 contiguous bytes of it per step (32 K-elements,
+// two steps in flight = 256 B per thread, 128 KB per SM), splits them into 16 + 16 packed half2 registers and writes
+// them with two tcgen05.st into the stage's a0 / a1 columns - no STS, no fence.proxy.async, and the MMA's A reads leave
+// the shared-memory port to the W1 image.  Twelve producer warps (544 threads in all, so that a thread may hold its
+// 2 x 32 loaded floats plus the 32 packed results: 120 registers) form 3 groups (warp / 4) of 4 lane quadrants
+// (warp % 4, as tcgen05.st requires); step s of the CTA's flat (tile, 32-wide K-slice) stream belongs to group s % 3
+// and to TMEM stage s % 3, so every group owns one stage and one full / empty barrier pair; 96 KB of loads in flight.
+constexpr int HT_KS = 32;                    // K elements per step (128 bytes of a row)
+constexpr int HT_NKS = D / HT_KS;            // 16 steps per tile
+constexpr int HT_GROUPS = 3;                 // producer groups = TMEM A stages
+constexpr int HT_PROD_WARPS = 4 * HT_GROUPS; // 12: three groups of four lane-quadrant warps (120 registers per thread)
+constexpr int HT_WARP_MMA = HF_EPI_WARPS + HT_PROD_WARPS;   // 16
+constexpr int HT_THREADS = (HT_WARP_MMA + 1) * 32;          // 544
+constexpr int HT_STAGE_COLS = 32;            // a0: 16 columns of packed half2, a1: 16 columns
+constexpr int HT_ACC_COL0 = 0;               // two accumulators of 64 columns
+constexpr int HT_A_COL0 = 128;               // three A stages of 32 columns
+constexpr int HT_TMEM_COLS = 256;
+constexpr size_t HT_SMEM = (size_t)HF_BIMG_BYTES + 1024;
+
+__device__ __forceinline__ void ht_umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(b_desc), "r"(HF_IDESC), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+        : "memory");
+}
+__device__ __forceinline__ void ht_tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void ht_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__global__ void __maxnreg__(120)
+head_rows_f16t_kernel(const float* __restrict__ feat, const float* __restrict__ keys, int64_t key_stride, int C,
+                      const int32_t* __restrict__ sel_rows, int64_t n_slots, const unsigned char* __restrict__ img,
+                      const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
+                      unsigned active_mask, float* __restrict__ gate, float* __restrict__ final_scores,
+                      int* __restrict__ domain_flag) {
+    extern __shared__ unsigned char ht_smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[HT_GROUPS], empty_bar[HT_GROUPS], tfull_bar[2], tempty_bar[2], b_bar;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float w2s[HF_G * HF_H], b1s[HF_H], b2s[HF_G];
+
+    unsigned char* bsm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(ht_smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (tid < HF_G * HF_H) w2s[tid] = w2[tid];
+    if (tid < HF_H) b1s[tid] = b1[tid];
+    if (tid < HF_G) b2s[tid] = b2[tid];
+    if (tid == 0) {
+        for (int s = 0; s < HT_GROUPS; ++s) {
+            mbar_init(&full_bar[s], 4);        // the group's four lane-quadrant warps
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tfull_bar[a], 1);
+            mbar_init(&tempty_bar[a], HF_EPI_WARPS);
+        }
+        mbar_init(&b_bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == HT_WARP_MMA) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                     "r"((uint32_t)HT_TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    hf_fence_before();
+    __syncthreads();
+    hf_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    const int64_t n_tiles = (n_slots + HF_M - 1) / HF_M;
+    const float descale = reinterpret_cast<const HeadF16Tail*>(img + HF_BIMG_BYTES)->descale;
+
+    if (warp >= HF_EPI_WARPS && warp < HT_WARP_MMA) {
+        // =============================== A producers: thread = row of the tile =====================
+        const int pw = warp - HF_EPI_WARPS;          // 0..11
+        const int quad = warp & 3;                   // TMEM lane quadrant this warp may access (warp id % 4)
+        const int grp = pw >> 2;                     // 0..2: owns steps s with s % 3 == grp, and TMEM stage grp
+        const int r = quad * 32 + lane;              // row of the tile = TMEM lane
+        const float sx = (float)(1 << HF_SX);
+        const uint32_t a_taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + HT_A_COL0 + grp * HT_STAGE_COLS;
+        // cursor over this group's steps of the flat stream (non-empty tiles of this CTA x 16 K-slices): every third one
+        int64_t ltile = blockIdx.x;
+        int lks = grp;
+        const float4* lsrc = nullptr;
+        auto seek = [&]() {   // make ltile the next tile with rows, fetch this thread's row pointer
+            while (ltile < n_tiles && !hf_tile_has_rows(sel_rows, ltile * HF_M, n_slots, lane)) ltile += gridDim.x;
+            if (ltile >= n_tiles) return;
+            const int64_t sl = ltile * HF_M + r;
+            int64_t row = -1;
+            if (sl < n_slots) row = sel_rows ? (int64_t)sel_rows[sl] : sl;
+            lsrc = row >= 0 ? reinterpret_cast<const float4*>(feat + row * D) : nullptr;
+        };
+        auto issue = [&](float4 (&b)[8]) -> bool {
+            if (ltile >= n_tiles) return false;
+            if (lsrc) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) b[i] = __ldg(lsrc + lks * (HT_KS / 4) + i);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) b[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            lks += HT_GROUPS;
+            if (lks >= HT_NKS) {          // 16 is not a multiple of 3: the group's phase shifts from tile to tile
+                lks -= HT_NKS;
+                ltile += gridDim.x;
+                seek();
+            }
+            return true;
+        };
+        float4 buf[2][8];
+        bool pending[2];
+        seek();
+        pending[0] = issue(buf[0]);
+        pending[1] = issue(buf[1]);
+        uint32_t parity = 0;
+        while (pending[0]) {
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                if (pending[s]) {
+                    uint32_t hi[16], lo[16];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        uint4 h, l;
+                        hf_split8(buf[s][2 * i], buf[s][2 * i + 1], sx, h, l);
+                        hi[4 * i] = h.x; hi[4 * i + 1] = h.y; hi[4 * i + 2] = h.z; hi[4 * i + 3] = h.w;
+                        lo[4 * i] = l.x; lo[4 * i + 1] = l.y; lo[4 * i + 2] = l.z; lo[4 * i + 3] = l.w;
+                    }
+                    pending[s] = issue(buf[s]);            // the registers are free again: next loads leave now
+                    mbar_wait(&empty_bar[grp], parity ^ 1u);   // the MMAs that read this stage have completed
+                    hf_fence_after();
+                    ht_tmem_st16(a_taddr, hi);
+                    ht_tmem_st16(a_taddr + 16, lo);
+                    ht_wait_st();
+                    hf_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&full_bar[grp]);
+                    parity ^= 1u;
+                }
+            }
+        }
+    } else if (warp == HT_WARP_MMA) {
+        // =============================== MMA issuer ================================================
+        if (lane == 0) {   // W1 image -> shared memory, once per CTA
+            const uint64_t policy = l2_policy_evict_last();
+            mbar_arrive_expect_tx(&b_bar, HF_BIMG_BYTES);
+            for (int kb = 0; kb < HF_NKB; ++kb)
+                bulk_g2s(bsm + (size_t)kb * 2 * HF_B_BYTES, img + (size_t)kb * 2 * HF_B_BYTES, 2 * HF_B_BYTES, &b_bar, policy);
+            mbar_wait(&b_bar, 0);
+        }
+        __syncwarp();
+        int acc = 0, st = 0;
+        uint32_t acc_parity = 0, parity = 0;      // all stages flip together every HT_GROUPS steps
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            if (!hf_tile_has_rows(sel_rows, tile * HF_M, n_slots, lane)) continue;
+            if (lane == 0) {
+                mbar_wait(&tempty_bar[acc], acc_parity ^ 1u);
+                hf_fence_after();
+            }
+            __syncwarp();
+            const uint32_t tmem_d = tmem_base + HT_ACC_COL0 + acc * HF_H;
+            for (int ks = 0; ks < HT_NKS; ++ks) {
+                if (lane == 0) {
+                    mbar_wait(&full_bar[st], parity);
+                    hf_fence_after();
+                    const uint32_t a0 = tmem_base + HT_A_COL0 + st * HT_STAGE_COLS, a1 = a0 + 16;
+                    const uint32_t b0 = smem_u32(bsm + (size_t)(ks >> 1) * 2 * HF_B_BYTES) + (uint32_t)(ks & 1) * 64u;
+                    const uint32_t bl = b0 + HF_B_BYTES;
+#pragma unroll
+                    for (int k16 = 0; k16 < HT_KS / 16; ++k16) {
+                        const uint64_t db0 = hf_desc_sw128(b0 + k16 * 32), db1 = hf_desc_sw128(bl + k16 * 32);
+                        ht_umma_ts(tmem_d, a0 + k16 * 8, db1, (ks | k16) != 0 ? 1u : 0u);
+                        ht_umma_ts(tmem_d, a1 + k16 * 8, db0, 1u);
+                        ht_umma_ts(tmem_d, a0 + k16 * 8, db0, 1u);
+                    }
+                    hf_commit(&empty_bar[st]);
+                    if (ks == HT_NKS - 1) hf_commit(&tfull_bar[acc]);
+                }
+                __syncwarp();
+                if (++st == HT_GROUPS) { st = 0; parity ^= 1u; }
+            }
+            if (++acc == 2) { acc = 0; acc_parity ^= 1u; }
+        }
+    } else {
+        // =============================== epilogue (warps 0-3): as in head_rows_f16_kernel ==========
+        const float a0 = (active_mask & MOC_CLS_TOPK) ? 1.f : 0.f;
+        const float a1 = (active_mask & MOC_CLS_DELTA_SOFTMAX) ? 1.f : 0.f;
+        const float a2 = (active_mask & MOC_CLS_DELTA_DIFF) ? 1.f : 0.f;
+        const float a3 = (active_mask & MOC_CLS_BOTTOMK) ? 1.f : 0.f;
+        int acc = 0;
+        uint32_t acc_parity = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int64_t slot0 = tile * HF_M;
+            if (!hf_tile_has_rows(sel_rows, slot0, n_slots, lane)) continue;
+            const int64_t slot = slot0 + warp * 32 + lane;
+            int64_t row = -1;
+            if (slot < n_slots) row = sel_rows ? (int64_t)sel_rows[slot] : slot;
+            mbar_wait(&tfull_bar[acc], acc_parity);
+            hf_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + HT_ACC_COL0 + acc * HF_H;
+            float z[HF_G] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                float d[32];
+                hf_tmem_ld32(taddr + half * 32, d);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int jj = half * 32 + j;
+                    const float h = relu_nan(fmaf(d[j], descale, b1s[jj]));
+#pragma unroll
+                    for (int m = 0; m < HF_G; ++m) z[m] = fmaf(h, w2s[m * HF_H + jj], z[m]);
+                }
+            }
+            hf_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (++acc == 2) { acc = 0; acc_parity ^= 1u; }
+            if (row < 0) continue;
+            if (domain_flag != nullptr && !(fabsf(z[0] + z[1] + z[2] + z[3]) <= 3.0e38f)) atomicOr(domain_flag, 1);
+            float g[HF_G];
+#pragma unroll
+            for (int m = 0; m < HF_G; ++m) g[m] = sigmoidf_exact(z[m] + b2s[m]);
+            if (gate != nullptr) *reinterpret_cast<float4*>(gate + slot * HF_G) = make_float4(g[0], g[1], g[2], g[3]);
+            if (final_scores == nullptr) continue;
+            const float* kp = keys + row;
+            const float dlt = kp[(int64_t)(2 * C) * key_stride];
+            const float bgm = kp[(int64_t)(2 * C + 2) * key_stride];
+            for (int c0 = 0; c0 < C; c0 += 4) {
+                float lt[4], ls[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int cc = c0 + u < C ? c0 + u : C - 1;
+                    lt[u] = kp[(int64_t)cc * key_stride];
+                    ls[u] = kp[(int64_t)(C + cc) * key_stride];
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (c0 + u < C) {
+                        float f = a0 * __fmul_rn(g[0], lt[u]);
+                        f = __fadd_rn(f, a1 * __fmul_rn(g[1], ls[u]));
+                        f = __fadd_rn(f, a2 * __fmul_rn(g[2], dlt));
+                        f = __fadd_rn(f, a3 * __fmul_rn(g[3], bgm));
+                        final_scores[slot * C + c0 + u] = f;
+                    }
+                }
+            }
+        }
+    }
+
+    hf_fence_before();
+    __syncthreads();
+    if (warp == HT_WARP_MMA) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)HT_TMEM_COLS)
+                     : "memory");
+    }
+}
+
 size_t head_f16_workspace_bytes() { return (size_t)HF_BIMG_BYTES + sizeof(HeadF16Tail); }
 
 int launch_head_rows_f16(const float* feat, const float* keys, int64_t key_stride, int C, const int32_t* sel_rows,
@@ -421,6 +696,18 @@ int launch_head_rows_f16(const float* feat, const float* keys, int64_t key_strid
     MOC_CUDA(cudaFuncSetAttribute(head_rows_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HF_SMEM));
     const int64_t n_tiles = (n_slots + HF_M - 1) / HF_M;
     const int grid = (int)(n_tiles < sm_count() ? n_tiles : sm_count());
+    static int a_in_tmem = -1;          // MOC_HEAD_A=tmem|smem picks where the split patch tile lives
+    if (a_in_tmem < 0) {
+        const char* e = getenv("MOC_HEAD_A");
+        a_in_tmem = (e && e[0] == 's') ? 0 : (e && e[0] == 't') ? 1 : HF_DEFAULT_A_IN_TMEM;
+    }
+    if (a_in_tmem) {
+        MOC_CUDA(cudaFuncSetAttribute(head_rows_f16t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HT_SMEM));
+        head_rows_f16t_kernel<<<grid, HT_THREADS, HT_SMEM, st>>>(feat, keys, key_stride, C, sel_rows, n_slots, img, b1, w2,
+                                                                b2, active_mask, gate, final_scores, domain_flag);
+        MOC_LAUNCH_CHECK("head_rows_f16t_kernel");
+        return MOC_OK;
+    }
     head_rows_f16_kernel<<<grid, HF_THREADS, HF_SMEM, st>>>(feat, keys, key_stride, C, sel_rows, n_slots, img, b1, w2, b2,
                                                            active_mask, gate, final_scores, domain_flag);
     MOC_LAUNCH_CHECK("head_rows_f16_kernel");
