@@ -423,7 +423,7 @@ head_rows_f16_kernel(const float* __restrict__ feat, const float* __restrict__ k
 // two steps in flight = 256 B per thread, 128 KB per SM), splits them into 16 + 16 packed half2 registers and writes
 // them with two tcgen05.st into the stage's a0 / a1 columns - no STS, no fence.proxy.async, and the MMA's A reads leave
 // the shared-memory port to the W1 image.  Twelve producer warps (544 threads in all, so that a thread may hold its
-// 2 x 32 loaded floats plus the 32 packed results: 120 registers) form 3 groups (warp / 4) of 4 lane quadrants
+// 2 x 32 loaded floats plus the 32 packed results: 112 registers) form 3 groups (warp / 4) of 4 lane quadrants
 // (warp % 4, as tcgen05.st requires); step s of the CTA's flat (tile, 32-wide K-slice) stream belongs to group s % 3
 // and to TMEM stage s % 3, so every group owns one stage and one full / empty barrier pair; 96 KB of loads in flight.
 constexpr int HT_KS = 32;                    // K elements per step (128 bytes of a row)
@@ -458,7 +458,7 @@ __device__ __forceinline__ void ht_tmem_st16(uint32_t taddr, const uint32_t (&r)
 }
 __device__ __forceinline__ void ht_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-__global__ void __maxnreg__(120)
+__global__ void __maxnreg__(112)
 head_rows_f16t_kernel(const float* __restrict__ feat, const float* __restrict__ keys, int64_t key_stride, int C,
                       const int32_t* __restrict__ sel_rows, int64_t n_slots, const unsigned char* __restrict__ img,
                       const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
