@@ -422,8 +422,8 @@ head_rows_f16_kernel(const float* __restrict__ feat, const float* __restrict__ k
 // producer thread owns ONE ROW of the tile (its TMEM lane), loads 128 contiguous bytes of it per step (32 K-elements,
 // two steps in flight = 256 B per thread, 128 KB per SM), splits them into 16 + 16 packed half2 registers and writes
 // them with two tcgen05.st into the stage's a0 / a1 columns - no STS, no fence.proxy.async, and the MMA's A reads leave
-// the shared-memory port to the W1 image.  Twelve producer warps (544 threads in all, so that a thread may hold its
-// 2 x 32 loaded floats plus the 32 packed results: 112 registers) form 3 groups (warp / 4) of 4 lane quadrants
+// the shared-memory port to the W1 image.  Twelve producer warps (17 warps: registers are allocated for 20, which leaves 96 per thread - two
+// sets of 32 loaded floats plus 16 packed results at a time) form 3 groups (warp / 4) of 4 lane quadrants
 // (warp % 4, as tcgen05.st requires); step s of the CTA's flat (tile, 32-wide K-slice) stream belongs to group s % 3
 // and to TMEM stage s % 3, so every group owns one stage and one full / empty barrier pair; 96 KB of loads in flight.
 constexpr int HT_KS = 32;                    // K elements per step (128 bytes of a row)
@@ -456,9 +456,14 @@ __device__ __forceinline__ void ht_tmem_st16(uint32_t taddr, const uint32_t (&r)
         "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
         : "memory");
 }
+__device__ __forceinline__ void ht_tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(taddr), "r"(r[0]),
+                 "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
 __device__ __forceinline__ void ht_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-__global__ void __maxnreg__(112)
+__global__ void __launch_bounds__(HT_THREADS, 1)
 head_rows_f16t_kernel(const float* __restrict__ feat, const float* __restrict__ keys, int64_t key_stride, int C,
                       const int32_t* __restrict__ sel_rows, int64_t n_slots, const unsigned char* __restrict__ img,
                       const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
@@ -547,19 +552,22 @@ head_rows_f16t_kernel(const float* __restrict__ feat, const float* __restrict__ 
 #pragma unroll
             for (int s = 0; s < 2; ++s) {
                 if (pending[s]) {
-                    uint32_t hi[16], lo[16];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        uint4 h, l;
-                        hf_split8(buf[s][2 * i], buf[s][2 * i + 1], sx, h, l);
-                        hi[4 * i] = h.x; hi[4 * i + 1] = h.y; hi[4 * i + 2] = h.z; hi[4 * i + 3] = h.w;
-                        lo[4 * i] = l.x; lo[4 * i + 1] = l.y; lo[4 * i + 2] = l.z; lo[4 * i + 3] = l.w;
-                    }
-                    pending[s] = issue(buf[s]);            // the registers are free again: next loads leave now
                     mbar_wait(&empty_bar[grp], parity ^ 1u);   // the MMAs that read this stage have completed
                     hf_fence_after();
-                    ht_tmem_st16(a_taddr, hi);
-                    ht_tmem_st16(a_taddr + 16, lo);
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {           // 16 K-elements at a time: 8 + 8 packed registers alive
+                        uint32_t hi[8], lo[8];
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            uint4 h, l;
+                            hf_split8(buf[s][4 * hh + 2 * i], buf[s][4 * hh + 2 * i + 1], sx, h, l);
+                            hi[4 * i] = h.x; hi[4 * i + 1] = h.y; hi[4 * i + 2] = h.z; hi[4 * i + 3] = h.w;
+                            lo[4 * i] = l.x; lo[4 * i + 1] = l.y; lo[4 * i + 2] = l.z; lo[4 * i + 3] = l.w;
+                        }
+                        ht_tmem_st8(a_taddr + hh * 8, hi);
+                        ht_tmem_st8(a_taddr + 16 + hh * 8, lo);
+                    }
+                    pending[s] = issue(buf[s]);            // the registers are free again: next loads leave now
                     ht_wait_st();
                     hf_fence_before();
                     __syncwarp();
