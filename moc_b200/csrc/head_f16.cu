@@ -461,6 +461,27 @@ __device__ __forceinline__ void ht_tmem_st8(uint32_t taddr, const uint32_t (&r)[
                  "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                  : "memory");
 }
+// 16 lanes x 16 packed columns: registers {4 rep + 2 sel + j} <-> (lane t/4 + 8 sel, column 8 rep + 2 (t%4) + j)
+__device__ __forceinline__ void ht_tmem_st_16x256b_x2(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.16x256b.x2.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(taddr), "r"(r[0]),
+                 "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+// 4 floats (scaled here) -> 2 packed half2 hi + 2 packed half2 lo
+__device__ __forceinline__ void hf_split4(const float4& u, float s, uint2& hi, uint2& lo) {
+    const float x[4] = {u.x * s, u.y * s, u.z * s, u.w * s};
+    uint32_t h[2], l[2];
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        const __half2 a = __floats2half2_rn(x[2 * p], x[2 * p + 1]);
+        const float2 f = __half22float2(a);
+        const __half2 b = __floats2half2_rn(x[2 * p] - f.x, x[2 * p + 1] - f.y);
+        h[p] = *reinterpret_cast<const uint32_t*>(&a);
+        l[p] = *reinterpret_cast<const uint32_t*>(&b);
+    }
+    hi = make_uint2(h[0], h[1]);
+    lo = make_uint2(l[0], l[1]);
+}
 __device__ __forceinline__ void ht_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 __global__ void __launch_bounds__(HT_THREADS, 1)
@@ -510,29 +531,39 @@ head_rows_f16t_kernel(const float* __restrict__ feat, const float* __restrict__ 
         const int pw = warp - HF_EPI_WARPS;          // 0..11
         const int quad = warp & 3;                   // TMEM lane quadrant this warp may access (warp id % 4)
         const int grp = pw >> 2;                     // 0..2: owns steps s with s % 3 == grp, and TMEM stage grp
-        const int r = quad * 32 + lane;              // row of the tile = TMEM lane
+        // tcgen05.st.16x256b fragment: thread t holds, for the 16-lane half hh of the quadrant, rows 16 hh + t/4 and
+        // + 8, and of each row the packed columns 8 rep + 2 (t % 4) + {0, 1} = K elements 16 rep + 4 (t % 4) .. + 3 =
+        // float4 number 4 rep + t % 4 of the row's 32-element slice.  So the four threads of a row read 64 contiguous
+        // bytes per load instruction and a warp-wide load touches 8 rows (not 32: the one-row-per-thread version
+        // spent 77 % of the L1's tag throughput fetching every sector twice).
+        const int rq = lane >> 2, cq = lane & 3;
         const float sx = (float)(1 << HF_SX);
         const uint32_t a_taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + HT_A_COL0 + grp * HT_STAGE_COLS;
         // cursor over this group's steps of the flat stream (non-empty tiles of this CTA x 16 K-slices): every third one
         int64_t ltile = blockIdx.x;
         int lks = grp;
-        const float4* lsrc = nullptr;
-        auto seek = [&]() {   // make ltile the next tile with rows, fetch this thread's row pointer
+        const float4* lsrc[4];                       // rows (hh, sel): 16 hh + rq + 8 sel of the quadrant
+        auto seek = [&]() {   // make ltile the next tile with rows, fetch this thread's four row pointers
             while (ltile < n_tiles && !hf_tile_has_rows(sel_rows, ltile * HF_M, n_slots, lane)) ltile += gridDim.x;
             if (ltile >= n_tiles) return;
-            const int64_t sl = ltile * HF_M + r;
-            int64_t row = -1;
-            if (sl < n_slots) row = sel_rows ? (int64_t)sel_rows[sl] : sl;
-            lsrc = row >= 0 ? reinterpret_cast<const float4*>(feat + row * D) : nullptr;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int64_t sl = ltile * HF_M + quad * 32 + (i >> 1) * 16 + rq + (i & 1) * 8;
+                int64_t row = -1;
+                if (sl < n_slots) row = sel_rows ? (int64_t)sel_rows[sl] : sl;
+                lsrc[i] = row >= 0 ? reinterpret_cast<const float4*>(feat + row * D) + cq : nullptr;
+            }
         };
-        auto issue = [&](float4 (&b)[8]) -> bool {
+        auto issue = [&](float4 (&b)[8]) -> bool {   // b[2 i + rep] = float4 4 rep + cq of row i's slice
             if (ltile >= n_tiles) return false;
-            if (lsrc) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) b[i] = __ldg(lsrc + lks * (HT_KS / 4) + i);
-            } else {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) b[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = 0; i < 4; ++i) {
+                if (lsrc[i]) {
+                    b[2 * i] = __ldg(lsrc[i] + lks * (HT_KS / 4));
+                    b[2 * i + 1] = __ldg(lsrc[i] + lks * (HT_KS / 4) + 4);
+                } else {
+                    b[2 * i] = b[2 * i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
             }
             lks += HT_GROUPS;
             if (lks >= HT_NKS) {          // 16 is not a multiple of 3: the group's phase shifts from tile to tile
@@ -555,17 +586,21 @@ head_rows_f16t_kernel(const float* __restrict__ feat, const float* __restrict__ 
                     mbar_wait(&empty_bar[grp], parity ^ 1u);   // the MMAs that read this stage have completed
                     hf_fence_after();
 #pragma unroll
-                    for (int hh = 0; hh < 2; ++hh) {           // 16 K-elements at a time: 8 + 8 packed registers alive
+                    for (int hh = 0; hh < 2; ++hh) {           // one 16-lane half of the quadrant at a time
+                        // registers {4 rep + 2 sel + j}: repetition rep (8 columns), row rq + 8 sel, column 2 cq + j
                         uint32_t hi[8], lo[8];
 #pragma unroll
-                        for (int i = 0; i < 2; ++i) {
-                            uint4 h, l;
-                            hf_split8(buf[s][4 * hh + 2 * i], buf[s][4 * hh + 2 * i + 1], sx, h, l);
-                            hi[4 * i] = h.x; hi[4 * i + 1] = h.y; hi[4 * i + 2] = h.z; hi[4 * i + 3] = h.w;
-                            lo[4 * i] = l.x; lo[4 * i + 1] = l.y; lo[4 * i + 2] = l.z; lo[4 * i + 3] = l.w;
-                        }
-                        ht_tmem_st8(a_taddr + hh * 8, hi);
-                        ht_tmem_st8(a_taddr + 16 + hh * 8, lo);
+                        for (int sel = 0; sel < 2; ++sel)
+#pragma unroll
+                            for (int rep = 0; rep < 2; ++rep) {
+                                uint2 h, l;
+                                hf_split4(buf[s][2 * (2 * hh + sel) + rep], sx, h, l);
+                                hi[4 * rep + 2 * sel] = h.x; hi[4 * rep + 2 * sel + 1] = h.y;
+                                lo[4 * rep + 2 * sel] = l.x; lo[4 * rep + 2 * sel + 1] = l.y;
+                            }
+                        const uint32_t t = a_taddr + ((uint32_t)(hh * 16) << 16);
+                        ht_tmem_st_16x256b_x2(t, hi);
+                        ht_tmem_st_16x256b_x2(t + 16, lo);
                     }
                     pending[s] = issue(buf[s]);            // the registers are free again: next loads leave now
                     ht_wait_st();
