@@ -428,13 +428,15 @@ head_rows_f16_kernel(const float* __restrict__ feat, const float* __restrict__ k
 // and to TMEM stage s % 3, so every group owns one stage and one full / empty barrier pair; 96 KB of loads in flight.
 constexpr int HT_KS = 32;                    // K elements per step (128 bytes of a row)
 constexpr int HT_NKS = D / HT_KS;            // 16 steps per tile
-constexpr int HT_GROUPS = 3;                 // producer groups = TMEM A stages
-constexpr int HT_PROD_WARPS = 4 * HT_GROUPS; // 12: three groups of four lane-quadrant warps (120 registers per thread)
-constexpr int HT_WARP_MMA = HF_EPI_WARPS + HT_PROD_WARPS;   // 16
-constexpr int HT_THREADS = (HT_WARP_MMA + 1) * 32;          // 544
+constexpr int HT_GROUPS = 2;                 // producer groups of four lane-quadrant warps
+constexpr int HT_STAGES = 4;                 // TMEM A stages: step s -> group s % 2, stage s % 4 (two stages per group)
+constexpr int HT_SETS = 3;                   // 128-byte register sets of loads in flight per producer thread
+constexpr int HT_PROD_WARPS = 4 * HT_GROUPS; // 8
+constexpr int HT_WARP_MMA = HF_EPI_WARPS + HT_PROD_WARPS;   // 12
+constexpr int HT_THREADS = (HT_WARP_MMA + 1) * 32;          // 416: 13 warps, registers allocated for 16 -> 128 per thread
 constexpr int HT_STAGE_COLS = 32;            // a0: 16 columns of packed half2, a1: 16 columns
 constexpr int HT_ACC_COL0 = 0;               // two accumulators of 64 columns
-constexpr int HT_A_COL0 = 128;               // three A stages of 32 columns
+constexpr int HT_A_COL0 = 128;               // four A stages of 32 columns
 constexpr int HT_TMEM_COLS = 256;
 constexpr size_t HT_SMEM = (size_t)HF_BIMG_BYTES + 1024;
 
@@ -482,6 +484,13 @@ __device__ __forceinline__ void hf_split4(const float4& u, float s, uint2& hi, u
     hi = make_uint2(h[0], h[1]);
     lo = make_uint2(l[0], l[1]);
 }
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
 __device__ __forceinline__ void ht_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 __global__ void __launch_bounds__(HT_THREADS, 1)
@@ -491,7 +500,7 @@ head_rows_f16t_kernel(const float* __restrict__ feat, const float* __restrict__ 
                       unsigned active_mask, float* __restrict__ gate, float* __restrict__ final_scores,
                       int* __restrict__ domain_flag) {
     extern __shared__ unsigned char ht_smem_raw[];
-    __shared__ __align__(8) uint64_t full_bar[HT_GROUPS], empty_bar[HT_GROUPS], tfull_bar[2], tempty_bar[2], b_bar;
+    __shared__ __align__(8) uint64_t full_bar[HT_STAGES], empty_bar[HT_STAGES], tfull_bar[2], tempty_bar[2], b_bar;
     __shared__ uint32_t tmem_base_s;
     __shared__ float w2s[HF_G * HF_H], b1s[HF_H], b2s[HF_G];
 
@@ -502,7 +511,7 @@ head_rows_f16t_kernel(const float* __restrict__ feat, const float* __restrict__ 
     if (tid < HF_H) b1s[tid] = b1[tid];
     if (tid < HF_G) b2s[tid] = b2[tid];
     if (tid == 0) {
-        for (int s = 0; s < HT_GROUPS; ++s) {
+        for (int s = 0; s < HT_STAGES; ++s) {
             mbar_init(&full_bar[s], 4);        // the group's four lane-quadrant warps
             mbar_init(&empty_bar[s], 1);
         }
@@ -528,9 +537,9 @@ head_rows_f16t_kernel(const float* __restrict__ feat, const float* __restrict__ 
 
     if (warp >= HF_EPI_WARPS && warp < HT_WARP_MMA) {
         // =============================== A producers: thread = row of the tile =====================
-        const int pw = warp - HF_EPI_WARPS;          // 0..11
+        const int pw = warp - HF_EPI_WARPS;          // 0..7
         const int quad = warp & 3;                   // TMEM lane quadrant this warp may access (warp id % 4)
-        const int grp = pw >> 2;                     // 0..2: owns steps s with s % 3 == grp, and TMEM stage grp
+        const int grp = pw >> 2;                     // 0..1: owns steps s with s % 2 == grp, TMEM stages grp and grp + 2
         // tcgen05.st.16x256b fragment: thread t holds, for the 16-lane half hh of the quadrant, rows 16 hh + t/4 and
         // + 8, and of each row the packed columns 8 rep + 2 (t % 4) + {0, 1} = K elements 16 rep + 4 (t % 4) .. + 3 =
         // float4 number 4 rep + t % 4 of the row's 32-element slice.  So the four threads of a row read 64 contiguous
@@ -539,51 +548,53 @@ head_rows_f16t_kernel(const float* __restrict__ feat, const float* __restrict__ 
         const int rq = lane >> 2, cq = lane & 3;
         const float sx = (float)(1 << HF_SX);
         const uint32_t a_taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + HT_A_COL0 + grp * HT_STAGE_COLS;
-        // cursor over this group's steps of the flat stream (non-empty tiles of this CTA x 16 K-slices): every third one
+        // cursor over this group's steps of the flat stream (non-empty tiles of this CTA x 16 K-slices): every second one
         int64_t ltile = blockIdx.x;
         int lks = grp;
-        const float4* lsrc[4];                       // rows (hh, sel): 16 hh + rq + 8 sel of the quadrant
-        auto seek = [&]() {   // make ltile the next tile with rows, fetch this thread's four row pointers
+        int32_t lrow[4];                             // feature rows (hh, sel): tile rows 16 hh + rq + 8 sel of the quadrant; -1 = padding
+        const float4* fbase = reinterpret_cast<const float4*>(feat) + cq;
+        auto seek = [&]() {   // make ltile the next tile with rows, fetch this thread's four row numbers
             while (ltile < n_tiles && !hf_tile_has_rows(sel_rows, ltile * HF_M, n_slots, lane)) ltile += gridDim.x;
             if (ltile >= n_tiles) return;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int64_t sl = ltile * HF_M + quad * 32 + (i >> 1) * 16 + rq + (i & 1) * 8;
-                int64_t row = -1;
-                if (sl < n_slots) row = sel_rows ? (int64_t)sel_rows[sl] : sl;
-                lsrc[i] = row >= 0 ? reinterpret_cast<const float4*>(feat + row * D) + cq : nullptr;
+                lrow[i] = sl < n_slots ? (sel_rows ? sel_rows[sl] : (int32_t)sl) : -1;
             }
         };
         auto issue = [&](float4 (&b)[8]) -> bool {   // b[2 i + rep] = float4 4 rep + cq of row i's slice
             if (ltile >= n_tiles) return false;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                if (lsrc[i]) {
-                    b[2 * i] = __ldg(lsrc[i] + lks * (HT_KS / 4));
-                    b[2 * i + 1] = __ldg(lsrc[i] + lks * (HT_KS / 4) + 4);
+                if (lrow[i] >= 0) {   // streamed once: keep the rows out of the L1 (it holds this kernel's few spills)
+                    const float4* p = fbase + (int64_t)lrow[i] * (D / 4) + lks * (HT_KS / 4);
+                    b[2 * i] = ldg_stream(p);
+                    b[2 * i + 1] = ldg_stream(p + 4);
                 } else {
                     b[2 * i] = b[2 * i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             }
             lks += HT_GROUPS;
-            if (lks >= HT_NKS) {          // 16 is not a multiple of 3: the group's phase shifts from tile to tile
+            if (lks >= HT_NKS) {
                 lks -= HT_NKS;
                 ltile += gridDim.x;
                 seek();
             }
             return true;
         };
-        float4 buf[2][8];
-        bool pending[2];
+        float4 buf[HT_SETS][8];
+        bool pending[HT_SETS];
         seek();
-        pending[0] = issue(buf[0]);
-        pending[1] = issue(buf[1]);
+#pragma unroll
+        for (int s = 0; s < HT_SETS; ++s) pending[s] = issue(buf[s]);
         uint32_t parity = 0;
+        int half = 0;                                // which of the group's two stages the next step fills
         while (pending[0]) {
 #pragma unroll
-            for (int s = 0; s < 2; ++s) {
+            for (int s = 0; s < HT_SETS; ++s) {
                 if (pending[s]) {
-                    mbar_wait(&empty_bar[grp], parity ^ 1u);   // the MMAs that read this stage have completed
+                    const int stage = grp + 2 * half;
+                    mbar_wait(&empty_bar[stage], parity ^ 1u);   // the MMAs that read this stage have completed
                     hf_fence_after();
 #pragma unroll
                     for (int hh = 0; hh < 2; ++hh) {           // one 16-lane half of the quadrant at a time
@@ -598,7 +609,7 @@ head_rows_f16t_kernel(const float* __restrict__ feat, const float* __restrict__ 
                                 hi[4 * rep + 2 * sel] = h.x; hi[4 * rep + 2 * sel + 1] = h.y;
                                 lo[4 * rep + 2 * sel] = l.x; lo[4 * rep + 2 * sel + 1] = l.y;
                             }
-                        const uint32_t t = a_taddr + ((uint32_t)(hh * 16) << 16);
+                        const uint32_t t = a_taddr + ((uint32_t)(hh * 16) << 16) + half * 2 * HT_STAGE_COLS;
                         ht_tmem_st_16x256b_x2(t, hi);
                         ht_tmem_st_16x256b_x2(t + 16, lo);
                     }
@@ -606,8 +617,9 @@ head_rows_f16t_kernel(const float* __restrict__ feat, const float* __restrict__ 
                     ht_wait_st();
                     hf_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&full_bar[grp]);
-                    parity ^= 1u;
+                    if (lane == 0) mbar_arrive(&full_bar[stage]);
+                    half ^= 1;
+                    if (half == 0) parity ^= 1u;       // both of the group's stages have been used once more
                 }
             }
         }
@@ -622,7 +634,7 @@ head_rows_f16t_kernel(const float* __restrict__ feat, const float* __restrict__ 
         }
         __syncwarp();
         int acc = 0, st = 0;
-        uint32_t acc_parity = 0, parity = 0;      // all stages flip together every HT_GROUPS steps
+        uint32_t acc_parity = 0, parity = 0;      // all stages flip together every HT_STAGES steps
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             if (!hf_tile_has_rows(sel_rows, tile * HF_M, n_slots, lane)) continue;
             if (lane == 0) {
@@ -649,7 +661,7 @@ head_rows_f16t_kernel(const float* __restrict__ feat, const float* __restrict__ 
                     if (ks == HT_NKS - 1) hf_commit(&tfull_bar[acc]);
                 }
                 __syncwarp();
-                if (++st == HT_GROUPS) { st = 0; parity ^= 1u; }
+                if (++st == HT_STAGES) { st = 0; parity ^= 1u; }
             }
             if (++acc == 2) { acc = 0; acc_parity ^= 1u; }
         }
