@@ -428,16 +428,16 @@ head_rows_f16_kernel(const float* __restrict__ feat, const float* __restrict__ k
 // and to TMEM stage s % 3, so every group owns one stage and one full / empty barrier pair; 96 KB of loads in flight.
 constexpr int HT_KS = 32;                    // K elements per step (128 bytes of a row)
 constexpr int HT_NKS = D / HT_KS;            // 16 steps per tile
-constexpr int HT_GROUPS = 2;                 // producer groups of four lane-quadrant warps
-constexpr int HT_STAGES = 4;                 // TMEM A stages: step s -> group s % 2, stage s % 4 (two stages per group)
-constexpr int HT_SETS = 3;                   // 128-byte register sets of loads in flight per producer thread
-constexpr int HT_PROD_WARPS = 4 * HT_GROUPS; // 8
-constexpr int HT_WARP_MMA = HF_EPI_WARPS + HT_PROD_WARPS;   // 12
-constexpr int HT_THREADS = (HT_WARP_MMA + 1) * 32;          // 416: 13 warps, registers allocated for 16 -> 128 per thread
+constexpr int HT_GROUPS = 3;                 // producer groups of four lane-quadrant warps
+constexpr int HT_STAGES = 2 * HT_GROUPS;     // TMEM A stages: step s -> group s % 3, stage s % 6 (two stages per group)
+constexpr int HT_SETS = 2;                   // 128-byte register sets of loads in flight per producer thread
+constexpr int HT_PROD_WARPS = 4 * HT_GROUPS; // 12
+constexpr int HT_WARP_MMA = HF_EPI_WARPS + HT_PROD_WARPS;   // 16
+constexpr int HT_THREADS = (HT_WARP_MMA + 1) * 32;          // 544: 17 warps, registers allocated for 20 -> 96 per thread
 constexpr int HT_STAGE_COLS = 32;            // a0: 16 columns of packed half2, a1: 16 columns
 constexpr int HT_ACC_COL0 = 0;               // two accumulators of 64 columns
 constexpr int HT_A_COL0 = 128;               // four A stages of 32 columns
-constexpr int HT_TMEM_COLS = 256;
+constexpr int HT_TMEM_COLS = 512;
 constexpr size_t HT_SMEM = (size_t)HF_BIMG_BYTES + 1024;
 
 __device__ __forceinline__ void ht_umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc, uint32_t accumulate) {
@@ -537,9 +537,9 @@ head_rows_f16t_kernel(const float* __restrict__ feat, const float* __restrict__ 
 
     if (warp >= HF_EPI_WARPS && warp < HT_WARP_MMA) {
         // =============================== A producers: thread = row of the tile =====================
-        const int pw = warp - HF_EPI_WARPS;          // 0..7
+        const int pw = warp - HF_EPI_WARPS;          // 0..11
         const int quad = warp & 3;                   // TMEM lane quadrant this warp may access (warp id % 4)
-        const int grp = pw >> 2;                     // 0..1: owns steps s with s % 2 == grp, TMEM stages grp and grp + 2
+        const int grp = pw >> 2;                     // owns steps s with s % HT_GROUPS == grp, TMEM stages grp and grp + HT_GROUPS
         // tcgen05.st.16x256b fragment: thread t holds, for the 16-lane half hh of the quadrant, rows 16 hh + t/4 and
         // + 8, and of each row the packed columns 8 rep + 2 (t % 4) + {0, 1} = K elements 16 rep + 4 (t % 4) .. + 3 =
         // float4 number 4 rep + t % 4 of the row's 32-element slice.  So the four threads of a row read 64 contiguous
@@ -548,7 +548,7 @@ head_rows_f16t_kernel(const float* __restrict__ feat, const float* __restrict__ 
         const int rq = lane >> 2, cq = lane & 3;
         const float sx = (float)(1 << HF_SX);
         const uint32_t a_taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + HT_A_COL0 + grp * HT_STAGE_COLS;
-        // cursor over this group's steps of the flat stream (non-empty tiles of this CTA x 16 K-slices): every second one
+        // cursor over this group's steps of the flat stream (non-empty tiles of this CTA x 16 K-slices): every HT_GROUPS-th one
         int64_t ltile = blockIdx.x;
         int lks = grp;
         int32_t lrow[4];                             // feature rows (hh, sel): tile rows 16 hh + rq + 8 sel of the quadrant; -1 = padding
@@ -593,7 +593,7 @@ head_rows_f16t_kernel(const float* __restrict__ feat, const float* __restrict__ 
 #pragma unroll
             for (int s = 0; s < HT_SETS; ++s) {
                 if (pending[s]) {
-                    const int stage = grp + 2 * half;
+                    const int stage = grp + HT_GROUPS * half;
                     mbar_wait(&empty_bar[stage], parity ^ 1u);   // the MMAs that read this stage have completed
                     hf_fence_after();
 #pragma unroll
@@ -609,7 +609,7 @@ head_rows_f16t_kernel(const float* __restrict__ feat, const float* __restrict__ 
                                 hi[4 * rep + 2 * sel] = h.x; hi[4 * rep + 2 * sel + 1] = h.y;
                                 lo[4 * rep + 2 * sel] = l.x; lo[4 * rep + 2 * sel + 1] = l.y;
                             }
-                        const uint32_t t = a_taddr + ((uint32_t)(hh * 16) << 16) + half * 2 * HT_STAGE_COLS;
+                        const uint32_t t = a_taddr + ((uint32_t)(hh * 16) << 16) + half * HT_GROUPS * HT_STAGE_COLS;
                         ht_tmem_st_16x256b_x2(t, hi);
                         ht_tmem_st_16x256b_x2(t + 16, lo);
                     }
