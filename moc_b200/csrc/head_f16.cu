@@ -546,27 +546,30 @@ head_rows_f16t_kernel(const float* __restrict__ feat, const float* __restrict__ 
         // bytes per load instruction and a warp-wide load touches 8 rows (not 32: the one-row-per-thread version
         // spent 77 % of the L1's tag throughput fetching every sector twice).
         const int rq = lane >> 2, cq = lane & 3;
-        const float sx = (float)(1 << HF_SX);
+        static_assert(HF_SX == 4, "the producers scale by the literal 16");
         const uint32_t a_taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + HT_A_COL0 + grp * HT_STAGE_COLS;
-        // cursor over this group's steps of the flat stream (non-empty tiles of this CTA x 16 K-slices): every HT_GROUPS-th one
-        int64_t ltile = blockIdx.x;
+        // cursor over this group's steps of the flat stream (non-empty tiles of this CTA x 16 K-slices): every
+        // HT_GROUPS-th one.  32-bit arithmetic throughout (slots and rows are int32 quantities): registers are what
+        // this role is short of.
+        const int nt = (int)n_tiles, ns = (int)n_slots, gstride = (int)gridDim.x;
+        int ltile = blockIdx.x;
         int lks = grp;
         int32_t lrow[4];                             // feature rows (hh, sel): tile rows 16 hh + rq + 8 sel of the quadrant; -1 = padding
         const float4* fbase = reinterpret_cast<const float4*>(feat) + cq;
         auto seek = [&]() {   // make ltile the next tile with rows, fetch this thread's four row numbers
-            while (ltile < n_tiles && !hf_tile_has_rows(sel_rows, ltile * HF_M, n_slots, lane)) ltile += gridDim.x;
-            if (ltile >= n_tiles) return;
+            while (ltile < nt && !hf_tile_has_rows(sel_rows, (int64_t)ltile * HF_M, n_slots, lane)) ltile += gstride;
+            if (ltile >= nt) return;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int64_t sl = ltile * HF_M + quad * 32 + (i >> 1) * 16 + rq + (i & 1) * 8;
-                lrow[i] = sl < n_slots ? (sel_rows ? sel_rows[sl] : (int32_t)sl) : -1;
+                const int sl = ltile * HF_M + quad * 32 + (i >> 1) * 16 + rq + (i & 1) * 8;
+                lrow[i] = sl < ns ? (sel_rows ? sel_rows[sl] : sl) : -1;
             }
         };
-        auto issue = [&](float4 (&b)[8]) -> bool {   // b[2 i + rep] = float4 4 rep + cq of row i's slice
-            if (ltile >= n_tiles) return false;
+        auto issue = [&](float4 (&b)[8]) -> int {   // b[2 i + rep] = float4 4 rep + cq of row i's slice; 1 if a step was issued
+            if (ltile >= nt) return 0;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                if (lrow[i] >= 0) {   // streamed once: keep the rows out of the L1 (it holds this kernel's few spills)
+                if (lrow[i] >= 0) {   // streamed once: keep the rows out of the L1
                     const float4* p = fbase + (int64_t)lrow[i] * (D / 4) + lks * (HT_KS / 4);
                     b[2 * i] = ldg_stream(p);
                     b[2 * i + 1] = ldg_stream(p + 4);
@@ -577,22 +580,22 @@ head_rows_f16t_kernel(const float* __restrict__ feat, const float* __restrict__ 
             lks += HT_GROUPS;
             if (lks >= HT_NKS) {
                 lks -= HT_NKS;
-                ltile += gridDim.x;
+                ltile += gstride;
                 seek();
             }
-            return true;
+            return 1;
         };
         float4 buf[HT_SETS][8];
-        bool pending[HT_SETS];
         seek();
+        int ahead = 0;                               // steps issued and not yet written to tensor memory
 #pragma unroll
-        for (int s = 0; s < HT_SETS; ++s) pending[s] = issue(buf[s]);
+        for (int s = 0; s < HT_SETS; ++s) ahead += issue(buf[s]);
         uint32_t parity = 0;
         int half = 0;                                // which of the group's two stages the next step fills
-        while (pending[0]) {
+        while (ahead > 0) {
 #pragma unroll
             for (int s = 0; s < HT_SETS; ++s) {
-                if (pending[s]) {
+                if (ahead > 0) {
                     const int stage = grp + HT_GROUPS * half;
                     mbar_wait(&empty_bar[stage], parity ^ 1u);   // the MMAs that read this stage have completed
                     hf_fence_after();
@@ -605,7 +608,7 @@ head_rows_f16t_kernel(const float* __restrict__ feat, const float* __restrict__ 
 #pragma unroll
                             for (int rep = 0; rep < 2; ++rep) {
                                 uint2 h, l;
-                                hf_split4(buf[s][2 * (2 * hh + sel) + rep], sx, h, l);
+                                hf_split4(buf[s][2 * (2 * hh + sel) + rep], 16.0f, h, l);
                                 hi[4 * rep + 2 * sel] = h.x; hi[4 * rep + 2 * sel + 1] = h.y;
                                 lo[4 * rep + 2 * sel] = l.x; lo[4 * rep + 2 * sel + 1] = l.y;
                             }
@@ -613,7 +616,7 @@ head_rows_f16t_kernel(const float* __restrict__ feat, const float* __restrict__ 
                         ht_tmem_st_16x256b_x2(t, hi);
                         ht_tmem_st_16x256b_x2(t + 16, lo);
                     }
-                    pending[s] = issue(buf[s]);            // the registers are free again: next loads leave now
+                    ahead += issue(buf[s]) - 1;            // the registers are free again: next loads leave now
                     ht_wait_st();
                     hf_fence_before();
                     __syncwarp();
