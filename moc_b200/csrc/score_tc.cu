@@ -92,6 +92,19 @@ __device__ __forceinline__ void st_tmem_ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void st_tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32"
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // 2-D tiled tensor copy global -> shared (SASS: UTMALDG), completion counted in bytes on the mbarrier at `bar`
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar,
                                             uint64_t policy) {
@@ -127,9 +140,9 @@ struct ScoreTcGeom {
 };
 __host__ __device__ inline ScoreTcGeom score_tc_geom(int n_cols) {
     ScoreTcGeom g;
-    g.npa = (n_cols + 7) & ~7;
-    g.n_wide = (2 * g.npa + 15) & ~15;
-    g.n_narrow = (g.npa + 15) & ~15;
+    g.npa = (n_cols + 15) & ~15;     // a multiple of 16: the narrow MMA (N = npa) must stop exactly where b1 starts
+    g.n_wide = 2 * g.npa;
+    g.n_narrow = g.npa;
     return g;
 }
 
@@ -191,7 +204,7 @@ score_keys_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const float* 
     unsigned char* bsm = smem;                                    // resident prompt tiles
     unsigned char* asm_ = smem + b_bytes;                         // A stages (a0 | a1)
     unsigned char* rawsm = asm_ + ST_A_STAGES * ST_STAGE_BYTES;   // per-warp raw fp32 rings
-    const int tmem_cols = 128;                                    // two accumulators of n_narrow (<= 64) columns
+    const int tmem_cols = 256;                                    // two accumulators of n_wide (<= 128) columns
 
     // resident prompt tiles (already swizzled): plain copy, then make them visible to the async proxy
     for (int i = tid; i < b_bytes / 16; i += ST_THREADS)
@@ -286,8 +299,11 @@ score_keys_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const float* 
         }
     } else if (warp == ST_WARP_MMA) {
         // =============================== MMA issuer ================================================
-        const uint32_t idesc_narrow = st_idesc_f16(g.n_narrow);
-        const uint32_t b1_off = (uint32_t)g.npa * 128u;   // b1 starts npa rows into the tile (a whole number of swizzle atoms)
+        // a0 x [b0 ; b1] as ONE MMA of width 2 npa (columns [0, npa) = a0 b0, [npa, 2 npa) = a0 b1), then a1 x b0 of
+        // width npa accumulating into the first half: the a0 tile is read from shared memory once instead of twice
+        // (the kernel is bound by shared-memory bandwidth: TMA writes, the producers' LDS / STS and these operand
+        // reads share 128 B/clk), and there are two MMAs per k-step instead of three.  The epilogue adds the halves.
+        const uint32_t idesc_wide = st_idesc_f16(g.n_wide), idesc_narrow = st_idesc_f16(g.n_narrow);
         int stage = 0, acc = 0;
         uint32_t parity = 0, acc_parity = 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -307,12 +323,10 @@ score_keys_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const float* 
 #pragma unroll
                     for (int ks = 0; ks < ST_KB / 16; ++ks) {
                         const uint32_t o = ks * 32;  // 16 halves = 32 bytes along K inside the swizzled row
-                        // a0 b0 + a0 b1 + a1 b0, all into columns [0, n_narrow): the accumulator holds the finished sum
                         const uint64_t da0 = st_desc_sw128(a0 + o), da1 = st_desc_sw128(a1 + o);
-                        const uint64_t db0 = st_desc_sw128(bt + o), db1 = st_desc_sw128(bt + b1_off + o);
-                        umma_f16(tmem_d, da0, db1, idesc_narrow, (kb | ks) != 0 ? 1u : 0u);
-                        umma_f16(tmem_d, da1, db0, idesc_narrow, 1u);
-                        umma_f16(tmem_d, da0, db0, idesc_narrow, 1u);
+                        const uint64_t db = st_desc_sw128(bt + o);
+                        umma_f16(tmem_d, da0, db, idesc_wide, (kb | ks) != 0 ? 1u : 0u);
+                        umma_f16(tmem_d, da1, db, idesc_narrow, 1u);
                     }
                     st_commit(&empty_bar[stage]);
                     if (kb == ST_NKB - 1) st_commit(&tfull_bar[acc]);
@@ -336,17 +350,17 @@ score_keys_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const float* 
             const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * acc_cols;
             // Columns are handled in groups of 8 behind warp-uniform guards: whole groups of classes run without
             // per-element predicates (C = 30 -> three of four), only the group straddling C / n_cols is predicated.
+            // column c of the scores = (a0 b0 + a1 b0)[c] + (a0 b1)[c]: accumulator columns c and npa + c.  npa is a
+            // multiple of 16, so the second half starts at 16-column granularity: it is read with x16 loads.
             float v[NCHUNK * 32];
 #pragma unroll
-            for (int ch = 0; ch < NCHUNK; ++ch) {
-                float d[32];
-                st_tmem_ld32(taddr + ch * 32, d);
+            for (int q = 0; q < NCHUNK * 2; ++q) {
+                if (q * 16 < n_cols) {
+                    float d0[16], d1[16];
+                    st_tmem_ld16(taddr + q * 16, d0);
+                    st_tmem_ld16(taddr + g.npa + q * 16, d1);
 #pragma unroll
-                for (int i0 = 0; i0 < 32; i0 += 8) {
-                    if (ch * 32 + i0 < n_cols) {
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) v[ch * 32 + i0 + e] = d[i0 + e] * descale;
-                    }
+                    for (int e = 0; e < 16; ++e) v[q * 16 + e] = (d0[e] + d1[e]) * descale;
                 }
             }
             st_fence_before();
