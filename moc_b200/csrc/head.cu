@@ -44,9 +44,8 @@ static size_t head_img_bytes() {
     const size_t a = head_tc_workspace_bytes(), b = head_f16_workspace_bytes();
     return ((a > b ? a : b) + 15) & ~(size_t)15;
 }
-// workspace = [ W1 image of whichever kernel runs | int32 domain flag (+ padding) | winner lists of the split pooling ]
-constexpr size_t HEAD_POOL_SCRATCH = 8u << 20;
-static size_t head_ws_bytes() { return head_img_bytes() + 16 + HEAD_POOL_SCRATCH; }
+// workspace = [ W1 image of whichever kernel runs | int32 domain flag (+ padding) ]
+static size_t head_ws_bytes() { return head_img_bytes() + 16; }
 static int launch_head_rows_mma(const float* feat, const float* keys, int64_t key_stride, int C, const int32_t* sel_rows,
                                 int64_t n_slots, const float* w1, const float* b1, const float* w2, const float* b2,
                                 unsigned active_mask, float* gate, float* final_scores, void* workspace, cudaStream_t st) {
@@ -255,25 +254,17 @@ constexpr int POOL_BATCH = 8;
 __global__ void __launch_bounds__(POOL_T)
 pool_final_block_kernel(const float* __restrict__ final_scores, const int64_t* __restrict__ sel_base,
                         const int32_t* __restrict__ sel_count, int C, int topk, float* __restrict__ bag_logits,
-                        int32_t* __restrict__ pool_pos, int parts, unsigned long long* __restrict__ cand) {
+                        int32_t* __restrict__ pool_pos) {
     extern __shared__ unsigned long long pool_best[];   // [C] round winners, then float sums [C]
-    // parts > 1: the slide's selected rows are cut into `parts` contiguous ranges, one CTA each; every CTA writes its
-    // per-class winners (sorted keys) to cand[slide][part][C][topk] and pool_merge_kernel finishes the job.  With
-    // hundreds of thousands of combined scores per slide (C = 30: 13 000 rows x 30) one CTA per slide is a long,
-    // latency-bound chain on a third of the SMs; the keys, their order and the summation order do not change.
-    const int slide = blockIdx.x / parts, part = blockIdx.x % parts, tid = threadIdx.x;
+    const int slide = blockIdx.x, tid = threadIdx.x;
     const int per = POOL_T / C, T = per * C;            // threads in use; thread t owns class t % C
-    const int S_all = sel_count[slide];
-    const int chunk = (S_all + parts - 1) / parts;
-    const int row_lo = part * chunk < S_all ? part * chunk : S_all;
-    const int row_hi = row_lo + chunk < S_all ? row_lo + chunk : S_all;
-    const int S = row_hi - row_lo;
-    const float* f = final_scores + (sel_base[slide] + row_lo) * C;
+    const int S = sel_count[slide];
+    const float* f = final_scores + sel_base[slide] * C;
     const int64_t total = (int64_t)S * C;
     float* sums = reinterpret_cast<float*>(pool_best + C);
     unsigned long long* thr = pool_best + 2 * C;          // [C] admission thresholds
     unsigned long long* tmax = thr + C;                   // [T] per-thread maxima
-    const int k_eff = topk < S ? topk : S;              // of this part; the merge takes min(topk, S_all) of all parts
+    const int k_eff = topk < S ? topk : S;
     unsigned long long lst[POOL_MAXK];
 #pragma unroll
     for (int j = 0; j < POOL_MAXK; ++j) lst[j] = 0ull;
@@ -284,7 +275,7 @@ pool_final_block_kernel(const float* __restrict__ final_scores, const int64_t* _
     // "some lane inserts" was true for ~95 % of the elements: 0.32 ms per 100 C=30 slides).
     unsigned long long mx = 0ull;
     if (tid < T) {
-        uint32_t i = (uint32_t)(row_lo + tid / C);      // row (in the slide) of element e = tid + m * T is row_lo + tid / C + m * per
+        uint32_t i = (uint32_t)(tid / C);               // row of element e = tid + m * T is tid / C + m * per
         for (int64_t e = tid; e < total; e += (int64_t)POOL_BATCH * T, i += (uint32_t)(POOL_BATCH * per)) {
             float v[POOL_BATCH];
 #pragma unroll
@@ -325,7 +316,7 @@ pool_final_block_kernel(const float* __restrict__ final_scores, const int64_t* _
     // Pass 2: sorted top lists of the keys at or above the class threshold
     if (tid < T) {
         const unsigned long long lim = thr[tid % C];
-        uint32_t i = (uint32_t)(row_lo + tid / C);
+        uint32_t i = (uint32_t)(tid / C);
         for (int64_t e = tid; e < total; e += (int64_t)POOL_BATCH * T, i += (uint32_t)(POOL_BATCH * per)) {
             float v[POOL_BATCH];
 #pragma unroll
@@ -360,90 +351,25 @@ pool_final_block_kernel(const float* __restrict__ final_scores, const int64_t* _
 #pragma unroll
             for (int j = 0; j + 1 < POOL_MAXK; ++j) lst[j] = lst[j + 1];
             lst[POOL_MAXK - 1] = 0ull;
-            if (cand != nullptr) {
-                cand[(((int64_t)slide * parts + part) * C + c) * topk + r] = win;
-            } else {
-                sums[c] += ord2f((uint32_t)(win >> 32));      // one writer per class and round: the summation order is fixed
-                if (pool_pos) pool_pos[((int64_t)slide * C + c) * topk + r] = (int32_t)(0xffffffffu - (uint32_t)(win & 0xffffffffull));
-            }
+            sums[c] += ord2f((uint32_t)(win >> 32));      // one writer per class and round: the summation order is fixed
+            if (pool_pos) pool_pos[((int64_t)slide * C + c) * topk + r] = (int32_t)(0xffffffffu - (uint32_t)(win & 0xffffffffull));
             pool_best[c] = 0ull;
         }
         __syncthreads();
     }
     if (tid < C) {
-        if (cand != nullptr) {
-            for (int r = k_eff; r < topk; ++r) cand[(((int64_t)slide * parts + part) * C + tid) * topk + r] = 0ull;
-        } else {
-            bag_logits[(int64_t)slide * C + tid] = k_eff > 0 ? sums[tid] / (float)k_eff : 0.f;
-            if (pool_pos)
-                for (int r = k_eff; r < topk; ++r) pool_pos[((int64_t)slide * C + tid) * topk + r] = -1;
-        }
+        bag_logits[(int64_t)slide * C + tid] = k_eff > 0 ? sums[tid] / (float)k_eff : 0.f;
+        if (pool_pos)
+            for (int r = k_eff; r < topk; ++r) pool_pos[((int64_t)slide * C + tid) * topk + r] = -1;
     }
-}
-
-// Second stage of the split pooling: thread per (slide, class) merges the parts' sorted winner lists - K rounds of
-// "largest head" - and sums the values in that (globally descending) order, exactly as the single-CTA version does.
-constexpr int POOL_MAX_PARTS = 8;
-__global__ void pool_merge_kernel(const unsigned long long* __restrict__ cand, const int32_t* __restrict__ sel_count,
-                                  int n_slides, int C, int topk, int parts, float* __restrict__ bag_logits,
-                                  int32_t* __restrict__ pool_pos) {
-    const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (item >= (int64_t)n_slides * C) return;
-    const int slide = (int)(item / C), c = (int)(item % C);
-    const int S = sel_count[slide];
-    const int k_eff = topk < S ? topk : S;
-    int head[POOL_MAX_PARTS];
-#pragma unroll
-    for (int p = 0; p < POOL_MAX_PARTS; ++p) head[p] = 0;
-    float sum = 0.f;
-    for (int r = 0; r < k_eff; ++r) {
-        unsigned long long best = 0ull;
-        int bp = 0;
-#pragma unroll
-        for (int p = 0; p < POOL_MAX_PARTS; ++p) {
-            if (p < parts && head[p] < topk) {
-                const unsigned long long key = cand[(((int64_t)slide * parts + p) * C + c) * topk + head[p]];
-                if (key > best) { best = key; bp = p; }
-            }
-        }
-#pragma unroll
-        for (int p = 0; p < POOL_MAX_PARTS; ++p)
-            if (p == bp) ++head[p];
-        sum += ord2f((uint32_t)(best >> 32));
-        if (pool_pos) pool_pos[item * topk + r] = (int32_t)(0xffffffffu - (uint32_t)(best & 0xffffffffull));
-    }
-    bag_logits[item] = k_eff > 0 ? sum / (float)k_eff : 0.f;
-    if (pool_pos)
-        for (int r = k_eff; r < topk; ++r) pool_pos[item * topk + r] = -1;
 }
 
 static int launch_pool_final(const float* final_scores, const int64_t* sel_base, const int32_t* sel_count, int n_slides,
-                             int C, int topk, float* bag_logits, int32_t* pool_pos, void* scratch, size_t scratch_bytes,
-                             cudaStream_t st) {
+                             int C, int topk, float* bag_logits, int32_t* pool_pos, cudaStream_t st) {
     if (topk <= POOL_MAXK && C <= POOL_T) {
         // round winners [C] (8 B) | sums [C] (4 B, padded to 8) | thresholds [C] | per-thread maxima [POOL_T]
         const size_t smem = (size_t)(3 * C + POOL_T) * sizeof(unsigned long long);
-        // wide class sets select thousands of rows per slide: cut every slide into row ranges, as many as keep the
-        // device busy and fit the scratch
-        int parts = 1;
-        if (scratch != nullptr && C >= 8) {
-            const size_t per_part = (size_t)n_slides * C * topk * sizeof(unsigned long long);
-            parts = 4;
-            while (parts > 1 && per_part * parts > scratch_bytes) parts >>= 1;
-        }
-        if (parts > 1) {
-            unsigned long long* cand = reinterpret_cast<unsigned long long*>(scratch);
-            pool_final_block_kernel<<<n_slides * parts, POOL_T, smem, st>>>(final_scores, sel_base, sel_count, C, topk,
-                                                                           bag_logits, pool_pos, parts, cand);
-            MOC_LAUNCH_CHECK("pool_final_block_kernel");
-            const int64_t items = (int64_t)n_slides * C;
-            pool_merge_kernel<<<(unsigned)((items + 127) / 128), 128, 0, st>>>(cand, sel_count, n_slides, C, topk, parts,
-                                                                              bag_logits, pool_pos);
-            MOC_LAUNCH_CHECK("pool_merge_kernel");
-            return MOC_OK;
-        }
-        pool_final_block_kernel<<<n_slides, POOL_T, smem, st>>>(final_scores, sel_base, sel_count, C, topk, bag_logits,
-                                                               pool_pos, 1, nullptr);
+        pool_final_block_kernel<<<n_slides, POOL_T, smem, st>>>(final_scores, sel_base, sel_count, C, topk, bag_logits, pool_pos);
         MOC_LAUNCH_CHECK("pool_final_block_kernel");
         return MOC_OK;
     }
@@ -799,10 +725,7 @@ extern "C" int moc_head_forward(const float* feat, const float* keys, int64_t ke
         }
     }
     {
-        unsigned char* scratch = workspace != nullptr && workspace_bytes >= head_ws_bytes()
-                                     ? reinterpret_cast<unsigned char*>(workspace) + head_img_bytes() + 16 : nullptr;
-        const int rc = launch_pool_final(final_scores, sel_base, sel_count, n_slides, n_classes, topk, bag_logits, pool_pos,
-                                         scratch, HEAD_POOL_SCRATCH, st);
+        const int rc = launch_pool_final(final_scores, sel_base, sel_count, n_slides, n_classes, topk, bag_logits, pool_pos, st);
         if (rc != MOC_OK) return rc;
     }
     return MOC_OK;
@@ -943,5 +866,5 @@ extern "C" int moc_ablation_forward(const float* keys, int64_t key_stride, int n
                                                                             sel_capacity_total, mode, final_scores);
         MOC_LAUNCH_CHECK("ablation_rows_kernel");
     }
-    return launch_pool_final(final_scores, sel_base, sel_count, n_slides, n_classes, topk, bag_logits, nullptr, nullptr, 0, st);
+    return launch_pool_final(final_scores, sel_base, sel_count, n_slides, n_classes, topk, bag_logits, nullptr, st);
 }

@@ -139,7 +139,6 @@ class MocEngine:
         # kernels from then on (3xTF32 gate, fp32 CUDA-core scoring) - the reference is finite for any finite feature
         self._wide_stores: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
         self._graphs: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()   # store -> captured training steps
-        self._graph_head_ws = None
 
     # ---- scoring -------------------------------------------------------------------------------
     def keys_for(self, store: RaggedBagStore, lo: int = 0, hi: Optional[int] = None, wide: bool = False) -> torch.Tensor:
@@ -397,9 +396,7 @@ class MocEngine:
         g.mask_pinned = torch.empty(n, dtype=torch.uint8, pin_memory=True)
         g.mask_dev = torch.ones(n, dtype=torch.uint8, device=dev)
         g.grads = torch.empty(ops.NUM_PARAMS, dtype=torch.float32, device=dev)
-        if self._graph_head_ws is None:        # one scratch for all captured steps: they replay one after another
-            self._graph_head_ws = ops.HeadWorkspace(dev)
-        g.head_ws = self._graph_head_ws
+        g.head_ws = ops.HeadWorkspace(dev)
         label = store.labels[slide:slide + 1]
         views = ops.split_grads(g.grads)
         torch.cuda.current_stream().synchronize()
