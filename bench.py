@@ -460,7 +460,7 @@ def run_ours(a):
         except Exception:
             tpeak, tsrc = 1400.0, "fallback (B200_PROFILING.md: ~1.4 PFLOP/s sustained)"
         roofline = {"bound": "tensor", "kernel": kernel, "achieved": tf, "peak": tpeak, "unit": "TFLOP/s",
-                    "frac": tf / tpeak, "traffic": None, "peak_source": tsrc,
+                    "frac": tf / tpeak, "traffic": traffic, "peak_source": tsrc,
                     "algorithmic_flops_per_launch": flops, "columns": n_cols, "avg_launch_ms": avg_ms,
                     "launches_timed": len(score_ms),
                     "share_of_step": avg_ms * len(score_ms) / a.steps / (ms_local / a.steps),
