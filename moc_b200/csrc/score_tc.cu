@@ -26,9 +26,10 @@
 //   warp 12     MMA issuer (one elected lane), two TMEM accumulators.
 //   warps 0-3   epilogue, thread = patch: softmax / top-2 / background sum+max, key planes written as full
 //               128-byte lines.
-// The prompt tile is [b0 ; b1] stacked along N (b1 starts at row NPa = round8(cols)); the three products a0 b1,
-// a1 b0, a0 b0 are three MMAs of width N_narrow = round16(NPa) into the same TMEM columns, so the accumulator
-// holds the finished sum (columns past the real prompt count pick up rows of the neighbouring block: unused).
+// The prompt tile is [b0 ; b1] stacked along N (b1 starts at row NPa = round16(cols)); a0 x [b0 ; b1] is ONE MMA of
+// width 2 NPa (accumulator columns [0, NPa) = a0 b0, [NPa, 2 NPa) = a0 b1) and a1 x b0 a second one of width NPa
+// into the first half; the epilogue adds the two halves.  (Three MMAs of width NPa into the same columns - the
+// first version - read the a0 tile twice; measured, the two forms run at the same speed: the producers bound it.)
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <stddef.h>
