@@ -430,10 +430,15 @@ constexpr int HT_KS = 32;                    // K elements per step (128 bytes o
 constexpr int HT_NKS = D / HT_KS;            // 16 steps per tile
 constexpr int HT_GROUPS = 3;                 // producer groups of four lane-quadrant warps
 constexpr int HT_STAGES = 2 * HT_GROUPS;     // TMEM A stages: step s -> group s % 3, stage s % 6 (two stages per group)
-constexpr int HT_SETS = 2;                   // 128-byte register sets of loads in flight per producer thread
+constexpr int HT_SETS = 3;                   // 128-byte register sets of loads in flight per producer thread: 144 KB per SM
 constexpr int HT_PROD_WARPS = 4 * HT_GROUPS; // 12
 constexpr int HT_WARP_MMA = HF_EPI_WARPS + HT_PROD_WARPS;   // 16
-constexpr int HT_THREADS = (HT_WARP_MMA + 1) * 32;          // 544: 17 warps, registers allocated for 20 -> 96 per thread
+// Five warpgroups: epilogue (warps 0-3), three producer groups (4-15), and one whose first warp issues the MMAs (its
+// other three warps only exist so that setmaxnreg, a warpgroup-wide instruction, can be executed).  The CTA starts at
+// 96 registers per thread (640 threads); the epilogue shrinks to 72, the MMA group to 32, and the producers grow to
+// 136: 72*128 + 32*128 + 136*384 = 65 536, the whole register file.
+constexpr int HT_THREADS = (HT_WARP_MMA + 4) * 32;          // 640
+constexpr int HT_REGS_EPI = 72, HT_REGS_MMA = 32, HT_REGS_PROD = 136;
 constexpr int HT_STAGE_COLS = 32;            // a0: 16 columns of packed half2, a1: 16 columns
 constexpr int HT_ACC_COL0 = 0;               // two accumulators of 64 columns
 constexpr int HT_A_COL0 = 128;               // four A stages of 32 columns
@@ -536,7 +541,8 @@ head_rows_f16t_kernel(const float* __restrict__ feat, const float* __restrict__ 
     const float descale = reinterpret_cast<const HeadF16Tail*>(img + HF_BIMG_BYTES)->descale;
 
     if (warp >= HF_EPI_WARPS && warp < HT_WARP_MMA) {
-        // =============================== A producers: thread = row of the tile =====================
+        // =============================== A producers ===============================================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(HT_REGS_PROD));
         const int pw = warp - HF_EPI_WARPS;          // 0..11
         const int quad = warp & 3;                   // TMEM lane quadrant this warp may access (warp id % 4)
         const int grp = pw >> 2;                     // owns steps s with s % HT_GROUPS == grp, TMEM stages grp and grp + HT_GROUPS
@@ -626,8 +632,10 @@ head_rows_f16t_kernel(const float* __restrict__ feat, const float* __restrict__ 
                 }
             }
         }
-    } else if (warp == HT_WARP_MMA) {
-        // =============================== MMA issuer ================================================
+    } else if (warp >= HT_WARP_MMA) {
+        // =============================== MMA issuer (first warp of its warpgroup) ==================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(HT_REGS_MMA));
+        if (warp == HT_WARP_MMA) {
         if (lane == 0) {   // W1 image -> shared memory, once per CTA
             const uint64_t policy = l2_policy_evict_last();
             mbar_arrive_expect_tx(&b_bar, HF_BIMG_BYTES);
@@ -668,8 +676,10 @@ head_rows_f16t_kernel(const float* __restrict__ feat, const float* __restrict__ 
             }
             if (++acc == 2) { acc = 0; acc_parity ^= 1u; }
         }
+        }
     } else {
         // =============================== epilogue (warps 0-3): as in head_rows_f16_kernel ==========
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(HT_REGS_EPI));
         const float a0 = (active_mask & MOC_CLS_TOPK) ? 1.f : 0.f;
         const float a1 = (active_mask & MOC_CLS_DELTA_SOFTMAX) ? 1.f : 0.f;
         const float a2 = (active_mask & MOC_CLS_DELTA_DIFF) ? 1.f : 0.f;
