@@ -430,15 +430,16 @@ constexpr int HT_KS = 32;                    // K elements per step (128 bytes o
 constexpr int HT_NKS = D / HT_KS;            // 16 steps per tile
 constexpr int HT_GROUPS = 3;                 // producer groups of four lane-quadrant warps
 constexpr int HT_STAGES = 2 * HT_GROUPS;     // TMEM A stages: step s -> group s % 3, stage s % 6 (two stages per group)
-constexpr int HT_SETS = 3;                   // 128-byte register sets of loads in flight per producer thread: 144 KB per SM
+constexpr int HT_SETS = 2;                   // 128-byte register sets of loads in flight per producer thread: 96 KB per SM
 constexpr int HT_PROD_WARPS = 4 * HT_GROUPS; // 12
 constexpr int HT_WARP_MMA = HF_EPI_WARPS + HT_PROD_WARPS;   // 16
 // Five warpgroups: epilogue (warps 0-3), three producer groups (4-15), and one whose first warp issues the MMAs (its
-// other three warps only exist so that setmaxnreg, a warpgroup-wide instruction, can be executed).  The CTA starts at
-// 96 registers per thread (640 threads); the epilogue shrinks to 72, the MMA group to 32, and the producers grow to
-// 136: 72*128 + 32*128 + 136*384 = 65 536, the whole register file.
+// other three warps only exist so that setmaxnreg, a warpgroup-wide instruction, can be executed).  The CTA is
+// launched with 96 registers per thread (640 threads = 61 440 registers: that is the pool setmaxnreg moves registers
+// in - the SM's remaining 4 096 do not belong to it, and an .inc that the pool cannot satisfy spins forever); the
+// epilogue shrinks to 80, the MMA group to 40, and the producers grow to 120: 80*128 + 40*128 + 120*384 = 61 440.
 constexpr int HT_THREADS = (HT_WARP_MMA + 4) * 32;          // 640
-constexpr int HT_REGS_EPI = 72, HT_REGS_MMA = 32, HT_REGS_PROD = 136;
+constexpr int HT_REGS_EPI = 80, HT_REGS_MMA = 40, HT_REGS_PROD = 120;
 constexpr int HT_STAGE_COLS = 32;            // a0: 16 columns of packed half2, a1: 16 columns
 constexpr int HT_ACC_COL0 = 0;               // two accumulators of 64 columns
 constexpr int HT_A_COL0 = 128;               // four A stages of 32 columns
