@@ -33,6 +33,7 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <stddef.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -189,16 +190,30 @@ __global__ void score_tc_prep_kernel(const float* __restrict__ packed, int n_col
     *reinterpret_cast<uint2*>(tile + n1 * 128 + (((q >> 1) ^ (n1 & 7)) << 4) + ((q & 1) << 3)) = c1;
 }
 
-template <int NCHUNK, bool NORM>  // NCHUNK = ceil(n_cols/32): 1 or 2
-__global__ void __launch_bounds__(ST_THREADS, 1)
+// PW = producer warps.  8: one CTA of 13 warps, 128 registers each (the first version).  16: twice the producers, each
+// converting 8 instead of 16 patches per K-block step - the producers' LDS -> split -> STS chain is latency-bound with
+// two warps per scheduler - in a CTA of six warpgroups launched at 80 registers per thread whose pool setmaxnreg
+// redistributes: producers 64, the MMA issuer's group 40, the epilogue (64 live scores per thread) 160.
+template <int PW> struct StRoles {
+    static constexpr int WARP_MMA = ST_EPI_WARPS + PW;
+    static constexpr int THREADS = (PW == 16 ? WARP_MMA + 4 : WARP_MMA + 1) * 32;   // 768 / 416
+    static constexpr int ROWS_PER_WARP = ST_M / PW;                                  // 8 / 16
+    static constexpr int SLOTS_PER_STEP = ROWS_PER_WARP / ST_SLOT_ROWS;              // 1 / 2
+};
+constexpr int ST_REGS_PROD16 = 64, ST_REGS_MMA16 = 40, ST_REGS_EPI16 = 160;
+
+template <int NCHUNK, bool NORM, int PW>  // NCHUNK = ceil(n_cols/32): 1 or 2
+__global__ void __launch_bounds__(StRoles<PW>::THREADS, 1)
 score_keys_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const float* __restrict__ feat, int64_t n_rows,
                      const unsigned char* __restrict__ btiles,
                      int n_classes, int n_cols, ScoreTcGeom g, int ring_slots, float* __restrict__ keys,
                      int64_t key_stride, ScoreTcTail* __restrict__ tail) {
     extern __shared__ unsigned char st_smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[ST_A_STAGES], empty_bar[ST_A_STAGES], tfull_bar[2], tempty_bar[2];
-    __shared__ __align__(8) uint64_t raw_bar[ST_PROD_WARPS][ST_MAX_SLOTS];
+    __shared__ __align__(8) uint64_t raw_bar[PW][ST_MAX_SLOTS];
     __shared__ uint32_t tmem_base_s;
+    constexpr int WARP_MMA = StRoles<PW>::WARP_MMA, THREADS = StRoles<PW>::THREADS;
+    constexpr int RPW = StRoles<PW>::ROWS_PER_WARP, SPS = StRoles<PW>::SLOTS_PER_STEP;
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(st_smem_raw) + 1023) & ~(uintptr_t)1023);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b_bytes = (int)g.b_bytes();
@@ -208,23 +223,23 @@ score_keys_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const float* 
     const int tmem_cols = 256;                                    // two accumulators of n_wide (<= 128) columns
 
     // resident prompt tiles (already swizzled): plain copy, then make them visible to the async proxy
-    for (int i = tid; i < b_bytes / 16; i += ST_THREADS)
+    for (int i = tid; i < b_bytes / 16; i += THREADS)
         reinterpret_cast<uint4*>(bsm)[i] = __ldg(reinterpret_cast<const uint4*>(btiles) + i);
     fence_proxy_async_smem();
     if (tid == 0) {
         for (int s = 0; s < ST_A_STAGES; ++s) {
-            mbar_init(&full_bar[s], ST_PROD_WARPS);
+            mbar_init(&full_bar[s], PW);
             mbar_init(&empty_bar[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull_bar[a], 1);
             mbar_init(&tempty_bar[a], ST_EPI_WARPS);
         }
-        for (int w = 0; w < ST_PROD_WARPS; ++w)
+        for (int w = 0; w < PW; ++w)
             for (int s = 0; s < ring_slots; ++s) mbar_init(&raw_bar[w][s], 1);
         fence_mbar_init();
     }
-    if (warp == ST_WARP_MMA) {
+    if (warp == WARP_MMA) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
                      "r"((uint32_t)tmem_cols)
                      : "memory");
@@ -237,37 +252,38 @@ score_keys_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const float* 
     const int acc_cols = tmem_cols / 2;
     const int64_t n_tiles = (n_rows + ST_M - 1) / ST_M;
 
-    if (warp >= ST_EPI_WARPS && warp < ST_WARP_MMA) {
+    if (warp >= ST_EPI_WARPS && warp < WARP_MMA) {
         // =============================== producers ================================================
+        if (PW == 16) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(ST_REGS_PROD16));
         // The CTA's tiles form one flat stream of (tile, K-block) steps; in a step a warp converts the 256-byte
         // K-block piece of its 16 patches = 2 slots of 8 patches.  Slot u of the warp's stream lands in ring
         // position u % ring_slots; as soon as the warp has read a slot it re-arms it for slot u + ring_slots.
         const int pw = warp - ST_EPI_WARPS, rhalf = lane >> 4, q = lane & 15;
         const uint64_t policy = l2_policy_evict_first();
         const int64_t my_tiles = (int64_t)blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-        const int64_t n_slots_total = my_tiles * ST_NKB * 2;
+        const int64_t n_slots_total = my_tiles * ST_NKB * SPS;
         const uint32_t ring = smem_u32(rawsm) + (uint32_t)(pw * ring_slots * ST_SLOT_BYTES);
         const uint32_t bars = smem_u32(&raw_bar[pw][0]);
         // issue cursor: one elected lane arms the slot's barrier and launches ONE 2-D tensor copy (8 patches x
         // 64 floats; rows past the end of feat are zero-filled by the copy engine)
         int64_t i_tile = blockIdx.x, i_left = n_slots_total;
-        int i_sub = 0;  // (kb, half) = (i_sub >> 1, i_sub & 1) inside the tile
+        int i_sub = 0;  // (kb, slot of the step) = (i_sub / SPS, i_sub % SPS) inside the tile
         auto issue = [&](int pos) {
             if (lane == 0) {
-                const int64_t row0 = i_tile * ST_M + pw * 16 + (i_sub & 1) * ST_SLOT_ROWS;
+                const int64_t row0 = i_tile * ST_M + pw * RPW + (i_sub % SPS) * ST_SLOT_ROWS;
                 const uint32_t bar = bars + pos * 8;
                 mbar_arrive_expect_tx_a(bar, ST_SLOT_BYTES);
-                tma_load_2d(ring + pos * ST_SLOT_BYTES, &feat_map, (i_sub >> 1) * ST_KB, (int)row0, bar, policy);
+                tma_load_2d(ring + pos * ST_SLOT_BYTES, &feat_map, (i_sub / SPS) * ST_KB, (int)row0, bar, policy);
             }
-            if (++i_sub == 2 * ST_NKB) { i_sub = 0; i_tile += gridDim.x; }
+            if (++i_sub == SPS * ST_NKB) { i_sub = 0; i_tile += gridDim.x; }
             --i_left;
         };
         for (int s = 0; s < ring_slots; ++s)
             if (i_left > 0) issue(s);
-        uint32_t roff[8];
+        uint32_t roff[4 * SPS];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int r = pw * 16 + i * 2 + rhalf;
+        for (int i = 0; i < 4 * SPS; ++i) {
+            const int r = pw * RPW + i * 2 + rhalf;
             roff[i] = (uint32_t)(r * 128 + (((q >> 1) ^ (r & 7)) << 4) + ((q & 1) << 3));
         }
         const uint32_t a_base = smem_u32(asm_);
@@ -275,9 +291,9 @@ score_keys_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const float* 
         int stage = 0, pos = 0;
         uint32_t parity = 0, rparity = 0;
         for (int64_t step = 0; step < my_tiles * ST_NKB; ++step) {
-            uint2 c0[8], c1[8];
+            uint2 c0[4 * SPS], c1[4 * SPS];
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
+            for (int j = 0; j < SPS; ++j) {
                 mbar_wait_a(bars + pos * 8, rparity);
                 const uint32_t sp = ring + pos * ST_SLOT_BYTES + lds_off;
 #pragma unroll
@@ -289,7 +305,7 @@ score_keys_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const float* 
             mbar_wait(&empty_bar[stage], parity ^ 1u);
             const uint32_t a0 = a_base + stage * ST_STAGE_BYTES;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < 4 * SPS; ++i) {
                 sts64(a0 + roff[i], c0[i]);
                 sts64(a0 + ST_A_BYTES + roff[i], c1[i]);
             }
@@ -298,8 +314,10 @@ score_keys_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const float* 
             if (lane == 0) mbar_arrive(&full_bar[stage]);
             if (++stage == ST_A_STAGES) { stage = 0; parity ^= 1u; }
         }
-    } else if (warp == ST_WARP_MMA) {
-        // =============================== MMA issuer ================================================
+    } else if (warp >= WARP_MMA) {
+        // =============================== MMA issuer (first warp of its group) ======================
+        if (PW == 16) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(ST_REGS_MMA16));
+        if (warp == WARP_MMA) {
         // a0 x [b0 ; b1] as ONE MMA of width 2 npa (columns [0, npa) = a0 b0, [npa, 2 npa) = a0 b1), then a1 x b0 of
         // width npa accumulating into the first half: the a0 tile is read from shared memory once instead of twice
         // (the kernel is bound by shared-memory bandwidth: TMA writes, the producers' LDS / STS and these operand
@@ -337,8 +355,10 @@ score_keys_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const float* 
             }
             if (++acc == 2) { acc = 0; acc_parity ^= 1u; }
         }
+        }
     } else {
         // =============================== epilogue (warps 0-3): thread = patch ========================
+        if (PW == 16) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(ST_REGS_EPI16));
         const int C = n_classes;
         const float descale = tail->descale;
         int acc = 0;
@@ -468,7 +488,7 @@ score_keys_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const float* 
 
     st_fence_before();
     __syncthreads();
-    if (warp == ST_WARP_MMA) {
+    if (warp == WARP_MMA) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)tmem_cols)
                      : "memory");
     }
@@ -868,6 +888,20 @@ static int make_feat_map(CUtensorMap* map, const float* feat, int64_t n_rows) {
     return MOC_OK;
 }
 
+template <int NCHUNK, bool NORM, int PW>
+static int launch_tc_pw(const CUtensorMap& map, const float* feat, int64_t n_rows, const unsigned char* prep, int C, int n_cols,
+                        const ScoreTcGeom& g, int ring_slots, size_t smem, float* keys, int64_t key_stride, cudaStream_t st) {
+    MOC_CUDA(cudaFuncSetAttribute(score_keys_tc_kernel<NCHUNK, NORM, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+    const int64_t n_tiles = (n_rows + ST_M - 1) / ST_M;
+    const int grid = (int)(n_tiles < sm_count() ? n_tiles : sm_count());
+    ScoreTcTail* tail = reinterpret_cast<ScoreTcTail*>(const_cast<unsigned char*>(prep) + g.b_bytes());
+    score_keys_tc_kernel<NCHUNK, NORM, PW><<<grid, StRoles<PW>::THREADS, smem, st>>>(map, feat, n_rows, prep, C, n_cols, g,
+                                                                                    ring_slots, keys, key_stride, tail);
+    MOC_LAUNCH_CHECK("score_keys_tc_kernel");
+    return MOC_OK;
+}
+
 template <int NCHUNK, bool NORM>
 static int launch_tc(const float* feat, int64_t n_rows, const unsigned char* prep, int C, int n_cols, float* keys,
                      int64_t key_stride, cudaStream_t st) {
@@ -875,22 +909,25 @@ static int launch_tc(const float* feat, int64_t n_rows, const unsigned char* pre
     const size_t b_bytes = g.b_bytes();
     const size_t budget = 227 * 1024 - 1024 - 2048;  // alignment slack, static shared memory
     const size_t fixed = b_bytes + (size_t)ST_A_STAGES * ST_STAGE_BYTES;
-    int ring_slots = fixed < budget ? (int)((budget - fixed) / ((size_t)ST_PROD_WARPS * ST_SLOT_BYTES)) : 0;
-    if (ring_slots > ST_MAX_SLOTS) ring_slots = ST_MAX_SLOTS;
+    auto slots_for = [&](int pw) {
+        int n = fixed < budget ? (int)((budget - fixed) / ((size_t)pw * ST_SLOT_BYTES)) : 0;
+        return n > ST_MAX_SLOTS ? ST_MAX_SLOTS : n;
+    };
+    static int force_pw = -1;       // MOC_SCORE_TC_PRODUCERS=8|16 (developer A/B switch)
+    if (force_pw < 0) {
+        const char* e = getenv("MOC_SCORE_TC_PRODUCERS");
+        force_pw = e ? atoi(e) : 0;
+    }
+    // sixteen producer warps whenever their rings still hold two slots each
+    const int pw = force_pw == 8 ? 8 : (slots_for(16) >= 2 ? 16 : 8);
+    const int ring_slots = slots_for(pw);
     MOC_CHECK_SHAPE(ring_slots >= 2, "moc_score_keys_tc: %d prompt columns do not fit the tensor-core kernel", n_cols);
-    const size_t smem = fixed + (size_t)ring_slots * ST_PROD_WARPS * ST_SLOT_BYTES + 1024;
-    MOC_CUDA(cudaFuncSetAttribute(score_keys_tc_kernel<NCHUNK, NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem));
-    const int64_t n_tiles = (n_rows + ST_M - 1) / ST_M;
-    const int grid = (int)(n_tiles < sm_count() ? n_tiles : sm_count());
-    ScoreTcTail* tail = reinterpret_cast<ScoreTcTail*>(const_cast<unsigned char*>(prep) + b_bytes);
+    const size_t smem = fixed + (size_t)ring_slots * pw * ST_SLOT_BYTES + 1024;
     CUtensorMap map;
     const int rc = make_feat_map(&map, feat, n_rows);
     if (rc != MOC_OK) return rc;
-    score_keys_tc_kernel<NCHUNK, NORM><<<grid, ST_THREADS, smem, st>>>(map, feat, n_rows, prep, C, n_cols, g, ring_slots,
-                                                                      keys, key_stride, tail);
-    MOC_LAUNCH_CHECK("score_keys_tc_kernel");
-    return MOC_OK;
+    return pw == 16 ? launch_tc_pw<NCHUNK, NORM, 16>(map, feat, n_rows, prep, C, n_cols, g, ring_slots, smem, keys, key_stride, st)
+                    : launch_tc_pw<NCHUNK, NORM, 8>(map, feat, n_rows, prep, C, n_cols, g, ring_slots, smem, keys, key_stride, st);
 }
 
 template <bool NORM>
