@@ -28,9 +28,9 @@ int launch_head_rows_f16(const float* feat, const float* keys, int64_t key_strid
                          unsigned active_mask, float* gate, float* final_scores, void* workspace, int* domain_flag,
                          cudaStream_t st);
 
-// MOC_HEAD_IMPL = auto (default: FP16x3 up to 8 classes, 3xTF32 beyond - see head_f16.cu) | f16 | tf32 | simt.  The
-// 3xTF32 and CUDA-core kernels also serve as in-tree cross-checks of the FP16x3 path and for features outside its
-// |x| < 4094 domain.
+// MOC_HEAD_IMPL = auto (default: FP16x3, see head_f16.cu) | f16 | tf32 | simt.  The 3xTF32 kernel serves features
+// outside the FP16x3 kernel's |x| < 4094 range (MOC_HEAD_WIDE_DOMAIN); it and the CUDA-core kernel are also the
+// in-tree cross-checks.
 static int head_impl() {
     static int cached = -1;
     if (cached < 0) {
@@ -52,7 +52,8 @@ static int launch_head_rows_mma(const float* feat, const float* keys, int64_t ke
     const int impl = head_impl();
     const bool wide = (active_mask & MOC_HEAD_WIDE_DOMAIN) != 0;   // the caller asks for the range-free kernel
     int* flag = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(workspace) + head_img_bytes());
-    return (impl == 1 || wide || (impl == 3 && C > 8))
+    (void)C;   // the FP16x3 kernel with its A operand in tensor memory is ahead at every class count (C = 30: 5.98 vs 6.55 ms)
+    return (impl == 1 || wide)
                ? launch_head_rows_tc(feat, keys, key_stride, C, sel_rows, n_slots, w1, b1, w2, b2, active_mask, gate,
                                      final_scores, workspace, st)
                : launch_head_rows_f16(feat, keys, key_stride, C, sel_rows, n_slots, w1, b1, w2, b2, active_mask, gate,

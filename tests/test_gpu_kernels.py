@@ -464,7 +464,7 @@ def test_out_of_range_features_match_the_oracle(c, big):
     """Features beyond the fast kernels' range (|x| >= 4094 for the FP16x3 gate MLP, >= 65504 for the tensor-core
     scoring of wide prompt sets) are finite in the reference (fp32 matmul); the flag-checked passes of the engine and
     slide_process must re-dispatch to the range-free kernels and return the oracle's finite values."""
-    from moc_b200 import RaggedBagStore, slide_process
+    from moc_b200 import RaggedBagStore, ops, slide_process
     from moc_b200.engine import MocEngine
     from moc_b200 import synthetic
     j, k = 100, 10
@@ -478,15 +478,16 @@ def test_out_of_range_features_match_the_oracle(c, big):
     store = RaggedBagStore.from_bags(bags, labels, DEV)
     unchecked = eng.eval_logits(store, prm)
     got = eng.eval_logits(store, prm, check_domain=True)
-    # 30 classes: 3xTF32 gate kernel (no limit) and FP16x3 scoring (limit 65504), so 5000 is still in range there
-    expect_wide = not (c == 30 and big < 65504)
-    assert eng.is_wide(store) == expect_wide and torch.isfinite(got).all()
+    assert eng.is_wide(store) and torch.isfinite(got).all()
     if c == 2:      # the FP16x3 gate kernel alone is loud about it: non-finite gates, non-finite bag logits
         assert not torch.isfinite(unchecked[1]).all()
-    elif expect_wide:   # tensor-core scoring: non-finite keys for the offending rows and the flag in the prompt image
+    else:           # and it raises its flag; the tensor-core scoring of the wide prompt set has its own, for |x| >= 65504
+        ws = ops.head_workspace(DEV)
+        ws.clear_flag()
         eng.prompts.tc_flag.zero_()
         eng.eval_logits(store.__class__.from_bags(bags, labels, DEV), prm)
-        assert int(eng.prompts.tc_flag.item()) != 0
+        assert ws.overflowed() or int(eng.prompts.tc_flag.item()) != 0
+        assert (int(eng.prompts.tc_flag.item()) != 0) == (big >= 65504)
     for i, x in enumerate(bags):
         ref = O.slide_eval_logits(oprm, x, w, we, c, j, k)
         close(got[i:i + 1], ref, rtol=1e-3, atol=1e-5)
