@@ -13,15 +13,16 @@ python tools/time_loops.py > gpurun_out/${TAG}_time_loops.log 2>&1
 SMALL="--slides 200 --steps 2 --warmup 3 --no-cpu-baseline --no-e2e"
 SMALL4="--workload cfg4 --slides 80 --steps 2 --warmup 3 --no-cpu-baseline --no-e2e"
 SMALLB="--workload cfg3bank --slides 200 --steps 2 --warmup 3 --no-cpu-baseline --no-e2e"
-python bench.py $SMALL > gpurun_out/plain2.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -k "$KREGEX" -c 100 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py $SMALL > gpurun_out/ncu_l.log 2>&1
-python bench.py $SMALL4 > gpurun_out/plain4.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -k "$KREGEX" -c 100 --csv --log-file gpurun_out/${TAG}_launches_cfg4.csv python bench.py $SMALL4 > gpurun_out/ncu_l4.log 2>&1
+FULL="--steps 1 --warmup 3 --no-cpu-baseline --no-e2e"     # launch lists at the full size of the bench lines
+python bench.py $FULL > gpurun_out/plain2.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none -k "$KREGEX" -c 60 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py $FULL > gpurun_out/ncu_l.log 2>&1
+python bench.py --workload cfg4 $FULL > gpurun_out/plain4.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none -k "$KREGEX" -c 60 --csv --log-file gpurun_out/${TAG}_launches_cfg4.csv python bench.py --workload cfg4 $FULL > gpurun_out/ncu_l4.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:score_keys_regw -s 3 -c 1 -o gpurun_out/${TAG}_score -f python bench.py $SMALL > gpurun_out/ncu_s.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:head_rows_f16_kernel -s 3 -c 1 -o gpurun_out/${TAG}_head -f python bench.py $SMALL > gpurun_out/ncu_h.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:head_rows_f16t -s 3 -c 1 -o gpurun_out/${TAG}_head -f python bench.py $SMALL > gpurun_out/ncu_h.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:select_mark -s 3 -c 1 -o gpurun_out/${TAG}_select -f python bench.py $SMALL > gpurun_out/ncu_sel.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:score_keys_tc -s 3 -c 1 -o gpurun_out/${TAG}_score_tc -f python bench.py $SMALL4 > gpurun_out/ncu_stc.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:head_rows_tc -s 3 -c 1 -o gpurun_out/${TAG}_head_tc -f python bench.py $SMALL4 > gpurun_out/ncu_htc.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:head_rows_f16t -s 3 -c 1 -o gpurun_out/${TAG}_head_c30 -f python bench.py $SMALL4 > gpurun_out/ncu_htc.log 2>&1
 python bench.py $SMALLB > gpurun_out/plainb.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:score_bank_tc -s 3 -c 1 -o gpurun_out/${TAG}_score_bank -f python bench.py $SMALLB > gpurun_out/ncu_sb.log 2>&1
 for f in gpurun_out/${TAG}_bench_*.json; do python -c "
