@@ -1,16 +1,17 @@
 // Gate MLP of the head on the 5th-generation tensor cores with FP16x3 operands (fp32-accurate), W1 resident in
 // shared memory.  Same contract as head_tc.cu (senet's Linear(512,64) for every selected patch, main_moc.py:303, fused
-// with ReLU, the 64->4 layer, the sigmoid and the classifier-bank combination, main_moc.py:390-403); this is the
-// default for up to 8 classes; head_tc.cu (3xTF32) serves wider class sets and stays selectable with MOC_HEAD_IMPL=tf32.
+// with ReLU, the 64->4 layer, the sigmoid and the classifier-bank combination, main_moc.py:390-403).  Two kernels:
+// head_rows_f16t_kernel (further down; the default at every class count) keeps the split patch tile in TENSOR
+// memory, head_rows_f16_kernel (round 1's default, MOC_HEAD_A=smem) stages it in shared memory.  head_tc.cu (3xTF32)
+// serves features outside the FP16 split's range and stays selectable with MOC_HEAD_IMPL=tf32.
 //
 // Why: an M128 N64 K8 tf32 MMA reads 6 KB of operands for 32 cycles of tensor work, more than the 128 B/clk the
 // SM's shared memory delivers, and the producers' stores and the W1 bulk copies share that port (measured on the
 // TF32 kernel: no loads -> same time, no MMAs -> -26 %, neither -> -45 %).  FP16 operands halve every one of those
 // byte streams per unit of K, halve the number of producer -> MMA hand-offs per row, and the whole split W1
 // (64 x 512 x 2 halves = 128 KB) then fits in shared memory once per CTA instead of being streamed from L2 for every
-// row tile.  Measured: 0.274 -> 0.225 ms per 200 NSCLC slides; at C = 30, where the epilogue's 62 key loads and 30
-// stores per row weigh more, the 256-row TF32 kernel is still ahead (1.28 vs 1.47 ms per 100 slides), so
-// moc_head_forward uses this kernel up to 8 classes and head_tc.cu beyond.
+// row tile.  Measured: 0.274 -> 0.225 ms per 200 NSCLC slides for the shared-memory-staged kernel, 0.164 ms with the A
+// operand in tensor memory.
 //
 // Precision: x * 2^4 = a0 + a1 and w * 2^SW = b0 + b1 with a0, b0 the nearest FP16 and a1, b1 the FP16 of the
 // remainder (exact to 2^-22 relative, or 2^-29 absolute on x where a1 becomes subnormal); D = a0 b0 + a0 b1 + a1 b0
@@ -412,7 +413,7 @@ head_rows_f16_kernel(const float* __restrict__ feat, const float* __restrict__ k
 }
 
 // =====================================================================================================
-// Variant with the A operand in TENSOR MEMORY (MOC_HEAD_IMPL=f16t; the default once validated on hardware).
+// The A operand in TENSOR MEMORY: the default gate kernel (MOC_HEAD_A=smem selects the kernel above).
 //
 // What bounds head_rows_f16_kernel is memory-level parallelism, not request size: tools/probe_gather_kblock.cu gathers
 // the same sparse rows K-block by K-block at 4.5 TB/s with 64 KB of loads in flight per SM (what 16 producer warps x
