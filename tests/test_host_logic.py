@@ -35,6 +35,10 @@ def test_sass_uses_bulk_copy_engine():
     out = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in out
     assert "UBLKCP" in out and "SYNCS" in out
+    # tensor-core paths: tcgen05.mma (UTC*MMA), accumulators read back (LDTM), TMA tensor copies (UTMALDG), the gate
+    # kernel's A operand written to tensor memory (STTM) and the register re-split between warp roles (USETMAXREG)
+    for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG", "STTM", "USETMAXREG"):
+        assert mnemonic in out, mnemonic
 
 
 def test_ops_fail_loudly_without_cuda():
