@@ -891,16 +891,10 @@ __host__ __device__ inline GateGeom gate_geom(int n_cols) {
     g.npa = g.hid0 + MOC_HIDDEN;
     return g;
 }
-// Seven warpgroups: key epilogue (warps 0-3), gate epilogue (4-7: the two halves of the epilogue run side by side - one
-// warp per scheduler doing both was the kernel's bottleneck at 3.8 TB/s), sixteen producers (8-23), and the group of the
-// MMA issuer (24) and the B loader (25).  Launched at 72 registers per thread (896 threads = 64 512 registers), which
-// setmaxnreg redistributes: keys 152, gate 64, producers 64, MMA group 32 - exactly the pool.
 constexpr int SG_PW = 16;
-constexpr int SG_EPI_WARPS = 8, SG_WARP_GATE = 4;
-constexpr int SG_WARP_MMA = SG_EPI_WARPS + SG_PW;    // 24; warp 25 loads B, 26-27 idle (setmaxnreg is warpgroup-wide)
-constexpr int SG_THREADS = (SG_WARP_MMA + 4) * 32;   // 896
+constexpr int SG_WARP_MMA = ST_EPI_WARPS + SG_PW;    // 20; warp 21 loads B, 22-23 idle (setmaxnreg is warpgroup-wide)
+constexpr int SG_THREADS = (SG_WARP_MMA + 4) * 32;   // 768
 constexpr int SG_ACC_COLS = 256;
-constexpr int SG_REGS_KEYS = 152, SG_REGS_GATE = 64, SG_REGS_PROD = 64, SG_REGS_MMA = 32;
 
 template <int NCHUNK>   // NCHUNK = ceil(prompt columns / 32): 1 or 2
 __global__ void __launch_bounds__(SG_THREADS, 1)
@@ -937,7 +931,7 @@ score_gate_tc_kernel(const __grid_constant__ CUtensorMap feat_map, int64_t n_row
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull_bar[a], 1);
-            mbar_init(&tempty_bar[a], SG_EPI_WARPS);
+            mbar_init(&tempty_bar[a], ST_EPI_WARPS);
         }
         for (int w = 0; w < SG_PW; ++w)
             for (int s = 0; s < ring_slots; ++s) mbar_init(&raw_bar[w][s], 1);
@@ -956,10 +950,10 @@ score_gate_tc_kernel(const __grid_constant__ CUtensorMap feat_map, int64_t n_row
     const int64_t n_tiles = (n_rows + ST_M - 1) / ST_M;
     const int64_t my_tiles = (int64_t)blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
-    if (warp >= SG_EPI_WARPS && warp < SG_WARP_MMA) {
+    if (warp >= ST_EPI_WARPS && warp < SG_WARP_MMA) {
         // =============================== producers (as score_keys_tc_kernel<..., 16>) ================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(SG_REGS_PROD));
-        const int pw = warp - SG_EPI_WARPS, rhalf = lane >> 4, q = lane & 15;
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(ST_REGS_PROD16));
+        const int pw = warp - ST_EPI_WARPS, rhalf = lane >> 4, q = lane & 15;
         const uint64_t policy = l2_policy_evict_first();
         const uint32_t ring = smem_u32(rawsm) + (uint32_t)(pw * ring_slots * ST_SLOT_BYTES);
         const uint32_t bars = smem_u32(&raw_bar[pw][0]);
@@ -1009,7 +1003,7 @@ score_gate_tc_kernel(const __grid_constant__ CUtensorMap feat_map, int64_t n_row
             if (++stage == ST_A_STAGES) { stage = 0; parity ^= 1u; }
         }
     } else if (warp >= SG_WARP_MMA) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(SG_REGS_MMA));
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(ST_REGS_MMA16));
         if (warp == SG_WARP_MMA + 1) {
             // =============================== B loader: one K-block tile of the image per step ===========
             if (lane == 0) {
@@ -1065,20 +1059,20 @@ score_gate_tc_kernel(const __grid_constant__ CUtensorMap feat_map, int64_t n_row
                 if (++acc == 2) { acc = 0; acc_parity ^= 1u; }
             }
         }
-    } else if (warp >= SG_WARP_GATE) {
-        // =============================== gate epilogue (warps 4-7): thread = patch ===================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(SG_REGS_GATE));
+    } else {
+        // =============================== epilogue (warps 0-3): thread = patch ========================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(ST_REGS_EPI16));
+        const int C = n_classes, n_cols = g.n_cols;
         const float descale = tail->descale;
-        const int quad = warp & 3;
         int acc = 0;
         uint32_t acc_parity = 0;
         bool bad = false;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int64_t row = tile * ST_M + quad * 32 + lane;
+            const int64_t row = tile * ST_M + warp * 32 + lane;
             mbar_wait(&tfull_bar[acc], acc_parity);
             st_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * SG_ACC_COLS;
-            // hidden unit j = accumulator columns hid0 + j and npa + hid0 + j
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * SG_ACC_COLS;
+            // gate: hidden unit j = accumulator columns hid0 + j and npa + hid0 + j
             float z[MOC_GATES] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int q = 0; q < MOC_HIDDEN / 16; ++q) {
@@ -1093,31 +1087,6 @@ score_gate_tc_kernel(const __grid_constant__ CUtensorMap feat_map, int64_t n_row
                     for (int m = 0; m < MOC_GATES; ++m) z[m] = fmaf(h, w2s[m * MOC_HIDDEN + j], z[m]);
                 }
             }
-            st_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-            if (++acc == 2) { acc = 0; acc_parity ^= 1u; }
-            if (row >= n_rows) continue;
-            const float probe = (z[0] + z[1] + z[2] + z[3]) * 0.f;
-            bad |= (probe != probe);
-            *reinterpret_cast<float4*>(gates + row * MOC_GATES) =
-                make_float4(sigmoidf_exact(z[0] + b2s[0]), sigmoidf_exact(z[1] + b2s[1]), sigmoidf_exact(z[2] + b2s[2]),
-                            sigmoidf_exact(z[3] + b2s[3]));
-        }
-        if (bad) atomicExch(&tail->flag, 1);
-    } else {
-        // =============================== key epilogue (warps 0-3): thread = patch ====================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(SG_REGS_KEYS));
-        const int C = n_classes, n_cols = g.n_cols;
-        const float descale = tail->descale;
-        int acc = 0;
-        uint32_t acc_parity = 0;
-        bool bad = false;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int64_t row = tile * ST_M + warp * 32 + lane;
-            mbar_wait(&tfull_bar[acc], acc_parity);
-            st_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * SG_ACC_COLS;
             float v[NCHUNK * 32];
 #pragma unroll
             for (int q = 0; q < NCHUNK * 2; ++q) {
@@ -1134,7 +1103,10 @@ score_gate_tc_kernel(const __grid_constant__ CUtensorMap feat_map, int64_t n_row
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
             if (++acc == 2) { acc = 0; acc_parity ^= 1u; }
             if (row >= n_rows) continue;
-            float probe = 0.f;
+            float probe = fmaf(z[0] + z[1] + z[2] + z[3], 0.f, 0.f);
+            *reinterpret_cast<float4*>(gates + row * MOC_GATES) =
+                make_float4(sigmoidf_exact(z[0] + b2s[0]), sigmoidf_exact(z[1] + b2s[1]), sigmoidf_exact(z[2] + b2s[2]),
+                            sigmoidf_exact(z[3] + b2s[3]));
             float m1 = -INFINITY, m2 = -INFINITY, bsum = 0.f, bmax = -INFINITY;
             float* kp = keys + row;
 #pragma unroll
