@@ -436,8 +436,7 @@ def run_ours(a):
     rows_per_launch = sum(score_rows) / len(score_rows)
     achieved = rows_per_launch * 2048 / (avg_ms * 1e-3) / 1e9
     kernel = ("score_bank_tc_kernel" if bank is not None else
-              "score_keys_regw_kernel<%d>" % (N_CLASSES + 4) if eng.prompts.tc is None else
-              "score_gate_tc_kernel" if getattr(eng, "_gate_prompts", None) is not None else "score_keys_tc_kernel")
+              "score_keys_regw_kernel<%d>" % (N_CLASSES + 4) if eng.prompts.tc is None else "score_keys_tc_kernel")
     traffic = ncu_traffic_bytes(kernel, rows_per_launch)
     roofline = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,

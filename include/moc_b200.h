@@ -107,28 +107,6 @@ int moc_prepare_prompt_bank_tc(const float* bank, const int32_t* class_offsets, 
 int moc_score_keys_bank_tc(const float* feat, int64_t n_rows, const void* image, int n_classes, int n_prompts,
                            int n_bg, int normalize, float* keys, int64_t key_stride, void* stream);
 
-/* Scoring and GATE in one pass, for evaluation over wide prompt sets (9..64 columns): the first layer of senet
- * (main_moc.py:303) is 64 more columns of the scoring contraction - the scoring kernel already holds every patch as the
- * tensor cores' A operand - and the kernel's epilogue finishes the gate (ReLU, 64 -> 4, sigmoid; main_moc.py:304-312)
- * beside the keys.  gates [n_rows][4] (16-byte aligned) come out for EVERY patch; moc_head_combine then forms the gated
- * sums of the selected rows and pools them without touching the features (at 30 classes the selected rows are a
- * quarter of the bag, and gathering them cost a quarter of the pass).  The image holds the split prompts AND the split
- * W1: rebuild it (moc_prepare_gate_prompts_tc, a few small kernels) whenever W1 changed.  Results equal
- * moc_score_keys_tc + moc_head_forward within the usual tolerance; same |x| < 65504 range and flag convention. */
-size_t moc_gate_prompts_tc_bytes(int n_classes, int n_ext);
-size_t moc_gate_prompts_tc_flag_offset(int n_classes, int n_ext);
-int moc_prepare_gate_prompts_tc(const float* packed, int n_classes, int n_ext, const float* w1, void* image,
-                                size_t image_bytes, void* stream);
-int moc_score_keys_gates_tc(const float* feat, int64_t n_rows, const void* image, int n_classes, int n_ext,
-                            const float* b1, const float* w2, const float* b2, float* keys, int64_t key_stride,
-                            float* gates, void* stream);
-/* moc_head_forward without the gate MLP: `gates` [rows of feat][4] were computed by moc_score_keys_gates_tc.
- * gate_out (nullable) [S_total][4] receives the selected rows' gates; other outputs as moc_head_forward. */
-int moc_head_combine(const float* keys, int64_t key_stride, int n_classes, const int64_t* sel_base,
-                     const int32_t* sel_rows, const int32_t* sel_count, int n_slides, int64_t sel_capacity_total,
-                     const float* gates, unsigned active_mask, int topk, float* gate_out, float* final_scores,
-                     float* bag_logits, int32_t* pool_pos, void* stream);
-
 /* ---- a2 + selection keys: the streaming kernel ----------------------------
  * Replaces `feat @ zeroshot_weights`, `feat @ zeroshot_weights_ext`
  * (main_moc.py:336-337) and the per-row arithmetic of the four selectors

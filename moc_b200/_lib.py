@@ -41,11 +41,6 @@ SIGNATURES = {
     "moc_prompt_bank_tc_flag_offset": (sz, [i32, i32]),
     "moc_prepare_prompt_bank_tc": (i32, [p, p, i32, i32, p, i32, p, sz, p]),
     "moc_score_keys_bank_tc": (i32, [p, i64, p, i32, i32, i32, i32, p, i64, p]),
-    "moc_gate_prompts_tc_bytes": (sz, [i32, i32]),
-    "moc_gate_prompts_tc_flag_offset": (sz, [i32, i32]),
-    "moc_prepare_gate_prompts_tc": (i32, [p, i32, i32, p, p, sz, p]),
-    "moc_score_keys_gates_tc": (i32, [p, i64, p, i32, i32, p, p, p, p, i64, p, p]),
-    "moc_head_combine": (i32, [p, i64, i32, p, p, p, i32, i64, p, u32, i32, p, p, p, p, p]),
     "moc_score_keys": (i32, [p, i64, p, i32, i32, i32, p, i64, p]),
     "moc_score_keys_ex": (i32, [p, i64, p, i32, i32, i32, p, i64, i32, p]),
     "moc_prompts_tc_bytes": (sz, [i32, i32]),

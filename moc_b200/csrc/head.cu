@@ -21,10 +21,6 @@ int launch_head_rows_tc(const float* feat, const float* keys, int64_t key_stride
                         int64_t n_slots, const float* w1, const float* b1, const float* w2, const float* b2,
                         unsigned active_mask, float* gate, float* final_scores, void* workspace, cudaStream_t st);
 
-// score_tc.cu: gated combination from precomputed gates (the fused scoring + gate kernel's second half)
-int launch_head_combine(const float* keys, int64_t key_stride, int C, const int32_t* sel_rows, int64_t n_slots,
-                        const float* gates, unsigned active_mask, float* gate_out, float* final_scores, cudaStream_t st);
-
 // head_f16.cu: the tcgen05 FP16x3 implementation (default): half the shared-memory bytes per unit of K, W1 resident
 size_t head_f16_workspace_bytes();
 int launch_head_rows_f16(const float* feat, const float* keys, int64_t key_stride, int C, const int32_t* sel_rows,
@@ -734,24 +730,6 @@ extern "C" int moc_head_forward(const float* feat, const float* keys, int64_t ke
         if (rc != MOC_OK) return rc;
     }
     return MOC_OK;
-}
-
-extern "C" int moc_head_combine(const float* keys, int64_t key_stride, int n_classes, const int64_t* sel_base,
-                                const int32_t* sel_rows, const int32_t* sel_count, int n_slides,
-                                int64_t sel_capacity_total, const float* gates, unsigned active_mask, int topk,
-                                float* gate_out, float* final_scores, float* bag_logits, int32_t* pool_pos, void* stream) {
-    MOC_CHECK_ARG(keys && sel_base && sel_rows && sel_count && gates && final_scores && bag_logits,
-                  "moc_head_combine: null pointer");
-    MOC_CHECK_ARG(n_slides >= 0 && sel_capacity_total >= 0 && topk >= 1, "moc_head_combine: bad sizes");
-    MOC_CHECK_SHAPE(n_classes >= 2 && n_classes < MOC_MAX_COLS, "moc_head_combine: bad class count %d", n_classes);
-    if (n_slides == 0) return MOC_OK;
-    cudaStream_t st = (cudaStream_t)stream;
-    {
-        const int rc = launch_head_combine(keys, key_stride, n_classes, sel_rows, sel_capacity_total, gates, active_mask,
-                                           gate_out, final_scores, st);
-        if (rc != MOC_OK) return rc;
-    }
-    return launch_pool_final(final_scores, sel_base, sel_count, n_slides, n_classes, topk, bag_logits, pool_pos, st);
 }
 
 extern "C" int moc_cross_entropy(const float* bag_logits, const int64_t* labels, int n_slides, int n_classes,

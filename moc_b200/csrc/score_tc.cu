@@ -149,16 +149,11 @@ __host__ __device__ inline ScoreTcGeom score_tc_geom(int n_cols) {
 }
 
 // One block: SW = 14 - floor(log2(max|w|)), so that max|w| * 2^SW lies in [2^14, 2^15).
-__global__ void score_tc_scale_kernel(const float* __restrict__ packed, int n, ScoreTcTail* __restrict__ tail,
-                                      const float* __restrict__ more = nullptr, int n_more = 0) {
+__global__ void score_tc_scale_kernel(const float* __restrict__ packed, int n, ScoreTcTail* __restrict__ tail) {
     __shared__ float red[32];
     float m = 0.f;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const float a = fabsf(packed[i]);
-        if (a <= 3.0e38f) m = fmaxf(m, a);
-    }
-    for (int i = threadIdx.x; i < n_more; i += blockDim.x) {   // a second matrix sharing the scale (the gate's W1)
-        const float a = fabsf(more[i]);
         if (a <= 3.0e38f) m = fmaxf(m, a);
     }
 #pragma unroll
@@ -180,14 +175,12 @@ __global__ void score_tc_scale_kernel(const float* __restrict__ packed, int n, S
 // packed fp32 K-major prompts [cols_pad][512] -> per K-block (64) tile of n_wide rows x 128 B: rows [0,npa) b0,
 // rows [npa, 2 npa) b1, 128B-swizzled, scaled by 2^SW (the image is zero-filled beforehand).
 __global__ void score_tc_prep_kernel(const float* __restrict__ packed, int n_cols, ScoreTcGeom g,
-                                     const ScoreTcTail* __restrict__ tail, unsigned char* __restrict__ out,
-                                     int row_off = 0) {
+                                     const ScoreTcTail* __restrict__ tail, unsigned char* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;  // (col n, 8-byte half-chunk of 4 k-elements)
     if (i >= n_cols * (D / 4)) return;
-    const int src = i / (D / 4), qq = i % (D / 4);
-    const int n = src + row_off;                          // tile row of this column (the gate's W1 sits after the prompts)
+    const int n = i / (D / 4), qq = i % (D / 4);
     const int kb = qq / 16, q = qq % 16;
-    const float4 v = reinterpret_cast<const float4*>(packed + (size_t)src * D)[qq];
+    const float4 v = reinterpret_cast<const float4*>(packed + (size_t)n * D)[qq];
     const float sc = tail->scale;
     uint2 c0, c1;
     split4(make_float4(v.x * sc, v.y * sc, v.z * sc, v.w * sc), c0, c1);
@@ -865,347 +858,6 @@ score_bank_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const float* 
     }
 }
 
-// =====================================================================================================
-// Scoring + GATE fused (evaluation passes over wide prompt sets, e.g. EBRAINS-30).
-//
-// At C = 30 a slide selects ~13 000 of its 50 000 patches, and the gate kernel's gather of those rows (26 % of the bag,
-// 10.7 GB per 400-slide pass) costs a quarter of the pass.  But the scoring kernel already has every patch, split into
-// FP16 halves, in shared memory as the tensor cores' A operand: the gate's first layer (senet's Linear(512, 64),
-// main_moc.py:303) is 64 more columns of the same contraction.  This kernel appends W1's rows to the prompt tile
-// ([prompts | pad to 16 | W1] = NPa columns; [b0 ; b1] = 2 NPa rows per K-block), streams that tile per K-block like the
-// bank kernel (it no longer fits shared memory for all eight K-blocks), and its epilogue finishes the gate
-// (ReLU, the 64 -> 4 layer, sigmoid) next to the key arithmetic: 16 more bytes per patch written, no gather at all -
-// head_combine_kernel then forms the gated sums of the selected rows from keys and gates alone.
-// Same producers (16 warps), same setmaxnreg split and the same two-MMA scheme as score_keys_tc_kernel<..., 16>.
-struct GateGeom {
-    int n_cols;   // prompt columns
-    int hid0;     // first hidden column = prompt columns rounded up to 16
-    int npa;      // hid0 + 64: MMA width of a1 x b0, row of b1 inside a K-block tile
-    __host__ __device__ size_t tile_bytes() const { return (size_t)(2 * npa) * 128; }
-    __host__ __device__ size_t b_bytes() const { return (size_t)ST_NKB * tile_bytes(); }
-};
-__host__ __device__ inline GateGeom gate_geom(int n_cols) {
-    GateGeom g;
-    g.n_cols = n_cols;
-    g.hid0 = (n_cols + 15) & ~15;
-    g.npa = g.hid0 + MOC_HIDDEN;
-    return g;
-}
-constexpr int SG_PW = 16;
-constexpr int SG_WARP_MMA = ST_EPI_WARPS + SG_PW;    // 20; warp 21 loads B, 22-23 idle (setmaxnreg is warpgroup-wide)
-constexpr int SG_THREADS = (SG_WARP_MMA + 4) * 32;   // 768
-constexpr int SG_ACC_COLS = 256;
-
-template <int NCHUNK>   // NCHUNK = ceil(prompt columns / 32): 1 or 2
-__global__ void __launch_bounds__(SG_THREADS, 1)
-score_gate_tc_kernel(const __grid_constant__ CUtensorMap feat_map, int64_t n_rows, const unsigned char* __restrict__ image,
-                     int n_classes, GateGeom g, int ring_slots, const float* __restrict__ b1, const float* __restrict__ w2,
-                     const float* __restrict__ b2, float* __restrict__ keys, int64_t key_stride,
-                     float* __restrict__ gates, ScoreTcTail* __restrict__ tail) {
-    extern __shared__ unsigned char sg_smem_raw[];
-    __shared__ __align__(8) uint64_t full_bar[ST_A_STAGES], empty_bar[ST_A_STAGES], tfull_bar[2], tempty_bar[2];
-    __shared__ __align__(8) uint64_t bfull_bar[SB_B_STAGES], bempty_bar[SB_B_STAGES];
-    __shared__ __align__(8) uint64_t raw_bar[SG_PW][ST_MAX_SLOTS];
-    __shared__ uint32_t tmem_base_s;
-    __shared__ float w2s[MOC_GATES * MOC_HIDDEN], b1s[MOC_HIDDEN], b2s[MOC_GATES];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(sg_smem_raw) + 1023) & ~(uintptr_t)1023);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t tile_bytes = (uint32_t)g.tile_bytes();
-    unsigned char* bsm = smem;                                         // B ring: SB_B_STAGES K-block tiles
-    unsigned char* asm_ = smem + (size_t)SB_B_STAGES * tile_bytes;     // A stages (a0 | a1)
-    unsigned char* rawsm = asm_ + ST_A_STAGES * ST_STAGE_BYTES;        // per-warp raw fp32 rings
-    constexpr int tmem_cols = 2 * SG_ACC_COLS;
-    constexpr int RPW = ST_M / SG_PW;                                  // 8 patches per producer warp and step
-
-    if (tid < MOC_GATES * MOC_HIDDEN) w2s[tid] = w2[tid];
-    if (tid < MOC_HIDDEN) b1s[tid] = b1[tid];
-    if (tid < MOC_GATES) b2s[tid] = b2[tid];
-    if (tid == 0) {
-        for (int s = 0; s < ST_A_STAGES; ++s) {
-            mbar_init(&full_bar[s], SG_PW);
-            mbar_init(&empty_bar[s], 1);
-        }
-        for (int s = 0; s < SB_B_STAGES; ++s) {
-            mbar_init(&bfull_bar[s], 1);
-            mbar_init(&bempty_bar[s], 1);
-        }
-        for (int a = 0; a < 2; ++a) {
-            mbar_init(&tfull_bar[a], 1);
-            mbar_init(&tempty_bar[a], ST_EPI_WARPS);
-        }
-        for (int w = 0; w < SG_PW; ++w)
-            for (int s = 0; s < ring_slots; ++s) mbar_init(&raw_bar[w][s], 1);
-        fence_mbar_init();
-    }
-    if (warp == SG_WARP_MMA) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
-                     "r"((uint32_t)tmem_cols)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    st_fence_before();
-    __syncthreads();
-    st_fence_after();
-    const uint32_t tmem_base = tmem_base_s;
-    const int64_t n_tiles = (n_rows + ST_M - 1) / ST_M;
-    const int64_t my_tiles = (int64_t)blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-
-    if (warp >= ST_EPI_WARPS && warp < SG_WARP_MMA) {
-        // =============================== producers (as score_keys_tc_kernel<..., 16>) ================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(ST_REGS_PROD16));
-        const int pw = warp - ST_EPI_WARPS, rhalf = lane >> 4, q = lane & 15;
-        const uint64_t policy = l2_policy_evict_first();
-        const uint32_t ring = smem_u32(rawsm) + (uint32_t)(pw * ring_slots * ST_SLOT_BYTES);
-        const uint32_t bars = smem_u32(&raw_bar[pw][0]);
-        int64_t i_tile = blockIdx.x, i_left = my_tiles * ST_NKB;
-        int i_kb = 0;
-        auto issue = [&](int pos) {
-            if (lane == 0) {
-                const int64_t row0 = i_tile * ST_M + pw * RPW;
-                const uint32_t bar = bars + pos * 8;
-                mbar_arrive_expect_tx_a(bar, ST_SLOT_BYTES);
-                tma_load_2d(ring + pos * ST_SLOT_BYTES, &feat_map, i_kb * ST_KB, (int)row0, bar, policy);
-            }
-            if (++i_kb == ST_NKB) { i_kb = 0; i_tile += gridDim.x; }
-            --i_left;
-        };
-        for (int s = 0; s < ring_slots; ++s)
-            if (i_left > 0) issue(s);
-        uint32_t roff[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int r = pw * RPW + i * 2 + rhalf;
-            roff[i] = (uint32_t)(r * 128 + (((q >> 1) ^ (r & 7)) << 4) + ((q & 1) << 3));
-        }
-        const uint32_t a_base = smem_u32(asm_);
-        const uint32_t lds_off = (uint32_t)(rhalf * (ST_KB * 4) + q * 16);
-        int stage = 0, pos = 0;
-        uint32_t parity = 0, rparity = 0;
-        for (int64_t step = 0; step < my_tiles * ST_NKB; ++step) {
-            uint2 c0[4], c1[4];
-            mbar_wait_a(bars + pos * 8, rparity);
-            const uint32_t sp = ring + pos * ST_SLOT_BYTES + lds_off;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) split4(lds128(sp + i * 2 * (ST_KB * 4)), c0[i], c1[i]);
-            __syncwarp();
-            if (i_left > 0) issue(pos);
-            if (++pos == ring_slots) { pos = 0; rparity ^= 1u; }
-            mbar_wait(&empty_bar[stage], parity ^ 1u);
-            const uint32_t a0 = a_base + stage * ST_STAGE_BYTES;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                sts64(a0 + roff[i], c0[i]);
-                sts64(a0 + ST_A_BYTES + roff[i], c1[i]);
-            }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&full_bar[stage]);
-            if (++stage == ST_A_STAGES) { stage = 0; parity ^= 1u; }
-        }
-    } else if (warp >= SG_WARP_MMA) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(ST_REGS_MMA16));
-        if (warp == SG_WARP_MMA + 1) {
-            // =============================== B loader: one K-block tile of the image per step ===========
-            if (lane == 0) {
-                const uint64_t policy = l2_policy_evict_last();
-                int bs = 0;
-                uint32_t bparity = 0;
-                for (int64_t step = 0; step < my_tiles * ST_NKB; ++step) {
-                    const int kb = (int)(step % ST_NKB);
-                    mbar_wait(&bempty_bar[bs], bparity ^ 1u);
-                    mbar_arrive_expect_tx(&bfull_bar[bs], tile_bytes);
-                    for (uint32_t o = 0; o < tile_bytes; o += 16384u)
-                        bulk_g2s(bsm + (size_t)bs * tile_bytes + o, image + (size_t)kb * tile_bytes + o,
-                                 tile_bytes - o < 16384u ? tile_bytes - o : 16384u, &bfull_bar[bs], policy);
-                    if (++bs == SB_B_STAGES) { bs = 0; bparity ^= 1u; }
-                }
-            }
-        } else if (warp == SG_WARP_MMA) {
-            // =============================== MMA issuer ================================================
-            const uint32_t idesc_wide = st_idesc_f16(2 * g.npa), idesc_narrow = st_idesc_f16(g.npa);
-            int stage = 0, acc = 0, bs = 0;
-            uint32_t parity = 0, acc_parity = 0, bparity = 0;
-            for (int64_t t = 0; t < my_tiles; ++t) {
-                if (lane == 0) {
-                    mbar_wait(&tempty_bar[acc], acc_parity ^ 1u);
-                    st_fence_after();
-                }
-                __syncwarp();
-                const uint32_t tmem_d = tmem_base + acc * SG_ACC_COLS;
-                for (int kb = 0; kb < ST_NKB; ++kb) {
-                    if (lane == 0) {
-                        mbar_wait(&full_bar[stage], parity);
-                        mbar_wait(&bfull_bar[bs], bparity);
-                        st_fence_after();
-                        const uint32_t a0 = smem_u32(asm_ + (size_t)stage * ST_STAGE_BYTES);
-                        const uint32_t a1 = a0 + ST_A_BYTES;
-                        const uint32_t bt = smem_u32(bsm + (size_t)bs * tile_bytes);
-#pragma unroll
-                        for (int ks = 0; ks < ST_KB / 16; ++ks) {
-                            const uint32_t o = ks * 32;
-                            const uint64_t da0 = st_desc_sw128(a0 + o), da1 = st_desc_sw128(a1 + o);
-                            const uint64_t db = st_desc_sw128(bt + o);
-                            umma_f16(tmem_d, da0, db, idesc_wide, (kb | ks) != 0 ? 1u : 0u);
-                            umma_f16(tmem_d, da1, db, idesc_narrow, 1u);
-                        }
-                        st_commit(&empty_bar[stage]);
-                        st_commit(&bempty_bar[bs]);
-                        if (kb == ST_NKB - 1) st_commit(&tfull_bar[acc]);
-                    }
-                    __syncwarp();
-                    if (++stage == ST_A_STAGES) { stage = 0; parity ^= 1u; }
-                    if (++bs == SB_B_STAGES) { bs = 0; bparity ^= 1u; }
-                }
-                if (++acc == 2) { acc = 0; acc_parity ^= 1u; }
-            }
-        }
-    } else {
-        // =============================== epilogue (warps 0-3): thread = patch ========================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(ST_REGS_EPI16));
-        const int C = n_classes, n_cols = g.n_cols;
-        const float descale = tail->descale;
-        int acc = 0;
-        uint32_t acc_parity = 0;
-        bool bad = false;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int64_t row = tile * ST_M + warp * 32 + lane;
-            mbar_wait(&tfull_bar[acc], acc_parity);
-            st_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * SG_ACC_COLS;
-            // gate: hidden unit j = accumulator columns hid0 + j and npa + hid0 + j
-            float z[MOC_GATES] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int q = 0; q < MOC_HIDDEN / 16; ++q) {
-                float d0[16], d1[16];
-                st_tmem_ld16(taddr + g.hid0 + q * 16, d0);
-                st_tmem_ld16(taddr + g.npa + g.hid0 + q * 16, d1);
-#pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                    const int j = q * 16 + e;
-                    const float h = relu_nan(fmaf(d0[e] + d1[e], descale, b1s[j]));
-#pragma unroll
-                    for (int m = 0; m < MOC_GATES; ++m) z[m] = fmaf(h, w2s[m * MOC_HIDDEN + j], z[m]);
-                }
-            }
-            float v[NCHUNK * 32];
-#pragma unroll
-            for (int q = 0; q < NCHUNK * 2; ++q) {
-                if (q * 16 < n_cols) {
-                    float d0[16], d1[16];
-                    st_tmem_ld16(taddr + q * 16, d0);
-                    st_tmem_ld16(taddr + g.npa + q * 16, d1);
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) v[q * 16 + e] = (d0[e] + d1[e]) * descale;
-                }
-            }
-            st_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-            if (++acc == 2) { acc = 0; acc_parity ^= 1u; }
-            if (row >= n_rows) continue;
-            float probe = fmaf(z[0] + z[1] + z[2] + z[3], 0.f, 0.f);
-            *reinterpret_cast<float4*>(gates + row * MOC_GATES) =
-                make_float4(sigmoidf_exact(z[0] + b2s[0]), sigmoidf_exact(z[1] + b2s[1]), sigmoidf_exact(z[2] + b2s[2]),
-                            sigmoidf_exact(z[3] + b2s[3]));
-            float m1 = -INFINITY, m2 = -INFINITY, bsum = 0.f, bmax = -INFINITY;
-            float* kp = keys + row;
-#pragma unroll
-            for (int c0 = 0; c0 < NCHUNK * 32; c0 += 8) {
-                if (c0 < n_cols) {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const int c = c0 + e;
-                        const float x = v[c];
-                        if (c < C) {
-                            probe = fmaf(x, 0.f, probe);
-                            m2 = fmaxf(m2, fminf(m1, x));
-                            m1 = fmaxf(m1, x);
-                            kp[(int64_t)c * key_stride] = x;
-                        } else if (c < n_cols) {
-                            probe = fmaf(x, 0.f, probe);
-                            bsum += x;
-                            bmax = fmaxf(bmax, x);
-                        }
-                    }
-                }
-            }
-            bad |= (probe != probe);
-            float esum = 0.f;
-#pragma unroll
-            for (int c0 = 0; c0 < NCHUNK * 32; c0 += 8) {
-                if (c0 < C) {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        if (c0 + e < C) {
-                            v[c0 + e] = expf(v[c0 + e] - m1);
-                            esum += v[c0 + e];
-                        }
-                    }
-                }
-            }
-            const float inv_sum = 1.0f / esum;
-            float* ks = kp + (int64_t)C * key_stride;
-#pragma unroll
-            for (int c0 = 0; c0 < NCHUNK * 32; c0 += 8) {
-                if (c0 < C) {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e)
-                        if (c0 + e < C) ks[(int64_t)(c0 + e) * key_stride] = v[c0 + e] * inv_sum;
-                }
-            }
-            kp[(int64_t)(2 * C) * key_stride] = fabsf(m1 - m2);
-            kp[(int64_t)(2 * C + 1) * key_stride] = bsum;
-            kp[(int64_t)(2 * C + 2) * key_stride] = bmax;
-        }
-        if (bad) atomicExch(&tail->flag, 1);
-    }
-
-    st_fence_before();
-    __syncthreads();
-    if (warp == SG_WARP_MMA) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)tmem_cols)
-                     : "memory");
-    }
-}
-
-// Gated combination of the selected rows from keys and precomputed gates (no feature access): thread = selected slot.
-__global__ void head_combine_kernel(const float* __restrict__ keys, int64_t key_stride, int C,
-                                    const int32_t* __restrict__ sel_rows, int64_t n_slots, const float* __restrict__ gates,
-                                    unsigned active_mask, float* __restrict__ gate_out, float* __restrict__ final_scores) {
-    const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot >= n_slots) return;
-    const int32_t row = sel_rows[slot];
-    if (row < 0) return;
-    const float4 g = *reinterpret_cast<const float4*>(gates + (int64_t)row * MOC_GATES);
-    if (gate_out != nullptr) *reinterpret_cast<float4*>(gate_out + slot * MOC_GATES) = g;
-    const float a0 = (active_mask & MOC_CLS_TOPK) ? 1.f : 0.f;
-    const float a1 = (active_mask & MOC_CLS_DELTA_SOFTMAX) ? 1.f : 0.f;
-    const float a2 = (active_mask & MOC_CLS_DELTA_DIFF) ? 1.f : 0.f;
-    const float a3 = (active_mask & MOC_CLS_BOTTOMK) ? 1.f : 0.f;
-    const float* kp = keys + row;
-    const float dlt = kp[(int64_t)(2 * C) * key_stride];
-    const float bgm = kp[(int64_t)(2 * C + 2) * key_stride];
-    for (int c0 = 0; c0 < C; c0 += 4) {
-        float lt[4], ls[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int cc = c0 + u < C ? c0 + u : C - 1;
-            lt[u] = kp[(int64_t)cc * key_stride];
-            ls[u] = kp[(int64_t)(C + cc) * key_stride];
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            if (c0 + u < C) {
-                float f = a0 * __fmul_rn(g.x, lt[u]);
-                f = __fadd_rn(f, a1 * __fmul_rn(g.y, ls[u]));
-                f = __fadd_rn(f, a2 * __fmul_rn(g.z, dlt));
-                f = __fadd_rn(f, a3 * __fmul_rn(g.w, bgm));
-                final_scores[slot * C + c0 + u] = f;
-            }
-        }
-    }
-}
-
 // feat viewed as a 2-D fp32 tensor [n_rows][512]; box = one raw slot (ST_SLOT_ROWS patches x ST_KB floats).
 static int make_feat_map(CUtensorMap* map, const float* feat, int64_t n_rows) {
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -1300,38 +952,6 @@ static int launch_bank(const float* feat, int64_t n_rows, const unsigned char* i
     return MOC_OK;
 }
 
-template <int NCHUNK>
-static int launch_gate(const float* feat, int64_t n_rows, const unsigned char* image, int C, const GateGeom& g,
-                       const float* b1, const float* w2, const float* b2, float* keys, int64_t key_stride, float* gates,
-                       cudaStream_t st) {
-    const size_t budget = 227 * 1024 - 1024 - 3072;  // alignment slack, static shared memory (barriers, W2, biases)
-    const size_t fixed = (size_t)SB_B_STAGES * g.tile_bytes() + (size_t)ST_A_STAGES * ST_STAGE_BYTES;
-    int ring_slots = fixed < budget ? (int)((budget - fixed) / ((size_t)SG_PW * ST_SLOT_BYTES)) : 0;
-    if (ring_slots > ST_MAX_SLOTS) ring_slots = ST_MAX_SLOTS;
-    MOC_CHECK_SHAPE(ring_slots >= 2, "moc_score_keys_gates_tc: %d prompt columns do not fit the fused kernel", g.n_cols);
-    const size_t smem = fixed + (size_t)ring_slots * SG_PW * ST_SLOT_BYTES + 1024;
-    MOC_CUDA(cudaFuncSetAttribute(score_gate_tc_kernel<NCHUNK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int64_t n_tiles = (n_rows + ST_M - 1) / ST_M;
-    const int grid = (int)(n_tiles < sm_count() ? n_tiles : sm_count());
-    ScoreTcTail* tail = reinterpret_cast<ScoreTcTail*>(const_cast<unsigned char*>(image) + g.b_bytes());
-    CUtensorMap map;
-    const int rc = make_feat_map(&map, feat, n_rows);
-    if (rc != MOC_OK) return rc;
-    score_gate_tc_kernel<NCHUNK><<<grid, SG_THREADS, smem, st>>>(map, n_rows, image, C, g, ring_slots, b1, w2, b2, keys,
-                                                                key_stride, gates, tail);
-    MOC_LAUNCH_CHECK("score_gate_tc_kernel");
-    return MOC_OK;
-}
-
-int launch_head_combine(const float* keys, int64_t key_stride, int C, const int32_t* sel_rows, int64_t n_slots,
-                        const float* gates, unsigned active_mask, float* gate_out, float* final_scores, cudaStream_t st) {
-    if (n_slots == 0) return MOC_OK;
-    head_combine_kernel<<<(unsigned)((n_slots + 255) / 256), 256, 0, st>>>(keys, key_stride, C, sel_rows, n_slots, gates,
-                                                                          active_mask, gate_out, final_scores);
-    MOC_LAUNCH_CHECK("head_combine_kernel");
-    return MOC_OK;
-}
-
 static int bank_args_ok(int n_classes, int n_prompts, int n_bg) {
     MOC_CHECK_SHAPE(n_classes >= 2 && n_classes <= MOC_BANK_MAX_CLASSES,
                     "prompt bank: 2..%d classes supported, got %d", MOC_BANK_MAX_CLASSES, n_classes);
@@ -1402,63 +1022,6 @@ extern "C" int moc_score_keys_bank_tc(const float* feat, int64_t n_rows, const v
     const unsigned char* p = reinterpret_cast<const unsigned char*>(image);
     return normalize ? launch_bank<true>(feat, n_rows, p, n_classes, g, keys, key_stride, (cudaStream_t)stream)
                      : launch_bank<false>(feat, n_rows, p, n_classes, g, keys, key_stride, (cudaStream_t)stream);
-}
-
-extern "C" size_t moc_gate_prompts_tc_bytes(int n_classes, int n_ext) {
-    (void)n_classes;
-    if (n_ext < 1 || n_ext > MOC_MAX_COLS) return 0;
-    return gate_geom(n_ext).b_bytes() + sizeof(ScoreTcTail);
-}
-
-extern "C" size_t moc_gate_prompts_tc_flag_offset(int n_classes, int n_ext) {
-    (void)n_classes;
-    return gate_geom(n_ext).b_bytes() + offsetof(ScoreTcTail, flag);
-}
-
-extern "C" int moc_prepare_gate_prompts_tc(const float* packed, int n_classes, int n_ext, const float* w1, void* image,
-                                           size_t image_bytes, void* stream) {
-    MOC_CHECK_ARG(packed && w1 && image, "moc_prepare_gate_prompts_tc: null pointer");
-    MOC_CHECK_SHAPE(n_classes >= 2 && n_ext > n_classes && n_ext <= MOC_MAX_COLS,
-                    "moc_prepare_gate_prompts_tc: need 2 <= C < C_ext <= %d, got C=%d C_ext=%d", MOC_MAX_COLS, n_classes,
-                    n_ext);
-    MOC_CHECK_ARG((reinterpret_cast<uintptr_t>(image) & 15) == 0, "moc_prepare_gate_prompts_tc: image must be 16-byte aligned");
-    if (image_bytes < moc_gate_prompts_tc_bytes(n_classes, n_ext)) {
-        set_error("moc_prepare_gate_prompts_tc: image needs %zu bytes, got %zu", moc_gate_prompts_tc_bytes(n_classes, n_ext),
-                  image_bytes);
-        return MOC_E_WORKSPACE;
-    }
-    cudaStream_t st = (cudaStream_t)stream;
-    const GateGeom g = gate_geom(n_ext);
-    unsigned char* out = reinterpret_cast<unsigned char*>(image);
-    ScoreTcTail* tail = reinterpret_cast<ScoreTcTail*>(out + g.b_bytes());
-    MOC_CUDA(cudaMemsetAsync(out, 0, g.b_bytes(), st));
-    score_tc_scale_kernel<<<1, 1024, 0, st>>>(packed, n_ext * D, tail, w1, MOC_HIDDEN * D);   // one scale for both
-    MOC_LAUNCH_CHECK("score_tc_scale_kernel");
-    ScoreTcGeom tg;
-    tg.npa = g.npa;
-    tg.n_wide = 2 * g.npa;
-    tg.n_narrow = g.npa;
-    score_tc_prep_kernel<<<(n_ext * (D / 4) + 255) / 256, 256, 0, st>>>(packed, n_ext, tg, tail, out, 0);
-    MOC_LAUNCH_CHECK("score_tc_prep_kernel");
-    score_tc_prep_kernel<<<(MOC_HIDDEN * (D / 4) + 255) / 256, 256, 0, st>>>(w1, MOC_HIDDEN, tg, tail, out, g.hid0);
-    MOC_LAUNCH_CHECK("score_tc_prep_kernel");
-    return MOC_OK;
-}
-
-extern "C" int moc_score_keys_gates_tc(const float* feat, int64_t n_rows, const void* image, int n_classes, int n_ext,
-                                       const float* b1, const float* w2, const float* b2, float* keys, int64_t key_stride,
-                                       float* gates, void* stream) {
-    MOC_CHECK_ARG(feat && image && b1 && w2 && b2 && keys && gates, "moc_score_keys_gates_tc: null pointer");
-    MOC_CHECK_ARG(n_rows >= 0 && key_stride >= n_rows, "moc_score_keys_gates_tc: bad n_rows / key_stride");
-    MOC_CHECK_SHAPE(n_classes >= 2 && n_ext > n_classes && n_ext <= MOC_MAX_COLS,
-                    "moc_score_keys_gates_tc: need 2 <= C < C_ext <= %d, got C=%d C_ext=%d", MOC_MAX_COLS, n_classes, n_ext);
-    MOC_CHECK_ARG((reinterpret_cast<uintptr_t>(feat) & 15) == 0 && (reinterpret_cast<uintptr_t>(gates) & 15) == 0,
-                  "moc_score_keys_gates_tc: feat and gates must be 16-byte aligned");
-    if (n_rows == 0) return MOC_OK;
-    const GateGeom g = gate_geom(n_ext);
-    const unsigned char* p = reinterpret_cast<const unsigned char*>(image);
-    return n_ext <= 32 ? launch_gate<1>(feat, n_rows, p, n_classes, g, b1, w2, b2, keys, key_stride, gates, (cudaStream_t)stream)
-                       : launch_gate<2>(feat, n_rows, p, n_classes, g, b1, w2, b2, keys, key_stride, gates, (cudaStream_t)stream);
 }
 
 extern "C" size_t moc_prompts_tc_bytes(int n_classes, int n_ext) {

@@ -14,7 +14,6 @@ again, like the reference.
 """
 from __future__ import annotations
 
-import os
 import weakref
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence
@@ -117,12 +116,6 @@ class MocEngine:
             if (w_from_bank - zeroshot_weights.float()).abs().max().item() > 1e-5:
                 raise _lib.MocError(_lib.E_ARG, "zeroshot_weights is not what the prompt bank collapses to")
         self.n_classes = self.prompts.n_classes
-        # wide prompt sets (tensor-core scoring): evaluation passes compute the gate of EVERY patch inside the scoring
-        # kernel (64 more columns of the same contraction) and never gather the selected rows (ops.GatePrompts)
-        self._gate_prompts = None
-        if (isinstance(self.prompts, ops.Prompts) and self.prompts.tc is not None and not normalize
-                and os.environ.get("MOC_FUSED_GATE", "1") != "0"):
-            self._gate_prompts = ops.GatePrompts(self.prompts)
         # slide_process never reads W_ext[:, :C] (only the background columns matter to it), but zs_evaluation with
         # bottomk_irrel_classifier_pooling pools (feats @ W_ext)[:, :C] (main_moc.py:428-432,
         # patch_selection_classifier.py:152-160).  In every shipped prompt file those columns equal W; when they do
@@ -289,8 +282,7 @@ class MocEngine:
 
     # ---- evaluation ----------------------------------------------------------------------------
     def eval_logits(self, store: RaggedBagStore, params: ops.HeadParams, mode: str = "eval",
-                    out: Optional[torch.Tensor] = None, check_domain: bool = False, allow_fused: bool = True
-                    ) -> torch.Tensor:
+                    out: Optional[torch.Tensor] = None, check_domain: bool = False) -> torch.Tensor:
         """Bag logits [n_slides, C] of every slide in the store under the current gate parameters.
 
         ``check_domain=True`` (what the loops pass; they read the logits back right afterwards): the fast kernels'
@@ -303,41 +295,21 @@ class MocEngine:
         act = _lib.active_bits(self.discard, mode)
         wide = self.is_wide(store)
         armed = check_domain and not wide
-        fused = allow_fused and self._gate_prompts is not None and not wide and not self.cache_scores
         if armed:
             ws = self._arm_flags(store.device)
-            if fused:
-                self._gate_prompts.flag.zero_()
         for lo, hi in self._waves(store):
+            keys = self.keys_for(store, lo, hi, wide)
             offs, offs_h, base, base_h = self._layout(store, lo, hi)
             feat = store.feat[store.offsets_h[lo]:store.offsets_h[hi]]
-            if fused:
-                keys, gates = self._score_gates(feat, params)
-                sel = ops.select_union(keys, offs, offs_h, c, self.topj, disc, None, base, base_h)
-                ho = ops.head_combine(keys, c, sel, gates, act, self.topk)
-            else:
-                keys = self.keys_for(store, lo, hi, wide)
-                sel = ops.select_union(keys, offs, offs_h, c, self.topj, disc, None, base, base_h)
-                ho = ops.head_forward(feat, keys, c, sel, params, act, self.topk, wide=wide)
+            sel = ops.select_union(keys, offs, offs_h, c, self.topj, disc, None, base, base_h)
+            ho = ops.head_forward(feat, keys, c, sel, params, act, self.topk, wide=wide)
             out[lo:hi] = ho.bag_logits
         if armed:
-            if self._flags_raised(ws) or (fused and int(self._gate_prompts.flag.item()) != 0):
+            if self._flags_raised(ws):
                 self._wide_stores[store] = True
                 return self.eval_logits(store, params, mode, out)
-            if not fused:       # the fused kernel's gate has the scoring range (65504), the stand-alone gate kernel 4094:
-                self._wide_stores.setdefault(store, False)   # only a pass through the latter clears a store for training
+            self._wide_stores.setdefault(store, False)
         return out
-
-    def _score_gates(self, feat: torch.Tensor, params: ops.HeadParams):
-        if self.score_events is None:
-            return ops.score_keys_gates(feat, self._gate_prompts, params)
-        self._gate_prompts.refresh(params)          # keep the image rebuild out of the timed scoring launch
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        r = ops.score_keys_gates(feat, self._gate_prompts, params)
-        b.record()
-        self.score_events.append((a, b, feat.size(0)))
-        return r
 
     def ablation_logits(self, store: RaggedBagStore, how: str, check_domain: bool = False) -> torch.Tensor:
         """Un-gated avg / sum / max of the four planes (ablation_evaluation, main_moc.py:523-582)."""
@@ -363,8 +335,8 @@ class MocEngine:
         """Decide, once per store, whether its features fit the fast kernels' range: one flag-checked evaluation pass
         over it (the few-shot training bags are a few dozen slides).  Every unmasked row is gated by that pass, and a
         masked training step only ever gates a subset of them.  Returns True when the range-free kernels are needed."""
-        if store not in self._wide_stores:      # through the kernels the training step itself uses (never the fused pass)
-            self.eval_logits(store, params, "train", check_domain=True, allow_fused=False)
+        if store not in self._wide_stores:
+            self.eval_logits(store, params, "train", check_domain=True)
         return self.is_wide(store)
 
     # ---- training ------------------------------------------------------------------------------
@@ -468,14 +440,9 @@ class MocEngine:
                 base_h = ops.selection_layout(ch.offsets_h, c, self.topj)
                 lay = (torch.tensor(base_h, dtype=torch.int64, device=dev), base_h)
                 per_host[(ci, self.topj)] = lay
-            if self._gate_prompts is not None:
-                keys, gates = self._score_gates(buf, params)
-                sel = ops.select_union(keys, ch.offsets, ch.offsets_h, c, self.topj, disc, None, lay[0], lay[1])
-                ho = ops.head_combine(keys, c, sel, gates, act, self.topk)
-            else:
-                keys = self._score(buf)
-                sel = ops.select_union(keys, ch.offsets, ch.offsets_h, c, self.topj, disc, None, lay[0], lay[1])
-                ho = ops.head_forward(buf, keys, c, sel, params, act, self.topk)
+            keys = self._score(buf)
+            sel = ops.select_union(keys, ch.offsets, ch.offsets_h, c, self.topj, disc, None, lay[0], lay[1])
+            ho = ops.head_forward(buf, keys, c, sel, params, act, self.topk)
             n = len(ch.offsets_h) - 1
             out[lo:lo + n] = ho.bag_logits
             lo += n

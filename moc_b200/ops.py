@@ -164,67 +164,6 @@ class BankPrompts:
                            image[off:off + 4].view(torch.int32))
 
 
-class GatePrompts:
-    """Prompt set + the gate's first layer in one tensor-core image (moc_prepare_gate_prompts_tc): what the fused
-    scoring + gate kernel of wide prompt sets reads.  Built once per (prompts, W1): ``refresh`` re-splits W1 when the
-    parameters changed (it compares the tensor's version counter and address)."""
-
-    def __init__(self, prompts: "Prompts"):
-        lib = _lib.load()
-        self.prompts = prompts
-        nb = lib.moc_gate_prompts_tc_bytes(prompts.n_classes, prompts.n_ext)
-        self.image = torch.empty(nb, dtype=torch.uint8, device=prompts.packed.device)
-        off = lib.moc_gate_prompts_tc_flag_offset(prompts.n_classes, prompts.n_ext)
-        self.flag = self.image[off:off + 4].view(torch.int32)
-        self._built_for = None
-
-    def refresh(self, params: "HeadParams") -> None:
-        key = (params.w1.data_ptr(), params.w1._version)
-        if key == self._built_for:
-            return
-        _count(4)
-        check(_lib.load().moc_prepare_gate_prompts_tc(self.prompts.packed.data_ptr(), self.prompts.n_classes,
-                                                      self.prompts.n_ext, params.w1.data_ptr(), self.image.data_ptr(),
-                                                      self.image.numel(), _stream()))
-        self._built_for = key
-
-
-def score_keys_gates(feat: torch.Tensor, gp: GatePrompts, params: "HeadParams",
-                     out: Optional[torch.Tensor] = None):
-    """(keys [2C+3, R], gates [R, 4]) for R rows of feat: scoring and the whole gate MLP in one pass over the bag."""
-    feat = _dev_f32(feat, "feat")
-    if feat.dim() != 2 or feat.size(1) != D:
-        raise MocError(_lib.E_SHAPE, "feat must be [rows,512], got %s" % (tuple(feat.shape),))
-    gp.refresh(params)
-    r = feat.size(0)
-    pr = gp.prompts
-    if out is None:
-        out = torch.empty(num_key_planes(pr.n_classes), r, device=feat.device, dtype=torch.float32)
-    gates = torch.empty(max(r, 1), GATES, device=feat.device, dtype=torch.float32)
-    _count(1)
-    check(_lib.load().moc_score_keys_gates_tc(feat.data_ptr(), r, gp.image.data_ptr(), pr.n_classes, pr.n_ext,
-                                              params.b1.data_ptr(), params.w2.data_ptr(), params.b2.data_ptr(),
-                                              out.data_ptr(), out.stride(0), gates.data_ptr(), _stream()))
-    return out, gates
-
-
-def head_combine(keys: torch.Tensor, n_classes: int, sel: "Selection", gates: torch.Tensor, active_mask: int, topk: int,
-                 want_gate: bool = False) -> "HeadOut":
-    """head_forward's second half for gates that were computed with the scores (score_keys_gates)."""
-    dev = keys.device
-    cap = max(sel.capacity, 1)
-    final = torch.empty(cap, n_classes, dtype=torch.float32, device=dev)
-    gate = torch.empty(cap, GATES, dtype=torch.float32, device=dev) if want_gate else None
-    bag = torch.empty(sel.n_slides, n_classes, dtype=torch.float32, device=dev)
-    pos = torch.empty(sel.n_slides, n_classes, topk, dtype=torch.int32, device=dev)
-    _count(2)
-    check(_lib.load().moc_head_combine(keys.data_ptr(), keys.stride(0), n_classes, sel.sel_base.data_ptr(),
-                                       sel.sel_rows.data_ptr(), sel.sel_count.data_ptr(), sel.n_slides, sel.capacity,
-                                       gates.data_ptr(), int(active_mask), int(topk), _ptr(gate), final.data_ptr(),
-                                       bag.data_ptr(), pos.data_ptr(), _stream()))
-    return HeadOut(final, bag, pos, gate, None)
-
-
 def num_key_planes(n_classes: int) -> int:
     return 2 * n_classes + 3
 
