@@ -51,14 +51,27 @@ def engine_for(args) -> MocEngine:
     return eng
 
 
+def _loader_iter_draw() -> None:
+    """What ``iter(DataLoader)`` does to the CPU default generator: one int64 draw for the iterator's base seed
+    (torch/utils/data/dataloader.py, _BaseDataLoaderIter.__init__; the same for num_workers 0 and 1).  Every loop of the
+    reference starts one iterator (``for ... in tqdm(loader)``, main_moc.py:380,:421,:472,:531), and train()'s half masks
+    come from the same generator (:330) - so a SEEDED reference run and a seeded run of these loops only draw the same
+    masks if the iterator's draw is mirrored, once per call, in the same place."""
+    torch.empty((), dtype=torch.int64).random_()
+
+
 def _store_of(loader, device) -> RaggedBagStore:
-    """The split as a resident store: directly, or by draining a generic loader once (cached on the dataset)."""
+    """The split as a resident store: directly, or by draining a generic loader once (cached on the dataset).
+    Consumes the CPU generator exactly as one ``iter(DataLoader)`` of the reference does."""
     ds = loader.dataset
     st = getattr(ds, "store", None)
     if st is not None:
+        _loader_iter_draw()
         return st
     st = getattr(ds, "_moc_b200_store", None)
-    if st is None:
+    if st is not None:
+        _loader_iter_draw()
+    if st is None:          # iterating the caller's own loader below makes the draw itself (if it is a DataLoader)
         keep = ds.repeat_num
         ds.repeat_num = ds.real_len()
         bags, labels, ids = [], [], []

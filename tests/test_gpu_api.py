@@ -345,3 +345,70 @@ def test_graph_captured_training_is_bit_identical_to_eager(golden):
     lg = M.train(model_g, tr, opt_g, DEV, a_g, masks=masks[:rep])
     le = M.train(model_e, tr, opt_e, DEV, a_e, masks=masks[:rep])
     assert torch.equal(lg, le) and all(torch.equal(pg, pe) for pg, pe in zip(model_g.parameters(), model_e.parameters()))
+
+
+def test_seeded_run_draws_the_reference_masks():
+    """A SEEDED run without explicit masks: the reference's loops consume the CPU generator once per
+    ``iter(DataLoader)`` (base seed) and once per training slide (``torch.rand(N) > 0.5``, main_moc.py:330).  Our loops
+    mirror both, so after the same ``torch.manual_seed`` a sequence train / evaluation / zs_evaluation / train gives the
+    parameters the reference's own functions give over a real torch DataLoader (lifted from oracle/_ref)."""
+    import types
+    import moc_b200 as M
+    from moc_b200 import loops, synthetic
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("the staged reference files (oracle/_ref) are not present")
+    c, j, k = 2, 64, 10
+    w, we = synthetic.prompt_matrices(c)
+    bags, labels = synthetic.make_cohort(4, [300, 350, 280, 320], c, cohort_seed=77)
+    rep = 6
+
+    class Split(torch.utils.data.Dataset):           # what Generic_Split looks like to the reference's loops
+        def __init__(self, repeat_num):
+            self.repeat_num = repeat_num
+
+        def real_len(self):
+            return len(bags)
+
+        def __len__(self):
+            return self.repeat_num if self.repeat_num else len(bags)
+
+        def __getitem__(self, idx):
+            if idx >= len(self):
+                raise IndexError
+            i = idx % len(bags)
+            return bags[i], labels[i], np.zeros((bags[i].size(0), 2), dtype=np.int64), "slide_%d" % i
+
+    args = types.SimpleNamespace(disable_tqdm=True, n_classes=c, topj=j, topk=k, discard_classifiers=[], pretrain="conch",
+                                 ablation_study="none", cache_scores=False)
+    ref = ref_loader.load()
+    ref.set_weights(w, we)
+    torch.manual_seed(21)
+    model_ref = ref.senet(512, 4)
+    init = {kk: v.clone() for kk, v in model_ref.state_dict().items()}
+    opt_ref = torch.optim.Adam(model_ref.parameters(), lr=1e-3, weight_decay=1e-4)
+    for workers in (0, 1):                             # the iterator's draw is the same with and without a worker
+        loader = torch.utils.data.DataLoader(Split(rep), batch_size=1, shuffle=False, num_workers=workers)
+        model_ref.load_state_dict(init)
+        opt_ref = torch.optim.Adam(model_ref.parameters(), lr=1e-3, weight_decay=1e-4)
+        torch.manual_seed(22)
+        ref.train(model_ref, loader, opt_ref, "cpu", args)
+        ev_ref = ref.evaluation(model_ref, loader, "cpu", args)
+        ref.zs_evaluation(loader, "cpu", args)
+        ref.train(model_ref, loader, opt_ref, "cpu", args)
+        want = {kk: v.clone() for kk, v in model_ref.state_dict().items()}
+
+        loops.set_prompts(w.to(DEV), we.to(DEV))
+        model = M.senet(512, 4)
+        model.load_state_dict(init)
+        model.to(DEV)
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4)
+        ours = M.BagLoader(M.BagDataset(M.RaggedBagStore.from_bags(bags, labels, DEV), repeat_num=rep))
+        torch.manual_seed(22)
+        M.train(model, ours, opt, DEV, args)
+        ev = M.evaluation(model, ours, DEV, args)
+        M.zs_evaluation(ours, DEV, args)
+        M.train(model, ours, opt, DEV, args)
+        assert ev["acc"] == ev_ref["acc"] and ev["auc"] == ev_ref["auc"] and abs(ev["loss"] - ev_ref["loss"]) < 5e-5
+        for kk, v in model.state_dict().items():
+            assert float((v.cpu() - want[kk]).abs().max()) < 2e-5, (workers, kk)
