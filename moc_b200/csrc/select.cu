@@ -12,6 +12,8 @@
 // version serves the stand-alone top-J / pooling kernels and degenerate columns.  The union of
 // the 2C+2 selections of a slide is a bitmap over its rows, so the ascending order of the reference's
 // sorted(set(...)) falls out of the compaction for free and nothing ever goes back to the host.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace moc {
@@ -330,6 +332,143 @@ __device__ bool select_rows_fast(const float* __restrict__ v, const uint8_t* __r
     return true;
 }
 
+// Expected size of the candidate set the sampled path aims for, and whether a column qualifies for it.
+__device__ __forceinline__ int sampled_target(int j) { return 3 * j + 400; }
+__device__ __forceinline__ bool sampled_applies(int n, int j) {
+    return n >= 8192 && sampled_target(j) <= 2560 && 4 * sampled_target(j) <= n;
+}
+
+// f(i, u) for every key of a contiguous unmasked column; 16-byte loads, FOUR in flight per thread (the column's first
+// touch comes from DRAM: with two, a CTA in its scan has 16 KB in flight, and the three CTAs of an SM are in a scan only
+// about half of the time).
+template <bool SMALLEST, typename F>
+__device__ __forceinline__ void scan_column4(const float* __restrict__ v, int n, F f) {
+    const int tid = threadIdx.x;
+    auto visit = [&](int i, float x) { f(i, sel_key<SMALLEST>(x)); };
+    int head = (4 - (int)((reinterpret_cast<uintptr_t>(v) >> 2) & 3)) & 3;
+    if (head > n) head = n;
+    if (tid < head) visit(tid, v[tid]);
+    const int n4 = (n - head) >> 2;
+    const float4* v4 = reinterpret_cast<const float4*>(v + head);
+    int k = tid;
+    for (; k + 3 * SEL_THREADS < n4; k += 4 * SEL_THREADS) {
+        const float4 a = __ldg(v4 + k), b = __ldg(v4 + k + SEL_THREADS), c = __ldg(v4 + k + 2 * SEL_THREADS),
+                     d = __ldg(v4 + k + 3 * SEL_THREADS);
+        const int ia = head + 4 * k, ib = ia + 4 * SEL_THREADS, ic = ib + 4 * SEL_THREADS, id = ic + 4 * SEL_THREADS;
+        visit(ia, a.x); visit(ia + 1, a.y); visit(ia + 2, a.z); visit(ia + 3, a.w);
+        visit(ib, b.x); visit(ib + 1, b.y); visit(ib + 2, b.z); visit(ib + 3, b.w);
+        visit(ic, c.x); visit(ic + 1, c.y); visit(ic + 2, c.z); visit(ic + 3, c.w);
+        visit(id, d.x); visit(id + 1, d.y); visit(id + 2, d.z); visit(id + 3, d.w);
+    }
+    for (; k < n4; k += SEL_THREADS) {
+        const float4 a = __ldg(v4 + k);
+        const int ia = head + 4 * k;
+        visit(ia, a.x); visit(ia + 1, a.y); visit(ia + 2, a.z); visit(ia + 3, a.w);
+    }
+    const int t0 = head + 4 * n4;
+    if (t0 + tid < n) visit(t0 + tid, v[t0 + tid]);
+}
+
+constexpr int FS_SMALL = 64;    // keys of the threshold bin ranked by brute force
+
+// ONE scan instead of three, for long unmasked columns and j << n (the evaluation pass: j = 400 of 20 000 - 100 000
+// patches, 2C + 2 selections per slide).  A CTA of the three-scan path spends its time in DRAM / L2 latency - three
+// dependent scans - and in a dozen block-wide histogram rounds; this path has one scan and two rounds:
+//   1. sample one 32-byte sector (8 keys) out of every `stride` keys, at most 4096 keys, into shared memory; one
+//      4096-bin histogram of the sample's own range gives the bin that holds the sample's key of rank r, r chosen so
+//      that about 3j + 400 keys of the whole column lie above that bin's lower edge t0 (independent draws would put
+//      the real count within +-10 % of it; sectors of neighbouring patches are correlated, hence the wide margins:
+//      anything in [j, 4096] is accepted);
+//   2. the scan parks every key >= t0 (with its row) in shared memory;
+//   3. if between j and FS_CAND keys were parked, the column's top j are the top j of those: one 4096-bin histogram
+//      of [t0, max] finds the threshold bin, keys above it are taken, and its (usually one to three) keys are ranked
+//      by brute force - ties at equal value to the lowest row indices, exactly like the other paths.
+// Returns false (block-uniform) with nothing emitted when the parked count falls outside [j, FS_CAND] or the threshold
+// bin is crowded with equal keys; the caller then runs the three-scan path.
+template <bool SMALLEST, typename Emit>
+__device__ bool select_rows_sampled(const float* __restrict__ v, int n, int j, SelShared& sh, FastShared& fs, Emit emit) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // ---- 1. sample, its range, one histogram round
+    int stride = 128;
+    if (n > 65536) stride = ((n + 511) / 512 + 7) & ~7;
+    const unsigned int m = (unsigned int)(n / stride) * 8u;             // <= 4096
+    uint32_t lo = 0xffffffffu, hi = 0u;
+    for (unsigned int c = tid; c < m; c += SEL_THREADS) {
+        const uint32_t u = sel_key<SMALLEST>(__ldg(v + (size_t)(c >> 3) * stride + (c & 7u)));
+        fs.cand[c].x = u;
+        lo = min(lo, u);
+        hi = max(hi, u);
+    }
+    for (int b = tid; b < FS_BINS; b += SEL_THREADS) fs.hist[b] = 0;
+    lo = __reduce_min_sync(FULL, lo);
+    hi = __reduce_max_sync(FULL, hi);
+    if (lane == 0) { sh.hist[warp] = lo; sh.hist[SEL_WARPS + warp] = hi; }
+    if (tid == 0) { sh.taken = 0; sh.n_kept = 0; }
+    __syncthreads();
+    for (int w = 0; w < SEL_WARPS; ++w) { lo = min(lo, sh.hist[w]); hi = max(hi, sh.hist[SEL_WARPS + w]); }
+    int bits = 32 - __clz(hi - lo);
+    int shift = bits > FS_BITS ? bits - FS_BITS : 0;
+    for (unsigned int c = tid; c < m; c += SEL_THREADS) atomicAdd(&fs.hist[(fs.cand[c].x - lo) >> shift], 1u);
+    __syncthreads();
+    unsigned int r = (unsigned int)(((int64_t)sampled_target(j) * m + n - 1) / n);
+    r = r < 1u ? 1u : (r > m ? m : r);
+    find_bin_desc<FS_BINS>(fs.hist, r, sh);
+    const uint32_t t0 = lo + (sh.prefix << shift);
+    __syncthreads();
+    for (int b = tid; b < FS_BINS; b += SEL_THREADS) fs.hist[b] = 0;    // for round 3; nobody reads it before the next barrier
+    // ---- 2. the scan
+    uint32_t mx = 0u;
+    scan_column4<SMALLEST>(v, n, [&](int i, uint32_t u) {
+        if (u >= t0) {
+            mx = max(mx, u);
+            const unsigned int slot = atomicAdd(&sh.taken, 1u);
+            if (slot < (unsigned int)FS_CAND) fs.cand[slot] = make_uint2(u, (unsigned int)i);
+        }
+    });
+    mx = __reduce_max_sync(FULL, mx);
+    if (lane == 0 && mx) atomicMax(&sh.n_kept, mx);
+    __syncthreads();
+    const unsigned int n_cand = sh.taken;
+    const uint32_t top = sh.n_kept;
+    if (n_cand < (unsigned int)j || n_cand > (unsigned int)FS_CAND) {
+        __syncthreads();
+        return false;
+    }
+    // ---- 3. threshold bin of [t0, top]
+    bits = 32 - __clz(top - t0);
+    shift = bits > FS_BITS ? bits - FS_BITS : 0;
+    for (unsigned int c = tid; c < n_cand; c += SEL_THREADS) atomicAdd(&fs.hist[(fs.cand[c].x - t0) >> shift], 1u);
+    __syncthreads();
+    find_bin_desc<FS_BINS>(fs.hist, (unsigned int)j, sh);
+    const uint32_t bin_lo = t0 + (sh.prefix << shift);
+    const uint32_t bin_hi = bin_lo + (shift == 0 ? 0u : ((1u << shift) - 1u));      // inclusive
+    const unsigned int need = sh.need, n_bin = sh.n_equal;
+    __syncthreads();
+    if (need == n_bin) {            // the whole threshold bin belongs to the top j
+        for (unsigned int c = tid; c < n_cand; c += SEL_THREADS)
+            if (fs.cand[c].x >= bin_lo) emit((int)fs.cand[c].y);
+        return true;
+    }
+    if (n_bin > (unsigned int)FS_SMALL) return false;
+    uint2* small = reinterpret_cast<uint2*>(fs.hist);                               // the histogram is done with
+    if (tid == 0) sh.taken = 0;
+    __syncthreads();
+    for (unsigned int c = tid; c < n_cand; c += SEL_THREADS) {
+        const uint2 e = fs.cand[c];
+        if (e.x > bin_hi) emit((int)e.y);
+        else if (e.x >= bin_lo) small[atomicAdd(&sh.taken, 1u)] = e;
+    }
+    __syncthreads();
+    if ((unsigned int)tid < n_bin) {
+        const uint2 e = small[tid];
+        unsigned int before = 0;
+        for (unsigned int d = 0; d < n_bin; ++d)
+            before += (small[d].x > e.x) || (small[d].x == e.x && small[d].y < e.y);
+        if (before < need) emit((int)e.y);
+    }
+    return true;
+}
+
 template <bool HAS_MASK>
 __device__ int count_kept(const uint8_t* __restrict__ mk, int n, SelShared& sh) {
     if (!HAS_MASK) return n;
@@ -348,7 +487,7 @@ template <bool HAS_MASK>
 __global__ void __launch_bounds__(SEL_THREADS, 3)   // 40 registers: three CTAs per SM (two: -20 %; four: worse at C = 30)
 select_mark_kernel(const float* __restrict__ keys, int64_t key_stride, const int64_t* __restrict__ offsets, int C,
                    int topj, unsigned discard_mask, const uint8_t* __restrict__ row_mask,
-                   unsigned int* __restrict__ bitmap) {
+                   unsigned int* __restrict__ bitmap, int sampled) {
     extern __shared__ __align__(16) unsigned char sel_dyn_smem[];
     FastShared& fs = *reinterpret_cast<FastShared*>(sel_dyn_smem);
     __shared__ SelShared sh;
@@ -373,6 +512,12 @@ select_mark_kernel(const float* __restrict__ keys, int64_t key_stride, const int
         atomicOr(&bitmap[r >> 5], 1u << (r & 31));
     };
     if (j > 0 && j < n_kept) {
+        if (!HAS_MASK && sampled && sampled_applies(n, j)) {
+            const bool done = smallest ? select_rows_sampled<true>(v, n, j, sh, fs, mark)
+                                       : select_rows_sampled<false>(v, n, j, sh, fs, mark);
+            if (done) return;
+            __syncthreads();
+        }
         const bool done = smallest ? select_rows_fast<true, HAS_MASK>(v, mk, n, j, sh, fs, mark)
                                    : select_rows_fast<false, HAS_MASK>(v, mk, n, j, sh, fs, mark);
         if (done) return;
@@ -623,19 +768,24 @@ extern "C" int moc_select_union(const float* keys, int64_t key_stride, const int
     unsigned int* bitmap = reinterpret_cast<unsigned int*>(workspace);
     MOC_CUDA(cudaMemsetAsync(bitmap, 0, need, st));
     const dim3 grid(n_slides, 2 * n_classes + 2);
+    static int sampled = -1;        // MOC_SELECT_SAMPLED=0: three-scan selection only (developer A/B switch)
+    if (sampled < 0) {
+        const char* e = getenv("MOC_SELECT_SAMPLED");
+        sampled = (e && e[0] == '0') ? 0 : 1;
+    }
     MOC_CUDA(cudaFuncSetAttribute(select_mark_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)sizeof(FastShared)));
     MOC_CUDA(cudaFuncSetAttribute(select_mark_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)sizeof(FastShared)));
     if (row_mask) {
         select_mark_kernel<true><<<grid, SEL_THREADS, sizeof(FastShared), st>>>(keys, key_stride, offsets, n_classes, topj, discard_mask,
-                                                              row_mask, bitmap);
+                                                              row_mask, bitmap, sampled);
         MOC_LAUNCH_CHECK("select_mark_kernel");
         compact_kernel<true><<<n_slides, CMP_THREADS, 0, st>>>(bitmap, offsets, row_mask, sel_base, sel_rows, sel_local,
                                                              sel_count);
     } else {
         select_mark_kernel<false><<<grid, SEL_THREADS, sizeof(FastShared), st>>>(keys, key_stride, offsets, n_classes, topj,
-                                                               discard_mask, nullptr, bitmap);
+                                                               discard_mask, nullptr, bitmap, sampled);
         MOC_LAUNCH_CHECK("select_mark_kernel");
         compact_kernel<false><<<n_slides, CMP_THREADS, 0, st>>>(bitmap, offsets, nullptr, sel_base, sel_rows, sel_local,
                                                               sel_count);

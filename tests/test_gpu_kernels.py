@@ -207,6 +207,56 @@ def test_select_union_ties_and_degenerate_columns(kind, masked):
             assert local[b:b + cnt[i]].tolist() == got
 
 
+@pytest.mark.parametrize("kind", ["normal", "sorted", "clumped", "spiky", "quantised", "few_distinct", "tiny_range"])
+@pytest.mark.parametrize("j", [10, 400, 720, 721])
+def test_select_union_one_scan_path(kind, j):
+    """Long unmasked columns take the sampled one-scan selection (select_rows_sampled: a provisional threshold from a
+    1/16 sample, one scan that parks everything above it, resolution on chip) and fall back to the three-scan path when
+    the parked count misses [j, 4096] or the threshold bin is crowded.  Whatever path a column takes the result is the
+    exact top-j set with ties to the lowest rows: sizes around the path's limits (8192, the 65 536 stride change), key
+    distributions that make the sample unrepresentative (sorted, clumped), stretch the histogram range (spiky) or tie
+    heavily (quantised, few_distinct).  j = 721 is past the path's limit (three scans)."""
+    from moc_b200 import ops
+    c = 2
+    sizes = [8191, 8192, 8193, 20000, 50001, 65536, 65537, 100003, 150000]
+    offs = [0]
+    for n in sizes:
+        offs.append(offs[-1] + n)
+    total = offs[-1]
+    rng = np.random.default_rng(sum(map(ord, kind)) * 1000 + j)
+    keys = rng.standard_normal((2 * c + 3, total)).astype(np.float32)
+    if kind == "sorted":
+        for i in range(len(sizes)):
+            keys[:, offs[i]:offs[i + 1]] = np.sort(keys[:, offs[i]:offs[i + 1]], axis=1)
+            keys[1::2, offs[i]:offs[i + 1]] = keys[1::2, offs[i]:offs[i + 1]][:, ::-1]
+    elif kind == "clumped":      # the largest (and smallest) keys sit in a few contiguous runs that straddle sample sectors
+        for i in range(len(sizes)):
+            lo, n = offs[i], sizes[i]
+            for p in range(keys.shape[0]):
+                for _ in range(3):
+                    a = int(rng.integers(0, n - 300))
+                    keys[p, lo + a + 8:lo + a + 8 + 250] += np.float32(4.0) * (1 if p != 2 * c + 1 else -1)
+    elif kind == "spiky":
+        idx = rng.integers(0, total, size=40)
+        keys[:, idx] *= np.float32(1e6)
+    elif kind == "quantised":
+        keys = np.round(keys, 2)
+    elif kind == "few_distinct":
+        keys = np.round(keys * 2).astype(np.float32)
+    elif kind == "tiny_range":
+        keys = (1.0 + keys * 1e-6).astype(np.float32)
+    kd = torch.from_numpy(np.ascontiguousarray(keys)).to(DEV)
+    offs_d = torch.tensor(offs, dtype=torch.int64, device=DEV)
+    sel = ops.select_union(kd, offs_d, offs, c, j, 0, None)
+    cnt = sel.sel_count.cpu().tolist()
+    rows = sel.sel_rows.cpu().numpy()
+    ref = _ref_union(keys, offs, c, j)
+    for i in range(len(sizes)):
+        b = sel.sel_base_h[i]
+        got = (rows[b:b + cnt[i]] - offs[i]).tolist()
+        assert got == ref[i], "slide %d (n=%d): %d vs %d rows" % (i, sizes[i], len(got), len(ref[i]))
+
+
 @pytest.mark.parametrize("name", SLIDE_CASES)
 def test_topj_sorted_golden(golden, name):
     """The selectors' public return value: sorted top-J indices per column."""
