@@ -26,6 +26,17 @@
  *       2C       |top1 - top2| of the row of L                    (_index.py:46-48)
  *       2C+1     sum of background similarities  Le[:, C:]        (_index.py:71-75)
  *       2C+2     max of background similarities  Le[:, C:]        (main_moc.py:365)
+ *    From MOC_KEYS_COMPACT_MIN_CLASSES classes on (EBRAINS-30) the C softmax planes are not stored: the scoring
+ *    kernels write C+4 planes
+ *       [0,C)    L[:,c]
+ *       C        lse = log sum_c exp(L[:,c])      (= max + log sum exp(L - max))
+ *       C+1      |top1 - top2|                    C+2   sum of background      C+3   max of background
+ *    and every consumer (gate / combination, backward, ablation, gather) forms softmax(L)[:,c] = expf(L[:,c] - lse)
+ *    on the fly (within 3e-7 relative of the stored form), while the softmax SELECTION ranks a slide's patches by
+ *    L[:,c] - lse, the logarithm of the same quantity: 136 instead of 252 bytes written per patch for 30 classes,
+ *    and two plane reads without an exponential per key in the selection.  moc_num_key_planes() and moc_key_plane()
+ *    give the counts and indices for a class count; moc_expand_keys() materialises the full 2C+3-plane layout from
+ *    either (what the stand-alone helpers and tests index directly).  moc_row_keys always writes the full layout.
  */
 #ifndef MOC_B200_H
 #define MOC_B200_H
@@ -43,6 +54,7 @@ extern "C" {
 #define MOC_MAX_COLS 64    /* C + number of background prompts, this build   */
 #define MOC_BANK_MAX_CLASSES 8   /* un-collapsed prompt bank: classes ...        */
 #define MOC_BANK_MAX_COLS 256    /* ... and bank prompts + background prompts    */
+#define MOC_KEYS_COMPACT_MIN_CLASSES 9   /* from here on keys are C+4 planes (above) */
 
 #define MOC_OK 0
 #define MOC_E_ARG (-1)        /* null pointer / negative size / bad flag      */
@@ -63,8 +75,21 @@ extern "C" {
 
 const char* moc_last_error(void);
 int moc_version(void);
-/* number of key planes for C classes: 2C+3 */
+/* number of key planes the scoring kernels write for C classes: 2C+3, or C+4 from MOC_KEYS_COMPACT_MIN_CLASSES on */
 int moc_num_key_planes(int n_classes);
+/* index of a named plane in that layout: which = MOC_PLANE_*; -1 when the layout does not store it (SOFTMAX0 in the
+ * compact layout, LSE in the full one).  SOFTMAX0 is the softmax plane of class 0 (class c: + c). */
+#define MOC_PLANE_TOP0 0
+#define MOC_PLANE_SOFTMAX0 1
+#define MOC_PLANE_DIFF 2
+#define MOC_PLANE_BG_SUM 3
+#define MOC_PLANE_BG_MAX 4
+#define MOC_PLANE_LSE 5
+int moc_key_plane(int n_classes, int which);
+/* keys (either layout, n_rows rows) -> the full 2C+3-plane layout in `full` (stride full_stride); a plain copy when
+ * the class count already uses it */
+int moc_expand_keys(const float* keys, int64_t key_stride, int n_classes, int64_t n_rows, float* full,
+                    int64_t full_stride, void* stream);
 
 /* ---- prompt matrices ------------------------------------------------------
  * Packs W [512,C] and the background columns of W_ext [512,C_ext] (both

@@ -27,6 +27,9 @@ class MocError(RuntimeError):
         self.code = code
 
 
+# named key planes (include/moc_b200.h: MOC_PLANE_*)
+PLANE_TOP0, PLANE_SOFTMAX0, PLANE_DIFF, PLANE_BG_SUM, PLANE_BG_MAX, PLANE_LSE = range(6)
+
 p, i32, i64, u32, f32, sz = C.c_void_p, C.c_int, C.c_int64, C.c_uint, C.c_float, C.c_size_t
 
 # name -> (restype, argtypes); must list every function include/moc_b200.h declares
@@ -34,6 +37,8 @@ SIGNATURES = {
     "moc_last_error": (C.c_char_p, []),
     "moc_version": (i32, []),
     "moc_num_key_planes": (i32, [i32]),
+    "moc_key_plane": (i32, [i32, i32]),
+    "moc_expand_keys": (i32, [p, i64, i32, i64, p, i64, p]),
     "moc_packed_cols": (i32, [i32, i32]),
     "moc_pack_prompts": (i32, [p, i32, p, i32, p, p]),
     "moc_collapse_prompt_bank": (i32, [p, p, i32, p, p]),

@@ -138,6 +138,89 @@ __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
         : "memory");
 }
 
+// ---- key-plane layout (include/moc_b200.h, top) ------------------------------------
+// full: [0,C) L | [C,2C) softmax | 2C diff | 2C+1 bg sum | 2C+2 bg max;  compact (C >= MOC_KEYS_COMPACT_MIN_CLASSES):
+// [0,C) L | C lse = log sum exp(L) | C+1 diff | C+2 bg sum | C+3 bg max.
+struct KeyLayout {
+    int n_planes, diff, bg_sum, bg_max;
+    int softmax0;       // full layout only (-1 otherwise)
+    int lse;            // compact layout only (-1 otherwise)
+    bool compact;
+};
+__host__ __device__ inline KeyLayout key_layout(int C) {
+    KeyLayout k;
+    k.compact = C >= MOC_KEYS_COMPACT_MIN_CLASSES;
+    if (k.compact) {
+        k.lse = C; k.diff = C + 1; k.bg_sum = C + 2; k.bg_max = C + 3;
+        k.softmax0 = -1; k.n_planes = C + 4;
+    } else {
+        k.softmax0 = C; k.diff = 2 * C; k.bg_sum = 2 * C + 1; k.bg_max = 2 * C + 2;
+        k.lse = -1; k.n_planes = 2 * C + 3;
+    }
+    return k;
+}
+// What a consumer needs of one row to form its softmax values: full layout - nothing (they are loaded); compact - lse.
+struct RowSoftmax {
+    float lse;
+    __device__ __forceinline__ float of(float l) const { return expf(l - lse); }
+};
+__device__ __forceinline__ RowSoftmax row_softmax_of(const float* __restrict__ kp, int64_t key_stride, const KeyLayout& kl) {
+    RowSoftmax r;
+    r.lse = kp[(int64_t)kl.lse * key_stride];
+    return r;
+}
+// the lse plane's value from the row maximum and sum exp(L - max) the scoring epilogues have at hand
+__device__ __forceinline__ float lse_of(float row_max, float exp_sum) { return row_max + logf(exp_sum); }
+
+// Gated combination of one selected row's four score planes for every class (main_moc.py:391-405): the association of
+// the reference, ((g0*L + g1*P) + g2*delta) + g3*bg, with no fma contraction.  KU classes per batch of key loads: every
+// load is a 32-byte sector of its own in a [planes, rows] array far larger than the L2, so with many classes the
+// dependent batches of DRAM latency were what a row tile waited for (C = 30 on the full layout, 62 loads per row:
+// four classes per batch 3.6 ms per 400 EBRAINS slides, eight 3.1 ms, sixteen 2.7 ms).
+template <int KU, bool COMPACT>
+__device__ __forceinline__ void combine_classes(const float* __restrict__ kp, int64_t key_stride, int C, RowSoftmax rs,
+                                                const float (&g)[4], float a0, float a1, float a2, float a3, float dlt,
+                                                float bgm, float* __restrict__ out) {
+    for (int c0 = 0; c0 < C; c0 += KU) {
+        float lt[KU], ls[COMPACT ? 1 : KU];
+#pragma unroll
+        for (int u = 0; u < KU; ++u) {
+            const int cc = c0 + u < C ? c0 + u : C - 1;
+            lt[u] = kp[(int64_t)cc * key_stride];
+            if (!COMPACT) ls[u] = kp[(int64_t)(C + cc) * key_stride];
+        }
+#pragma unroll
+        for (int u = 0; u < KU; ++u) {
+            if (c0 + u < C) {
+                float f = a0 * __fmul_rn(g[0], lt[u]);
+                f = __fadd_rn(f, a1 * __fmul_rn(g[1], COMPACT ? rs.of(lt[u]) : ls[u]));
+                f = __fadd_rn(f, a2 * __fmul_rn(g[2], dlt));
+                f = __fadd_rn(f, a3 * __fmul_rn(g[3], bgm));
+                out[c0 + u] = f;
+            }
+        }
+    }
+}
+#ifndef MOC_COMBINE_KU_COMPACT
+#define MOC_COMBINE_KU_COMPACT 16
+#endif
+// kp = keys + row, out = final_scores + slot * C
+__device__ __forceinline__ void combine_row(const float* __restrict__ kp, int64_t key_stride, int C, const float (&g)[4],
+                                            float a0, float a1, float a2, float a3, float* __restrict__ out) {
+    const KeyLayout kl = key_layout(C);
+    const float dlt = kp[(int64_t)kl.diff * key_stride];
+    const float bgm = kp[(int64_t)kl.bg_max * key_stride];
+    RowSoftmax rs = {0.f};
+    if (kl.compact) {
+        rs = row_softmax_of(kp, key_stride, kl);
+        combine_classes<MOC_COMBINE_KU_COMPACT, true>(kp, key_stride, C, rs, g, a0, a1, a2, a3, dlt, bgm, out);
+    } else if (C <= 4) {
+        combine_classes<4, false>(kp, key_stride, C, rs, g, a0, a1, a2, a3, dlt, bgm, out);
+    } else {
+        combine_classes<8, false>(kp, key_stride, C, rs, g, a0, a1, a2, a3, dlt, bgm, out);
+    }
+}
+
 // ---- order-preserving float <-> uint32 map (for radix selection) -------------
 __device__ __forceinline__ uint32_t f2ord(float f) {
     uint32_t u = __float_as_uint(f);

@@ -184,12 +184,17 @@ head_rows_kernel(const float* __restrict__ feat, const float* __restrict__ keys,
                 if (gate != nullptr && tx < G) gate[slot * G + tx] = tx == 0 ? g[0] : tx == 1 ? g[1] : tx == 2 ? g[2] : g[3];
                 if (final_scores == nullptr) continue;
                 const float* kp = keys + row;
-                const float dlt = kp[(int64_t)(2 * C) * key_stride];
-                const float bgm = kp[(int64_t)(2 * C + 2) * key_stride];
+                const KeyLayout kl = key_layout(C);
+                const float dlt = kp[(int64_t)kl.diff * key_stride];
+                const float bgm = kp[(int64_t)kl.bg_max * key_stride];
+                RowSoftmax rs = {0.f};
+                if (kl.compact) rs = row_softmax_of(kp, key_stride, kl);
                 for (int c = tx; c < C; c += 16) {
                     // same association as the reference: ((g0*L + g1*P) + g2*delta) + g3*bg, no fma contraction
-                    float f = a0 * __fmul_rn(g[0], kp[(int64_t)c * key_stride]);
-                    f = __fadd_rn(f, a1 * __fmul_rn(g[1], kp[(int64_t)(C + c) * key_stride]));
+                    const float lt = kp[(int64_t)c * key_stride];
+                    const float ls = kl.compact ? rs.of(lt) : kp[(int64_t)(C + c) * key_stride];
+                    float f = a0 * __fmul_rn(g[0], lt);
+                    f = __fadd_rn(f, a1 * __fmul_rn(g[1], ls));
                     f = __fadd_rn(f, a2 * __fmul_rn(g[2], dlt));
                     f = __fadd_rn(f, a3 * __fmul_rn(g[3], bgm));
                     final_scores[slot * C + c] = f;
@@ -490,11 +495,13 @@ head_bwd_rows_kernel(const float* __restrict__ feat, const float* __restrict__ k
                 const int k_eff = topk < S ? topk : S;
                 const float dF = dlogits[(int64_t)slide * C + c] / (float)k_eff;
                 const float* kp = keys + row;
+                const KeyLayout kl = key_layout(C);
                 float psi;
                 if (m == 0) psi = kp[(int64_t)c * key_stride];
-                else if (m == 1) psi = kp[(int64_t)(C + c) * key_stride];
-                else if (m == 2) psi = kp[(int64_t)(2 * C) * key_stride];
-                else psi = kp[(int64_t)(2 * C + 2) * key_stride];
+                else if (m == 1) psi = kl.compact ? row_softmax_of(kp, key_stride, kl).of(kp[(int64_t)c * key_stride])
+                                                  : kp[(int64_t)(C + c) * key_stride];
+                else if (m == 2) psi = kp[(int64_t)kl.diff * key_stride];
+                else psi = kp[(int64_t)kl.bg_max * key_stride];
                 dg = ((active_mask >> m) & 1u) ? dF * psi : 0.f;
             }
             dz2s[m] = dg * g * (1.f - g);
@@ -569,8 +576,10 @@ __global__ void ablation_rows_kernel(const float* __restrict__ keys, int64_t key
     const int32_t row = sel_rows[slot];
     if (row < 0) return;
     const float* kp = keys + row;
-    const float l = kp[(int64_t)c * key_stride], p = kp[(int64_t)(C + c) * key_stride];
-    const float d = kp[(int64_t)(2 * C) * key_stride], b = kp[(int64_t)(2 * C + 2) * key_stride];
+    const KeyLayout kl = key_layout(C);
+    const float l = kp[(int64_t)c * key_stride];
+    const float p = kl.compact ? row_softmax_of(kp, key_stride, kl).of(l) : kp[(int64_t)(C + c) * key_stride];
+    const float d = kp[(int64_t)kl.diff * key_stride], b = kp[(int64_t)kl.bg_max * key_stride];
     float f;
     if (mode == 2) {
         f = fmaxf(fmaxf(l, p), fmaxf(d, b));
@@ -601,10 +610,14 @@ gather_selected_kernel(const float* __restrict__ feat, const float* __restrict__
     }
     if (p_top) {
         const float* kp = keys + row;
-        const float dlt = kp[(int64_t)(2 * C) * key_stride], bgm = kp[(int64_t)(2 * C + 2) * key_stride];
+        const KeyLayout kl = key_layout(C);
+        const float dlt = kp[(int64_t)kl.diff * key_stride], bgm = kp[(int64_t)kl.bg_max * key_stride];
+        RowSoftmax rs = {0.f};
+        if (kl.compact) rs = row_softmax_of(kp, key_stride, kl);
         for (int c = lane; c < C; c += 32) {
-            p_top[s * C + c] = kp[(int64_t)c * key_stride];
-            p_softmax[s * C + c] = kp[(int64_t)(C + c) * key_stride];
+            const float lt = kp[(int64_t)c * key_stride];
+            p_top[s * C + c] = lt;
+            p_softmax[s * C + c] = kl.compact ? rs.of(lt) : kp[(int64_t)(C + c) * key_stride];
             p_diff[s * C + c] = dlt;
             p_bg[s * C + c] = bgm;
         }

@@ -379,28 +379,7 @@ head_rows_f16_kernel(const float* __restrict__ feat, const float* __restrict__ k
             for (int m = 0; m < HF_G; ++m) g[m] = sigmoidf_exact(z[m] + b2s[m]);
             if (gate != nullptr) *reinterpret_cast<float4*>(gate + slot * HF_G) = make_float4(g[0], g[1], g[2], g[3]);
             if (final_scores == nullptr) continue;
-            const float* kp = keys + row;
-            const float dlt = kp[(int64_t)(2 * C) * key_stride];
-            const float bgm = kp[(int64_t)(2 * C + 2) * key_stride];
-            for (int c0 = 0; c0 < C; c0 += 4) {   // four classes at a time, their eight key loads issued together
-                float lt[4], ls[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int cc = c0 + u < C ? c0 + u : C - 1;
-                    lt[u] = kp[(int64_t)cc * key_stride];
-                    ls[u] = kp[(int64_t)(C + cc) * key_stride];
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (c0 + u < C) {
-                        float f = a0 * __fmul_rn(g[0], lt[u]);
-                        f = __fadd_rn(f, a1 * __fmul_rn(g[1], ls[u]));
-                        f = __fadd_rn(f, a2 * __fmul_rn(g[2], dlt));
-                        f = __fadd_rn(f, a3 * __fmul_rn(g[3], bgm));
-                        final_scores[slot * C + c0 + u] = f;
-                    }
-                }
-            }
+            combine_row(keys + row, key_stride, C, g, a0, a1, a2, a3, final_scores + slot * C);
         }
     }
 
@@ -451,10 +430,6 @@ constexpr int HT_STAGE_COLS = 32;            // a0: 16 columns of packed half2, 
 constexpr int HT_ACC_COL0 = 0;               // two accumulators of 64 columns
 constexpr int HT_A_COL0 = 128;               // four A stages of 32 columns
 constexpr int HT_TMEM_COLS = 512;
-#ifndef MOC_HT_KU_WIDE
-#define MOC_HT_KU_WIDE 16
-#endif
-constexpr int HT_KU_WIDE = MOC_HT_KU_WIDE;   // classes per batch of key loads in the epilogue, for more than 8 classes
 constexpr size_t HT_SMEM = (size_t)HF_BIMG_BYTES + 1024;
 
 __device__ __forceinline__ void ht_umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc, uint32_t accumulate) {
@@ -509,35 +484,6 @@ __device__ __forceinline__ float4 ldg_stream(const float4* p) {
     return v;
 }
 __device__ __forceinline__ void ht_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-// Gated combination of one selected row's four score planes (main_moc.py:391-405) for all classes, KU classes per batch
-// = 2 KU independent key loads in flight per thread.  Every load is a 32-byte sector of its own in a [2C+3, rows] array
-// far larger than the L2; with many classes these dependent batches of DRAM latency were what a tile waited for
-// (C = 30, 62 loads per row: four classes per batch 3.6 ms per 400 slides, eight 3.1 ms).
-template <int KU>
-__device__ __forceinline__ void ht_combine(const float* __restrict__ kp, int64_t key_stride, int C, const float (&g)[HF_G],
-                                           float a0, float a1, float a2, float a3, float dlt, float bgm,
-                                           float* __restrict__ out) {
-    for (int c0 = 0; c0 < C; c0 += KU) {
-        float lt[KU], ls[KU];
-#pragma unroll
-        for (int u = 0; u < KU; ++u) {
-            const int cc = c0 + u < C ? c0 + u : C - 1;
-            lt[u] = kp[(int64_t)cc * key_stride];
-            ls[u] = kp[(int64_t)(C + cc) * key_stride];
-        }
-#pragma unroll
-        for (int u = 0; u < KU; ++u) {
-            if (c0 + u < C) {
-                float f = a0 * __fmul_rn(g[0], lt[u]);
-                f = __fadd_rn(f, a1 * __fmul_rn(g[1], ls[u]));
-                f = __fadd_rn(f, a2 * __fmul_rn(g[2], dlt));
-                f = __fadd_rn(f, a3 * __fmul_rn(g[3], bgm));
-                out[c0 + u] = f;
-            }
-        }
-    }
-}
 
 __global__ void __launch_bounds__(HT_THREADS, 1)
 head_rows_f16t_kernel(const float* __restrict__ feat, const float* __restrict__ keys, int64_t key_stride, int C,
@@ -766,12 +712,7 @@ head_rows_f16t_kernel(const float* __restrict__ feat, const float* __restrict__ 
             for (int m = 0; m < HF_G; ++m) g[m] = sigmoidf_exact(z[m] + b2s[m]);
             if (gate != nullptr) *reinterpret_cast<float4*>(gate + slot * HF_G) = make_float4(g[0], g[1], g[2], g[3]);
             if (final_scores == nullptr) continue;
-            const float* kp = keys + row;
-            const float dlt = kp[(int64_t)(2 * C) * key_stride];
-            const float bgm = kp[(int64_t)(2 * C + 2) * key_stride];
-            if (C <= 4) ht_combine<4>(kp, key_stride, C, g, a0, a1, a2, a3, dlt, bgm, final_scores + slot * C);
-            else if (C <= 8) ht_combine<8>(kp, key_stride, C, g, a0, a1, a2, a3, dlt, bgm, final_scores + slot * C);
-            else ht_combine<HT_KU_WIDE>(kp, key_stride, C, g, a0, a1, a2, a3, dlt, bgm, final_scores + slot * C);
+            combine_row(keys + row, key_stride, C, g, a0, a1, a2, a3, final_scores + slot * C);
         }
     }
 

@@ -337,30 +337,7 @@ head_rows_tc_kernel(const float* __restrict__ feat, const float* __restrict__ ke
                 for (int m = 0; m < TC_G; ++m) g[m] = sigmoidf_exact(z[sub][m] + b2s[m]);
                 if (gate != nullptr) *reinterpret_cast<float4*>(gate + slot * TC_G) = make_float4(g[0], g[1], g[2], g[3]);
                 if (final_scores == nullptr) continue;
-                const float* kp = keys + row;
-                const float dlt = kp[(int64_t)(2 * C) * key_stride];
-                const float bgm = kp[(int64_t)(2 * C + 2) * key_stride];
-                // four classes at a time with their eight key loads issued together: at C = 30 one load pair per
-                // iteration left the epilogue waiting on 30 dependent round trips per row
-                for (int c0 = 0; c0 < C; c0 += 4) {
-                    float lt[4], ls[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int cc = c0 + u < C ? c0 + u : C - 1;
-                        lt[u] = kp[(int64_t)cc * key_stride];
-                        ls[u] = kp[(int64_t)(C + cc) * key_stride];
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        if (c0 + u < C) {
-                            float f = a0 * __fmul_rn(g[0], lt[u]);
-                            f = __fadd_rn(f, a1 * __fmul_rn(g[1], ls[u]));
-                            f = __fadd_rn(f, a2 * __fmul_rn(g[2], dlt));
-                            f = __fadd_rn(f, a3 * __fmul_rn(g[3], bgm));
-                            final_scores[slot * C + c0 + u] = f;
-                        }
-                    }
-                }
+                combine_row(keys + row, key_stride, C, g, a0, a1, a2, a3, final_scores + slot * C);
             }
         }
     }

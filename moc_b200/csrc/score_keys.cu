@@ -20,6 +20,7 @@
 
 namespace moc {
 
+static_assert(8 <= MOC_KEYS_COMPACT_MIN_CLASSES, "score_keys_regw_kernel (C + n_bg <= 8) writes the full 2C+3-plane key layout");
 constexpr int RP = 4;                       // patches per stage
 constexpr int STAGE_BYTES = RP * ROW_BYTES; // 8 KB
 #ifndef MOC_SK_WARPS
@@ -377,16 +378,18 @@ score_keys_smemw_kernel(const float* __restrict__ feat, int64_t n_rows, const fl
         }
         if (row < n_rows) {
             const float inv_sum = 1.0f / esum;
+            const KeyLayout kl = key_layout(C);
             float* kp = keys + row;
             for (int c = j8; c < C; c += 8) {
                 const float v = sr[c];
                 kp[(int64_t)c * key_stride] = v;
-                kp[(int64_t)(C + c) * key_stride] = expf(v - m1) * inv_sum;
+                if (!kl.compact) kp[(int64_t)(C + c) * key_stride] = expf(v - m1) * inv_sum;
             }
             if (j8 == 0) {
-                kp[(int64_t)(2 * C) * key_stride] = fabsf(m1 - m2);
-                kp[(int64_t)(2 * C + 1) * key_stride] = bsum;
-                kp[(int64_t)(2 * C + 2) * key_stride] = bmax;
+                if (kl.compact) kp[(int64_t)kl.lse * key_stride] = lse_of(m1, esum);   // readers rebuild softmax: expf(L - lse)
+                kp[(int64_t)kl.diff * key_stride] = fabsf(m1 - m2);
+                kp[(int64_t)kl.bg_sum * key_stride] = bsum;
+                kp[(int64_t)kl.bg_max * key_stride] = bmax;
             }
         }
         __syncwarp();

@@ -360,6 +360,7 @@ score_keys_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const float* 
         // =============================== epilogue (warps 0-3): thread = patch ========================
         if (PW == 16) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(ST_REGS_EPI16));
         const int C = n_classes;
+        const KeyLayout kl = key_layout(C);
         const float descale = tail->descale;
         int acc = 0;
         uint32_t acc_parity = 0;
@@ -465,23 +466,29 @@ score_keys_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const float* 
                 }
             }
             const float inv_sum = 1.0f / esum;
-            float* ks = kp + (int64_t)C * key_stride;
+            if (kl.compact) {
+                // wide class sets: the softmax planes are not stored, only what rebuilds them, expf(L - lse)
+                // (C + 4 planes: 136 instead of 252 bytes per patch at C = 30)
+                kp[(int64_t)kl.lse * key_stride] = lse_of(m1, esum);
+            } else {
+                float* ks = kp + (int64_t)C * key_stride;
 #pragma unroll
-            for (int c0 = 0; c0 < NCHUNK * 32; c0 += 8) {
-                if (c0 < C) {
-                    if (c0 + 8 <= C) {
+                for (int c0 = 0; c0 < NCHUNK * 32; c0 += 8) {
+                    if (c0 < C) {
+                        if (c0 + 8 <= C) {
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) ks[(int64_t)(c0 + e) * key_stride] = v[c0 + e] * inv_sum;
-                    } else {
+                            for (int e = 0; e < 8; ++e) ks[(int64_t)(c0 + e) * key_stride] = v[c0 + e] * inv_sum;
+                        } else {
 #pragma unroll
-                        for (int e = 0; e < 8; ++e)
-                            if (c0 + e < C) ks[(int64_t)(c0 + e) * key_stride] = v[c0 + e] * inv_sum;
+                            for (int e = 0; e < 8; ++e)
+                                if (c0 + e < C) ks[(int64_t)(c0 + e) * key_stride] = v[c0 + e] * inv_sum;
+                        }
                     }
                 }
             }
-            kp[(int64_t)(2 * C) * key_stride] = fabsf(m1 - m2);
-            kp[(int64_t)(2 * C + 1) * key_stride] = bsum;
-            kp[(int64_t)(2 * C + 2) * key_stride] = bmax;
+            kp[(int64_t)kl.diff * key_stride] = fabsf(m1 - m2);
+            kp[(int64_t)kl.bg_sum * key_stride] = bsum;
+            kp[(int64_t)kl.bg_max * key_stride] = bmax;
         }
         if (bad) atomicExch(&tail->flag, 1);
     }
@@ -510,6 +517,7 @@ score_keys_tc_kernel(const __grid_constant__ CUtensorMap feat_map, const float* 
 //     evict-last: all CTAs read the same 416 KB image) into a two-stage ring, in step with the A stages
 //   * epilogue: thread = patch; the accumulator is read 32 columns at a time; a chunk that lies inside one class
 //     (almost all do) is tree-summed and added to that class's sum, boundary chunks go element by element
+static_assert(MOC_BANK_MAX_CLASSES < MOC_KEYS_COMPACT_MIN_CLASSES, "the bank kernel writes the full 2C+3-plane key layout");
 struct BankTail {                      // after the eight K-block tiles of the image
     float scale, descale;              // same first 16 bytes as ScoreTcTail (score_tc_scale_kernel writes them)
     int flag, pad;

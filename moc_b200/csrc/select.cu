@@ -37,12 +37,39 @@ __device__ __forceinline__ uint32_t sel_key(float v) {
     return SMALLEST ? ~u : u;
 }
 
+// A column of selection keys: one stored plane of a slide (possibly strided: the stand-alone top-J over [N,C] logits),
+// or - compact key layout, softmax selections - L_c - lse = log softmax(L)[:,c] formed from two planes on the fly: the
+// same ranking of the slide's patches as the softmax values themselves (up to rounding among near-equal keys).
+struct ColPlain {
+    static constexpr int kScanDepth = 4;
+    const float* v;
+    int64_t ld;
+    __device__ __forceinline__ float at(int i) const { return v[(int64_t)i * ld]; }
+    __device__ __forceinline__ bool vec() const { return ld == 1; }
+    __device__ __forceinline__ int head() const { return (4 - (int)((reinterpret_cast<uintptr_t>(v) >> 2) & 3)) & 3; }
+    __device__ __forceinline__ float4 at4(int head, int k) const { return __ldg(reinterpret_cast<const float4*>(v + head) + k); }
+};
+struct ColLogSoftmax {
+    static constexpr int kScanDepth = 2;
+    const float *l, *lse;
+    __device__ __forceinline__ float at(int i) const { return l[i] - lse[i]; }
+    // 16-byte loads need both planes in the same alignment phase (key_stride a multiple of 4: ops.alloc_keys pads it)
+    __device__ __forceinline__ bool vec() const {
+        return ((reinterpret_cast<uintptr_t>(l) ^ reinterpret_cast<uintptr_t>(lse)) & 15) == 0;
+    }
+    __device__ __forceinline__ int head() const { return (4 - (int)((reinterpret_cast<uintptr_t>(l) >> 2) & 3)) & 3; }
+    __device__ __forceinline__ float4 at4(int head, int k) const {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(l + head) + k);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(lse + head) + k);
+        return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w);
+    }
+};
+
 // Block-wide: value (as ordered uint) of the element of rank j (1-based, largest first) among the kept
-// rows of v[i*ld], i<n.  Leaves sh.prefix = threshold, sh.need = how many threshold-equal rows to take,
+// rows of the column.  Leaves sh.prefix = threshold, sh.need = how many threshold-equal rows to take,
 // sh.n_equal = how many exist.  Requires 1 <= j <= kept rows.
-template <bool SMALLEST, bool HAS_MASK>
-__device__ void radix_threshold(const float* __restrict__ v, int64_t ld, const uint8_t* __restrict__ mk, int n, int j,
-                                SelShared& sh) {
+template <bool SMALLEST, bool HAS_MASK, typename Col>
+__device__ void radix_threshold(const Col& col, const uint8_t* __restrict__ mk, int n, int j, SelShared& sh) {
     const int tid = threadIdx.x;
     uint32_t prefix = 0, known = 0;
     uint32_t need = (uint32_t)j;
@@ -54,7 +81,7 @@ __device__ void radix_threshold(const float* __restrict__ v, int64_t ld, const u
         unsigned int cur_cnt = 0;
         for (int i = tid; i < n; i += SEL_THREADS) {
             if (HAS_MASK && !mk[i]) continue;
-            const uint32_t u = sel_key<SMALLEST>(v[(int64_t)i * ld]);
+            const uint32_t u = sel_key<SMALLEST>(col.at(i));
             if ((u & known) != prefix) continue;
             const int b = (u >> shift) & 255;
             if (b == cur_bin) {
@@ -106,9 +133,9 @@ __device__ void radix_threshold(const float* __restrict__ v, int64_t ld, const u
 
 // Calls emit(i) for exactly the j selected rows (unordered, except that threshold ties are resolved towards
 // lower row indices).  Block-wide; all threads must call.
-template <bool SMALLEST, bool HAS_MASK, typename Emit>
-__device__ void select_rows(const float* __restrict__ v, int64_t ld, const uint8_t* __restrict__ mk, int n, int n_kept,
-                            int j, SelShared& sh, Emit emit) {
+template <bool SMALLEST, bool HAS_MASK, typename Col, typename Emit>
+__device__ void select_rows(const Col& col, const uint8_t* __restrict__ mk, int n, int n_kept, int j, SelShared& sh,
+                            Emit emit) {
     const int tid = threadIdx.x;
     if (j <= 0) return;
     if (j >= n_kept) {
@@ -116,13 +143,13 @@ __device__ void select_rows(const float* __restrict__ v, int64_t ld, const uint8
             if (!HAS_MASK || mk[i]) emit(i);
         return;
     }
-    radix_threshold<SMALLEST, HAS_MASK>(v, ld, mk, n, j, sh);
+    radix_threshold<SMALLEST, HAS_MASK>(col, mk, n, j, sh);
     const uint32_t thr = sh.prefix;
     const uint32_t need = sh.need;
     const bool all_equal_taken = (sh.n_equal == need);
     for (int i = tid; i < n; i += SEL_THREADS) {
         if (HAS_MASK && !mk[i]) continue;
-        const uint32_t u = sel_key<SMALLEST>(v[(int64_t)i * ld]);
+        const uint32_t u = sel_key<SMALLEST>(col.at(i));
         if (u > thr || (all_equal_taken && u == thr)) emit(i);
     }
     if (all_equal_taken) return;
@@ -133,7 +160,7 @@ __device__ void select_rows(const float* __restrict__ v, int64_t ld, const uint8
     for (int base = 0; base < n; base += SEL_THREADS) {
         const int i = base + tid;
         bool eq = false;
-        if (i < n && (!HAS_MASK || mk[i])) eq = sel_key<SMALLEST>(v[(int64_t)i * ld]) == thr;
+        if (i < n && (!HAS_MASK || mk[i])) eq = sel_key<SMALLEST>(col.at(i)) == thr;
         const unsigned int bal = __ballot_sync(FULL, eq);
         if (lane == 0) sh.warp_tot[warp] = __popc(bal);
         __syncthreads();
@@ -163,32 +190,35 @@ struct FastShared {
 };
 
 // f(i, u) for every kept key of a contiguous column; 16-byte loads, two in flight per thread.
-template <bool SMALLEST, bool HAS_MASK, typename F>
-__device__ __forceinline__ void scan_column(const float* __restrict__ v, const uint8_t* __restrict__ mk, int n, F f) {
+template <bool SMALLEST, bool HAS_MASK, typename Col, typename F>
+__device__ __forceinline__ void scan_column(const Col& col, const uint8_t* __restrict__ mk, int n, F f) {
     const int tid = threadIdx.x;
     auto visit = [&](int i, float x) {
         if (HAS_MASK && !mk[i]) return;
         f(i, sel_key<SMALLEST>(x));
     };
-    int head = (4 - (int)((reinterpret_cast<uintptr_t>(v) >> 2) & 3)) & 3;
+    if (!col.vec()) {
+        for (int i = tid; i < n; i += SEL_THREADS) visit(i, col.at(i));
+        return;
+    }
+    int head = col.head();
     if (head > n) head = n;
-    if (tid < head) visit(tid, v[tid]);
+    if (tid < head) visit(tid, col.at(tid));
     const int n4 = (n - head) >> 2;
-    const float4* v4 = reinterpret_cast<const float4*>(v + head);
     int k = tid;
     for (; k + SEL_THREADS < n4; k += 2 * SEL_THREADS) {
-        const float4 a = __ldg(v4 + k), b = __ldg(v4 + k + SEL_THREADS);
+        const float4 a = col.at4(head, k), b = col.at4(head, k + SEL_THREADS);
         const int ia = head + 4 * k, ib = ia + 4 * SEL_THREADS;
         visit(ia, a.x); visit(ia + 1, a.y); visit(ia + 2, a.z); visit(ia + 3, a.w);
         visit(ib, b.x); visit(ib + 1, b.y); visit(ib + 2, b.z); visit(ib + 3, b.w);
     }
     if (k < n4) {
-        const float4 a = __ldg(v4 + k);
+        const float4 a = col.at4(head, k);
         const int ia = head + 4 * k;
         visit(ia, a.x); visit(ia + 1, a.y); visit(ia + 2, a.z); visit(ia + 3, a.w);
     }
     const int t0 = head + 4 * n4;
-    if (t0 + tid < n) visit(t0 + tid, v[t0 + tid]);
+    if (t0 + tid < n) visit(t0 + tid, col.at(t0 + tid));
 }
 
 // Block-wide: the bin (counting from the top) where the running count reaches `need`.  Leaves sh.prefix = bin,
@@ -238,8 +268,8 @@ __device__ void find_bin_desc(const unsigned int* hist, unsigned int need, SelSh
 //           the remaining <= 20 bits are resolved with 10-bit digits and ties go to the lowest row indices.
 // Returns false (block-uniform) for columns too degenerate for the on-chip lists (e.g. thousands of equal keys
 // at the threshold); the caller then runs the generic path, which is correct on its own (marking is idempotent).
-template <bool SMALLEST, bool HAS_MASK, typename Emit>
-__device__ bool select_rows_fast(const float* __restrict__ v, const uint8_t* __restrict__ mk, int n, int j,
+template <bool SMALLEST, bool HAS_MASK, typename Col, typename Emit>
+__device__ bool select_rows_fast(const Col& v, const uint8_t* __restrict__ mk, int n, int j,
                                  SelShared& sh, FastShared& fs, Emit emit) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // ---- scan 1: range of the kept keys
@@ -341,32 +371,37 @@ __device__ __forceinline__ bool sampled_applies(int n, int j) {
 // f(i, u) for every key of a contiguous unmasked column; 16-byte loads, FOUR in flight per thread (the column's first
 // touch comes from DRAM: with two, a CTA in its scan has 16 KB in flight, and the three CTAs of an SM are in a scan only
 // about half of the time).
-template <bool SMALLEST, typename F>
-__device__ __forceinline__ void scan_column4(const float* __restrict__ v, int n, F f) {
+template <bool SMALLEST, typename Col, typename F>
+__device__ __forceinline__ void scan_column4(const Col& col, int n, F f) {
+    constexpr int DEPTH = Col::kScanDepth;      // 16-byte pieces in flight per thread: four loads either way
     const int tid = threadIdx.x;
     auto visit = [&](int i, float x) { f(i, sel_key<SMALLEST>(x)); };
-    int head = (4 - (int)((reinterpret_cast<uintptr_t>(v) >> 2) & 3)) & 3;
+    if (!col.vec()) {
+        for (int i = tid; i < n; i += SEL_THREADS) visit(i, col.at(i));
+        return;
+    }
+    int head = col.head();
     if (head > n) head = n;
-    if (tid < head) visit(tid, v[tid]);
+    if (tid < head) visit(tid, col.at(tid));
     const int n4 = (n - head) >> 2;
-    const float4* v4 = reinterpret_cast<const float4*>(v + head);
     int k = tid;
-    for (; k + 3 * SEL_THREADS < n4; k += 4 * SEL_THREADS) {
-        const float4 a = __ldg(v4 + k), b = __ldg(v4 + k + SEL_THREADS), c = __ldg(v4 + k + 2 * SEL_THREADS),
-                     d = __ldg(v4 + k + 3 * SEL_THREADS);
-        const int ia = head + 4 * k, ib = ia + 4 * SEL_THREADS, ic = ib + 4 * SEL_THREADS, id = ic + 4 * SEL_THREADS;
-        visit(ia, a.x); visit(ia + 1, a.y); visit(ia + 2, a.z); visit(ia + 3, a.w);
-        visit(ib, b.x); visit(ib + 1, b.y); visit(ib + 2, b.z); visit(ib + 3, b.w);
-        visit(ic, c.x); visit(ic + 1, c.y); visit(ic + 2, c.z); visit(ic + 3, c.w);
-        visit(id, d.x); visit(id + 1, d.y); visit(id + 2, d.z); visit(id + 3, d.w);
+    for (; k + (DEPTH - 1) * SEL_THREADS < n4; k += DEPTH * SEL_THREADS) {
+        float4 a[DEPTH];
+#pragma unroll
+        for (int d = 0; d < DEPTH; ++d) a[d] = col.at4(head, k + d * SEL_THREADS);
+#pragma unroll
+        for (int d = 0; d < DEPTH; ++d) {
+            const int i = head + 4 * (k + d * SEL_THREADS);
+            visit(i, a[d].x); visit(i + 1, a[d].y); visit(i + 2, a[d].z); visit(i + 3, a[d].w);
+        }
     }
     for (; k < n4; k += SEL_THREADS) {
-        const float4 a = __ldg(v4 + k);
+        const float4 a = col.at4(head, k);
         const int ia = head + 4 * k;
         visit(ia, a.x); visit(ia + 1, a.y); visit(ia + 2, a.z); visit(ia + 3, a.w);
     }
     const int t0 = head + 4 * n4;
-    if (t0 + tid < n) visit(t0 + tid, v[t0 + tid]);
+    if (t0 + tid < n) visit(t0 + tid, col.at(t0 + tid));
 }
 
 constexpr int FS_SMALL = 64;    // keys of the threshold bin ranked by brute force
@@ -385,8 +420,8 @@ constexpr int FS_SMALL = 64;    // keys of the threshold bin ranked by brute for
 //      by brute force - ties at equal value to the lowest row indices, exactly like the other paths.
 // Returns false (block-uniform) with nothing emitted when the parked count falls outside [j, FS_CAND] or the threshold
 // bin is crowded with equal keys; the caller then runs the three-scan path.
-template <bool SMALLEST, typename Emit>
-__device__ bool select_rows_sampled(const float* __restrict__ v, int n, int j, SelShared& sh, FastShared& fs, Emit emit) {
+template <bool SMALLEST, typename Col, typename Emit>
+__device__ bool select_rows_sampled(const Col& v, int n, int j, SelShared& sh, FastShared& fs, Emit emit) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // ---- 1. sample, its range, one histogram round
     int stride = 128;
@@ -394,7 +429,7 @@ __device__ bool select_rows_sampled(const float* __restrict__ v, int n, int j, S
     const unsigned int m = (unsigned int)(n / stride) * 8u;             // <= 4096
     uint32_t lo = 0xffffffffu, hi = 0u;
     for (unsigned int c = tid; c < m; c += SEL_THREADS) {
-        const uint32_t u = sel_key<SMALLEST>(__ldg(v + (size_t)(c >> 3) * stride + (c & 7u)));
+        const uint32_t u = sel_key<SMALLEST>(v.at((int)((c >> 3) * stride + (c & 7u))));
         fs.cand[c].x = u;
         lo = min(lo, u);
         hi = max(hi, u);
@@ -482,28 +517,59 @@ __device__ int count_kept(const uint8_t* __restrict__ mk, int n, SelShared& sh) 
     return (int)sh.n_kept;
 }
 
-// grid (n_slides, 2C+2): one selection of one slide per CTA; marks the chosen rows in the global bitmap.
-template <bool HAS_MASK>
-__global__ void __launch_bounds__(SEL_THREADS, 3)   // 40 registers: three CTAs per SM (two: -20 %; four: worse at C = 30)
+// One selection of one slide, whatever its column type: the one-scan path for long unmasked columns, else the
+// three-scan path, else (degenerate columns) the generic four-pass radix select.
+template <bool HAS_MASK, typename Col, typename Emit>
+__device__ __forceinline__ void select_one(const Col& col, const uint8_t* __restrict__ mk, int n, int n_kept, int j,
+                                           bool smallest, bool sampled, SelShared& sh, FastShared& fs, Emit mark) {
+    if (j > 0 && j < n_kept) {
+        if (!HAS_MASK && sampled && sampled_applies(n, j)) {
+            const bool done = smallest ? select_rows_sampled<true>(col, n, j, sh, fs, mark)
+                                       : select_rows_sampled<false>(col, n, j, sh, fs, mark);
+            if (done) return;
+            __syncthreads();
+        }
+        const bool done = smallest ? select_rows_fast<true, HAS_MASK>(col, mk, n, j, sh, fs, mark)
+                                   : select_rows_fast<false, HAS_MASK>(col, mk, n, j, sh, fs, mark);
+        if (done) return;
+        __syncthreads();
+    }
+    if (smallest) select_rows<true, HAS_MASK>(col, mk, n, n_kept, j, sh, mark);
+    else select_rows<false, HAS_MASK>(col, mk, n, n_kept, j, sh, mark);
+}
+
+// grid (2C+2, n_slides): one selection of one slide per CTA; marks the chosen rows in the global bitmap.  The CTAs of a
+// slide are neighbours in the grid, so they run at about the same time: what several of them read - the row mask, and
+// in the compact key layout (COMPACT; C >= MOC_KEYS_COMPACT_MIN_CLASSES) the lse plane every softmax selection needs
+// and the L_c plane the top-J and the softmax selection of class c share - comes from DRAM once.
+#ifndef MOC_SEL_COMPACT_CTAS
+#define MOC_SEL_COMPACT_CTAS 3
+#endif
+template <bool HAS_MASK, bool COMPACT>
+__global__ void __launch_bounds__(SEL_THREADS, COMPACT ? MOC_SEL_COMPACT_CTAS : 3)   // 40 registers: three CTAs per SM (two: -20 %; four: worse at C = 30)
 select_mark_kernel(const float* __restrict__ keys, int64_t key_stride, const int64_t* __restrict__ offsets, int C,
                    int topj, unsigned discard_mask, const uint8_t* __restrict__ row_mask,
                    unsigned int* __restrict__ bitmap, int sampled) {
     extern __shared__ __align__(16) unsigned char sel_dyn_smem[];
     FastShared& fs = *reinterpret_cast<FastShared*>(sel_dyn_smem);
     __shared__ SelShared sh;
-    const int q = blockIdx.y, slide = blockIdx.x;
+    // q: 2c = top-J of class c, 2c + 1 = softmax selection of class c (neighbours: they share L_c), 2C = |top1 - top2|,
+    // 2C + 1 = bottom-J of the background sum
+    const int q = blockIdx.x, slide = blockIdx.y;
+    const KeyLayout kl = key_layout(C);
     unsigned cls;
     int plane;
-    bool smallest = false;
-    if (q < C) { cls = MOC_CLS_TOPK; plane = q; }
-    else if (q < 2 * C) { cls = MOC_CLS_DELTA_SOFTMAX; plane = q; }
-    else if (q == 2 * C) { cls = MOC_CLS_DELTA_DIFF; plane = 2 * C; }
-    else { cls = MOC_CLS_BOTTOMK; plane = 2 * C + 1; smallest = true; }
+    bool smallest = false, softmax_col = false;
+    if (q < 2 * C) {
+        const int c = q >> 1;
+        if ((q & 1) == 0) { cls = MOC_CLS_TOPK; plane = c; }
+        else { cls = MOC_CLS_DELTA_SOFTMAX; plane = COMPACT ? c : kl.softmax0 + c; softmax_col = COMPACT; }
+    } else if (q == 2 * C) { cls = MOC_CLS_DELTA_DIFF; plane = kl.diff; }
+    else { cls = MOC_CLS_BOTTOMK; plane = kl.bg_sum; smallest = true; }
     if (discard_mask & cls) return;
     const int64_t row0 = offsets[slide];
     const int n = (int)(offsets[slide + 1] - row0);
     if (n <= 0) return;
-    const float* v = keys + (int64_t)plane * key_stride + row0;
     const uint8_t* mk = HAS_MASK ? row_mask + row0 : nullptr;
     const int n_kept = count_kept<HAS_MASK>(mk, n, sh);
     const int j = topj < n_kept ? topj : n_kept;
@@ -511,20 +577,14 @@ select_mark_kernel(const float* __restrict__ keys, int64_t key_stride, const int
         const int64_t r = row0 + i;
         atomicOr(&bitmap[r >> 5], 1u << (r & 31));
     };
-    if (j > 0 && j < n_kept) {
-        if (!HAS_MASK && sampled && sampled_applies(n, j)) {
-            const bool done = smallest ? select_rows_sampled<true>(v, n, j, sh, fs, mark)
-                                       : select_rows_sampled<false>(v, n, j, sh, fs, mark);
-            if (done) return;
-            __syncthreads();
-        }
-        const bool done = smallest ? select_rows_fast<true, HAS_MASK>(v, mk, n, j, sh, fs, mark)
-                                   : select_rows_fast<false, HAS_MASK>(v, mk, n, j, sh, fs, mark);
-        if (done) return;
-        __syncthreads();
+    const float* v = keys + (int64_t)plane * key_stride + row0;
+    if (COMPACT && softmax_col) {
+        const ColLogSoftmax col = {v, keys + (int64_t)kl.lse * key_stride + row0};
+        select_one<HAS_MASK>(col, mk, n, n_kept, j, smallest, sampled != 0, sh, fs, mark);
+    } else {
+        const ColPlain col = {v, 1};
+        select_one<HAS_MASK>(col, mk, n, n_kept, j, smallest, sampled != 0, sh, fs, mark);
     }
-    if (smallest) select_rows<true, HAS_MASK>(v, 1, mk, n, n_kept, j, sh, mark);
-    else select_rows<false, HAS_MASK>(v, 1, mk, n, n_kept, j, sh, mark);
 }
 
 // grid n_slides: bitmap -> ascending row list (+ index inside the masked bag), count per slide.
@@ -620,8 +680,9 @@ topj_sorted_kernel(const float* __restrict__ values, int n, int64_t ld, int64_t 
         // descending sort of (key, ~index): larger value first, lower index first among equals
         skeys[slot] = (unsigned long long)u << 32 | (unsigned long long)(0xffffffffu - (uint32_t)i);
     };
-    if (small) select_rows<true, false>(v, ld, nullptr, n, n, j, sh, push);
-    else select_rows<false, false>(v, ld, nullptr, n, n, j, sh, push);
+    const ColPlain column = {v, ld};
+    if (small) select_rows<true, false>(column, nullptr, n, n, j, sh, push);
+    else select_rows<false, false>(column, nullptr, n, n, j, sh, push);
     __syncthreads();
     // bitonic sort, descending
     for (int k = 2; k <= sort_pow2; k <<= 1) {
@@ -669,8 +730,9 @@ pool_topk_kernel(const float* __restrict__ keys, int64_t key_stride, const int64
         const unsigned int slot = atomicAdd(&n_out, 1u);
         win[slot] = ((unsigned long long)u << 32) | (unsigned long long)(0xffffffffu - (uint32_t)i);
     };
-    if (small) select_rows<true, false>(sv, 1, nullptr, n, n, k, sh, push);
-    else select_rows<false, false>(sv, 1, nullptr, n, n, k, sh, push);
+    const ColPlain col = {sv, 1};
+    if (small) select_rows<true, false>(col, nullptr, n, n, k, sh, push);
+    else select_rows<false, false>(col, nullptr, n, n, k, sh, push);
     __syncthreads();
     if (tid == 0) {
         // order the k winners (descending key, ascending row) so the fp32 sum has a fixed order
@@ -767,29 +829,33 @@ extern "C" int moc_select_union(const float* keys, int64_t key_stride, const int
     cudaStream_t st = (cudaStream_t)stream;
     unsigned int* bitmap = reinterpret_cast<unsigned int*>(workspace);
     MOC_CUDA(cudaMemsetAsync(bitmap, 0, need, st));
-    const dim3 grid(n_slides, 2 * n_classes + 2);
+    MOC_CHECK_SHAPE(n_slides <= 65535, "moc_select_union: at most 65535 slides per call, got %d", n_slides);
+    const dim3 grid(2 * n_classes + 2, n_slides);
     static int sampled = -1;        // MOC_SELECT_SAMPLED=0: three-scan selection only (developer A/B switch)
     if (sampled < 0) {
         const char* e = getenv("MOC_SELECT_SAMPLED");
         sampled = (e && e[0] == '0') ? 0 : 1;
     }
-    MOC_CUDA(cudaFuncSetAttribute(select_mark_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)sizeof(FastShared)));
-    MOC_CUDA(cudaFuncSetAttribute(select_mark_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)sizeof(FastShared)));
+    const bool compact = key_layout(n_classes).compact;
+#define MOC_SEL_LAUNCH(MASKED, COMPACT_)                                                                                  \
+    do {                                                                                                                  \
+        MOC_CUDA(cudaFuncSetAttribute(select_mark_kernel<MASKED, COMPACT_>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                      (int)sizeof(FastShared)));                                                          \
+        select_mark_kernel<MASKED, COMPACT_><<<grid, SEL_THREADS, sizeof(FastShared), st>>>(                              \
+            keys, key_stride, offsets, n_classes, topj, discard_mask, row_mask, bitmap, sampled);                         \
+    } while (0)
     if (row_mask) {
-        select_mark_kernel<true><<<grid, SEL_THREADS, sizeof(FastShared), st>>>(keys, key_stride, offsets, n_classes, topj, discard_mask,
-                                                              row_mask, bitmap, sampled);
+        if (compact) MOC_SEL_LAUNCH(true, true); else MOC_SEL_LAUNCH(true, false);
         MOC_LAUNCH_CHECK("select_mark_kernel");
         compact_kernel<true><<<n_slides, CMP_THREADS, 0, st>>>(bitmap, offsets, row_mask, sel_base, sel_rows, sel_local,
                                                              sel_count);
     } else {
-        select_mark_kernel<false><<<grid, SEL_THREADS, sizeof(FastShared), st>>>(keys, key_stride, offsets, n_classes, topj,
-                                                               discard_mask, nullptr, bitmap, sampled);
+        if (compact) MOC_SEL_LAUNCH(false, true); else MOC_SEL_LAUNCH(false, false);
         MOC_LAUNCH_CHECK("select_mark_kernel");
         compact_kernel<false><<<n_slides, CMP_THREADS, 0, st>>>(bitmap, offsets, nullptr, sel_base, sel_rows, sel_local,
                                                               sel_count);
     }
+#undef MOC_SEL_LAUNCH
     MOC_LAUNCH_CHECK("compact_kernel");
     return MOC_OK;
 }

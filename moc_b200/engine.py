@@ -23,13 +23,23 @@ import torch
 from . import _lib, ops
 from .bag_store import RaggedBagStore
 
-POOLINGS = {
-    # name -> (select plane0, select step, value plane0, value step, smallest) as functions of C
-    "topj": lambda c: (0, 1, 0, 1, False),
-    "delta_softmax": lambda c: (c, 1, 0, 1, False),
-    "delta_diff": lambda c: (2 * c, 0, 0, 1, False),
-    "bottomk_irrel": lambda c: (2 * c + 1, 0, 0, 1, True),
-}
+def _pooling_planes(pooling: str, c: int):
+    """(select plane0, select step, value plane0, value step, smallest, needs the full layout) of a zero-shot pooling
+    mode in the key layout of C classes.  The softmax selection indexes the C softmax planes, which the compact layout
+    of wide class sets does not store: that mode pools over ``ops.expand_keys``."""
+    from ._lib import PLANE_BG_SUM, PLANE_DIFF
+    if pooling == "topj":
+        return 0, 1, 0, 1, False, False
+    if pooling == "delta_softmax":
+        return c, 1, 0, 1, False, True
+    if pooling == "delta_diff":
+        return ops.key_plane(c, PLANE_DIFF), 0, 0, 1, False, False
+    if pooling == "bottomk_irrel":
+        return ops.key_plane(c, PLANE_BG_SUM), 0, 0, 1, True, False
+    raise KeyError(pooling)
+
+
+POOLINGS = ("topj", "delta_softmax", "delta_diff", "bottomk_irrel")
 
 
 @dataclass
@@ -210,7 +220,7 @@ class MocEngine:
     def _score(self, feat: torch.Tensor, out: Optional[torch.Tensor] = None, max_ctas: int = 0) -> torch.Tensor:
         if max_ctas == 0:
             if out is None:     # the calibration launches write the same keys into the buffer the real launch fills
-                out = torch.empty(ops.num_key_planes(self.n_classes), feat.size(0), dtype=torch.float32, device=feat.device)
+                out = ops.alloc_keys(self.n_classes, feat.size(0), feat.device)
             max_ctas = self._tuned_ctas(feat, out)
         if self.score_events is None:
             return ops.score_keys(feat, self.prompts, self.normalize, out=out, max_ctas=max_ctas)
@@ -257,7 +267,8 @@ class MocEngine:
     def zero_shot_logits(self, store: RaggedBagStore, pooling: str = "topj", check_domain: bool = False) -> torch.Tensor:
         """``check_domain``: see :meth:`eval_logits` (here only the tensor-core scoring of wide prompt sets can overflow)."""
         c = self.n_classes
-        sp0, ss, vp0, vs, small = POOLINGS[pooling](c)
+        sp0, ss, vp0, vs, small, want_full = _pooling_planes(pooling, c)
+        want_full = want_full and ops.num_key_planes(c) != 2 * c + 3
         out = torch.empty(len(store), c, dtype=torch.float32, device=store.device)
         ext_fg = self._prompts_ext_fg if pooling == "bottomk_irrel" else None
         wide = self.is_wide(store)
@@ -272,6 +283,8 @@ class MocEngine:
             else:   # class planes of this pass = feats @ W_ext[:, :C]; the background sum is the same either way
                 keys = ops.score_keys(store.feat[store.offsets_h[lo]:store.offsets_h[hi]], ext_fg, self.normalize, wide=wide)
             offs, _, _, _ = self._layout(store, lo, hi)
+            if want_full:
+                keys = ops.expand_keys(keys, c)
             out[lo:hi] = ops.pool_topk(keys, offs, hi - lo, c, self.topk, sp0, ss, vp0, vs, small)
         if armed:
             bad = self._flags_raised(ws) or (ext_fg is not None and ext_fg.tc_flag is not None and int(ext_fg.tc_flag.item()) != 0)

@@ -165,7 +165,33 @@ class BankPrompts:
 
 
 def num_key_planes(n_classes: int) -> int:
-    return 2 * n_classes + 3
+    """Planes the scoring kernels write for C classes: 2C+3, or C+4 in the compact layout of wide class sets
+    (include/moc_b200.h: a log-sum-exp plane instead of the C softmax planes, which every consumer forms on the fly)."""
+    return int(_lib.load().moc_num_key_planes(int(n_classes)))
+
+
+def key_plane(n_classes: int, which: int) -> int:
+    """Index of a named plane (``_lib.PLANE_*``) in the layout the scoring kernels use for C classes; -1 if not stored."""
+    return int(_lib.load().moc_key_plane(int(n_classes), int(which)))
+
+
+def alloc_keys(n_classes: int, rows: int, device) -> torch.Tensor:
+    """Key planes [planes, rows] whose plane stride is a multiple of 4 floats: every plane of a slide then sits in the
+    same 16-byte phase, which the selection kernel's two-plane (compact softmax) columns need for vector loads."""
+    pad = (int(rows) + 3) & ~3
+    return torch.empty(num_key_planes(n_classes), pad, dtype=torch.float32, device=device)[:, :rows]
+
+
+def expand_keys(keys: torch.Tensor, n_classes: int) -> torch.Tensor:
+    """The full 2C+3-plane layout [L | softmax | diff | bg sum | bg max] from whatever layout ``keys`` uses for C classes
+    (a copy when it is the full one already): what the stand-alone helpers, the zero-shot softmax pooling of wide class
+    sets and tests index directly."""
+    rows = keys.size(1)
+    full = torch.empty(2 * n_classes + 3, max(rows, 1), dtype=torch.float32, device=keys.device)[:, :rows]
+    _count(1)
+    check(_lib.load().moc_expand_keys(keys.data_ptr(), keys.stride(0), int(n_classes), rows, full.data_ptr(), full.stride(0),
+                                      _stream()))
+    return full
 
 
 def score_keys(feat: torch.Tensor, prompts, normalize: bool = False,
@@ -183,7 +209,7 @@ def score_keys(feat: torch.Tensor, prompts, normalize: bool = False,
         raise MocError(_lib.E_SHAPE, "feat must be [rows,512], got %s" % (tuple(feat.shape),))
     r = feat.size(0)
     if out is None:
-        out = torch.empty(num_key_planes(prompts.n_classes), r, device=feat.device, dtype=torch.float32)
+        out = alloc_keys(prompts.n_classes, r, feat.device)
     _count(1)
     if isinstance(prompts, BankPrompts):
         if wide:      # range-free: the collapsed matrix on the fp32 kernels (scoring is linear in the prompts)
@@ -507,10 +533,11 @@ def split_grads(flat: torch.Tensor):
 
 
 def row_keys(logits: torch.Tensor, n_fg: int) -> torch.Tensor:
-    """Key planes [2*n_fg+3, N] from logits [N, Ct] (first n_fg columns are classes, the rest background)."""
+    """Key planes [2*n_fg+3, N] (the full layout, whatever the class count) from logits [N, Ct] (first n_fg columns are
+    classes, the rest background): what the stand-alone selector / pooling functions slice."""
     x = _dev_f32(logits, "logits")
     n, ct = x.shape
-    keys = torch.empty(num_key_planes(n_fg), n, dtype=torch.float32, device=x.device)
+    keys = torch.empty(2 * n_fg + 3, n, dtype=torch.float32, device=x.device)    # always the full layout
     _count(1)
     check(_lib.load().moc_row_keys(x.data_ptr(), n, x.stride(0), n_fg, ct, keys.data_ptr(), keys.stride(0), _stream()))
     return keys

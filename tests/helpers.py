@@ -5,6 +5,13 @@ import torch
 RTOL, ATOL = 1e-3, 1e-6  # north_star: scores and logits within 1e-3 relative (plus an absolute floor at zero)
 
 
+def full_keys(keys, c):
+    """Key planes in the full 2C+3 layout [L | softmax | diff | bg sum | bg max] whatever layout the scoring kernels use
+    for c classes (moc_expand_keys: wide class sets store C+5 planes and rebuild the softmax planes on the fly)."""
+    from moc_b200 import ops
+    return ops.expand_keys(keys, c)
+
+
 def close(a, b, rtol=RTOL, atol=ATOL):
     a = a.detach().cpu().double().numpy() if isinstance(a, torch.Tensor) else np.asarray(a, dtype=np.float64)
     b = b.detach().cpu().double().numpy() if isinstance(b, torch.Tensor) else np.asarray(b, dtype=np.float64)

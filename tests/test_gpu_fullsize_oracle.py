@@ -73,10 +73,12 @@ def test_eval_pass_matches_oracle_at_full_size(c, sizes):
             gp = torch.tensor([b + pos_g[r] for r in common], device=DEV)
             rp = torch.tensor([pos_r[r] for r in common])
         rows = sel.sel_rows[gp].long()
-        close(keys[:c, rows].t(), slide["logits_top_classifier"][rp])
-        close(keys[c:2 * c, rows].t(), slide["logits_delta_softmax_classifier"][rp])
-        close(keys[2 * c, rows], slide["logits_delta_diff_classifier"][rp][:, 0], atol=2e-6)
-        close(keys[2 * c + 2, rows], slide["logits_bottomk_irrel_classifier"][rp][:, 0])
+        fk = ops.expand_keys(keys[:, offs[i]:offs[i + 1]], c)      # the full 2C+3-plane layout of this slide
+        rows = rows - offs[i]
+        close(fk[:c, rows].t(), slide["logits_top_classifier"][rp])
+        close(fk[c:2 * c, rows].t(), slide["logits_delta_softmax_classifier"][rp])
+        close(fk[2 * c, rows], slide["logits_delta_diff_classifier"][rp][:, 0], atol=2e-6)
+        close(fk[2 * c + 2, rows], slide["logits_bottomk_irrel_classifier"][rp][:, 0])
         close(out.gate[gp], gate_ref[rp], rtol=1e-4, atol=2e-6)
         close(out.final[gp], final_ref[rp], atol=4e-6)
         if got_idx == ref_idx:

@@ -4,7 +4,7 @@ import pytest
 import torch
 
 from oracle import moc_oracle as O
-from tests.helpers import assert_topj_set, assert_union_set, close, params_from_golden
+from tests.helpers import full_keys, assert_topj_set, assert_union_set, close, params_from_golden
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -39,7 +39,8 @@ def test_score_keys_golden(golden, name):
     pr = ops.Prompts.pack(w.to(DEV), we.to(DEV))
     keys = ops.score_keys(feat, pr)
     torch.cuda.synchronize()
-    assert keys.shape == (2 * c + 3, offs[-1])
+    assert keys.shape == (ops.num_key_planes(c), offs[-1])
+    keys = full_keys(keys, c)
     for i, x in enumerate(bags):
         ref = oracle_keys(x, w, we, c)
         got = keys[:, offs[i]:offs[i + 1]].cpu().numpy()
@@ -60,7 +61,7 @@ def test_score_keys_shapes(n_rows, c, n_ext):
     wa = torch.randn(n_ext, 512, generator=gen)
     wa = wa / wa.norm(dim=1, keepdim=True)
     w, we = wa[:c].t().contiguous(), wa.t().contiguous()
-    keys = ops.score_keys(x.to(DEV), ops.Prompts.pack(w.to(DEV), we.to(DEV)))
+    keys = full_keys(ops.score_keys(x.to(DEV), ops.Prompts.pack(w.to(DEV), we.to(DEV))), c)
     close(keys.cpu().numpy(), oracle_keys(x, w, we, c), rtol=1e-3, atol=2e-6)
 
 
@@ -80,7 +81,7 @@ def test_score_keys_both_impls(monkeypatch, impl, n_rows, c, n_ext):
     w, we = wa[:c].t().contiguous(), wa.t().contiguous()
     pr = ops.Prompts.pack(w.to(DEV), we.to(DEV))
     assert (pr.tc is not None) == (impl == "tc" or n_ext > 8)
-    keys = ops.score_keys(x.to(DEV), pr).cpu().numpy()
+    keys = full_keys(ops.score_keys(x.to(DEV), pr), c).cpu().numpy()
     close(keys, oracle_keys(x, w, we, c), rtol=1e-3, atol=2e-6)
     exact = (x.double() @ w.double()).numpy().T  # fp32-level accuracy of the raw similarities
     assert np.abs(keys[:c] - exact).max() < 4e-6
@@ -114,7 +115,7 @@ def test_score_keys_normalize_flag():
         wa = torch.randn(n_ext, 512, generator=gen)
         wa = wa / wa.norm(dim=1, keepdim=True)
         w, we = wa[:c].t().contiguous(), wa.t().contiguous()
-        keys = ops.score_keys(x.to(DEV), ops.Prompts.pack(w.to(DEV), we.to(DEV)), normalize=True)
+        keys = full_keys(ops.score_keys(x.to(DEV), ops.Prompts.pack(w.to(DEV), we.to(DEV)), normalize=True), c)
         xn = torch.nn.functional.normalize(x, dim=-1)
         close(keys.cpu().numpy(), oracle_keys(xn, w, we, c), rtol=1e-3, atol=2e-6)
 
@@ -331,10 +332,11 @@ def test_head_forward_golden(golden, name):
                 close(out.bag_logits[i:i + 1], g[q + "bag_logits"])
             # planes are the key rows of the selected patches
             rows = sel.sel_rows[gp].long()
-            close(keys[:c, rows].t(), g[q + "plane_top"][rp])
-            close(keys[c:2 * c, rows].t(), g[q + "plane_dsoftmax"][rp])
-            close(keys[2 * c, rows], g[q + "plane_ddiff"][rp][:, 0])
-            close(keys[2 * c + 2, rows], g[q + "plane_bottomk"][rp][:, 0])
+            fk = full_keys(keys, c)
+            close(fk[:c, rows].t(), g[q + "plane_top"][rp])
+            close(fk[c:2 * c, rows].t(), g[q + "plane_dsoftmax"][rp])
+            close(fk[2 * c, rows], g[q + "plane_ddiff"][rp][:, 0])
+            close(fk[2 * c + 2, rows], g[q + "plane_bottomk"][rp][:, 0])
 
 
 def test_pool_topk_zero_shot(golden):
@@ -348,6 +350,7 @@ def test_pool_topk_zero_shot(golden):
         keys = ops.score_keys(feat, ops.Prompts.pack(w.to(DEV), we.to(DEV)))
         offs_d = torch.tensor(offs, dtype=torch.int64, device=DEV)
         n = len(bags)
+        keys = full_keys(keys, c)                                             # plane indices below: the full layout
         zs = ops.pool_topk(keys, offs_d, n, c, k, 0, 1, 0, 1)                 # topj_pooling
         ds = ops.pool_topk(keys, offs_d, n, c, k, c, 1, 0, 1)                 # delta_softmax pooling
         dd = ops.pool_topk(keys, offs_d, n, c, k, 2 * c, 0, 0, 1)             # delta_diff pooling

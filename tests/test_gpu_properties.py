@@ -48,7 +48,9 @@ def test_full_size_pipeline_properties(c, sizes):
     prm = _params()
     keys, sel, out = _pipeline(feat, offs, w, we, c, prm)
     total = offs[-1]
-    assert keys.shape[1] == total
+    assert keys.shape == (ops.num_key_planes(c), total)
+    keys_stored = keys
+    keys = ops.expand_keys(keys, c)       # the checks below index the full 2C+3-plane layout
 
     # ---- scores: float64 product of the same inputs; softmax / |top1-top2| / background sum, max from them
     L64 = feat.double() @ w.double()
@@ -61,7 +63,7 @@ def test_full_size_pipeline_properties(c, sizes):
     assert (keys[2 * c + 2].double() - Le64.max(dim=1).values).abs().max().item() < 2e-5
 
     # ---- exact linearity under a power-of-two scale of the features
-    keys2 = ops.score_keys(feat * 2.0, ops.Prompts.pack(w, we))
+    keys2 = ops.expand_keys(ops.score_keys(feat * 2.0, ops.Prompts.pack(w, we)), c)
     if c + 4 <= 8:      # fp32 FMA kernel: scaling by 2 commutes with every rounding
         assert torch.equal(keys2[:c], keys[:c] * 2.0) and torch.equal(keys2[2 * c + 1:], keys[2 * c + 1:] * 2.0)
     else:               # FP16x3 tensor-core kernel: the low halves of small features are subnormal (2^-25 absolute floor)
@@ -104,7 +106,7 @@ def test_full_size_pipeline_properties(c, sizes):
 
     # ---- run-to-run determinism (bit-identical)
     keys_b, sel_b, out_b = _pipeline(feat, offs, w, we, c, prm)
-    assert torch.equal(keys_b, keys) and torch.equal(sel_b.sel_rows, sel.sel_rows)
+    assert torch.equal(keys_b, keys_stored) and torch.equal(sel_b.sel_rows, sel.sel_rows)
     assert torch.equal(out_b.bag_logits, out.bag_logits) and torch.equal(out_b.pool_pos, out.pool_pos)
 
 

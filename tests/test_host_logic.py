@@ -24,6 +24,10 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert declared == set(_lib.SIGNATURES), "ctypes table and header disagree: %s" % (declared ^ set(_lib.SIGNATURES))
     assert lib.moc_version() >= 100
     assert lib.moc_num_key_planes(3) == 9
+    # wide class sets: C+4 planes (log-sum-exp instead of the C softmax planes)
+    assert lib.moc_num_key_planes(8) == 19 and lib.moc_num_key_planes(9) == 13 and lib.moc_num_key_planes(30) == 34
+    assert [lib.moc_key_plane(3, k) for k in range(6)] == [0, 3, 6, 7, 8, -1]
+    assert [lib.moc_key_plane(30, k) for k in range(6)] == [0, -1, 31, 32, 33, 30]
     assert lib.moc_select_capacity(100000, 2, 400) == 2400 and lib.moc_select_capacity(50, 2, 400) == 50
     assert lib.moc_packed_cols(2, 6) == 8 and lib.moc_packed_cols(30, 34) == 36
 

@@ -40,7 +40,7 @@ def main():
         synthetic.make_bag(n, i % c, we, c, seed=i, device=dev, out=feat[i * n:(i + 1) * n])
     offs = [i * n for i in range(s + 1)]
     offs_d = torch.tensor(offs, dtype=torch.int64, device=dev)
-    keys = torch.empty(2 * c + 3, n * s, device=dev)
+    keys = ops.alloc_keys(c, n * s, dev)
     gb = feat.numel() * 4 / 1e9
     t, tmin = timeit(lambda: ops.score_keys(feat, pr, out=keys))
     print("score_keys  C=%d rows=%d  %.3f ms (min %.3f)  %.1f GB/s (best %.1f)" % (c, n * s, t, tmin, gb / t * 1e3, gb / tmin * 1e3))

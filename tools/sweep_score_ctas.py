@@ -16,7 +16,7 @@ def main():
     rows = 8_000_000
     feat = torch.randn(rows, 512, device=dev)
     feat /= feat.norm(dim=1, keepdim=True)
-    keys = torch.empty(2 * c + 3, rows, device=dev)
+    keys = ops.alloc_keys(c, rows, dev)
     out = []
     for cap in [int(v) for v in (sys.argv[1:] or ["148", "140", "136", "132", "128", "124", "116"])]:
         for _ in range(8):
