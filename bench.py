@@ -447,6 +447,12 @@ def run_ours(a):
                         "compute reads 7.3-7.4 TB/s on this part (tools/probe_stream.cu), so this read-mostly kernel "
                         "can exceed 1.0 of it; frac_of_read_only_7400 is the stricter figure",
                 "frac_of_read_only_7400": achieved / 7400.0}
+    # what the kernel must move in all: the patch rows it reads plus the key planes it writes (4 B x planes per patch:
+    # 28 B at C=2, 136 B at C=30 in the compact layout) - the DRAM roofline of a wide class set is set by this sum
+    key_bytes = 4 * ops.num_key_planes(N_CLASSES)
+    roofline["key_bytes_written_per_patch"] = key_bytes
+    roofline["achieved_incl_key_writes"] = achieved * (2048 + key_bytes) / 2048.0
+    roofline["frac_incl_key_writes"] = roofline["achieved_incl_key_writes"] / peak
 
     if bank is not None:
         # ~100 FLOP per byte: this configuration is bound by the tensor pipe, not by HBM.  Algorithmic work = one

@@ -7,11 +7,14 @@
 // Selection is an exact radix select on the order-preserving uint32 image of the fp32 keys: the value of rank
 // J is found digit by digit, rows strictly beyond it are taken, and ties at the threshold are taken in
 // ascending row order until exactly J rows are chosen (torch leaves tie order unspecified).  The batched
-// selection kernel scans a column three times with 16-byte loads (range, a 4096-bin histogram of the occupied
-// range, then marking + on-chip resolution of the threshold bin; see select_rows_fast).  The generic four-pass
-// version serves the stand-alone top-J / pooling kernels and degenerate columns.  The union of
-// the 2C+2 selections of a slide is a bitmap over its rows, so the ascending order of the reference's
-// sorted(set(...)) falls out of the compaction for free and nothing ever goes back to the host.
+// selection kernel reads a long unmasked column ONCE (select_rows_sampled: a provisional threshold from a 1/16 sample,
+// every key above it parked in shared memory, the top J resolved there) and otherwise scans it three times with
+// 16-byte loads (range, a 4096-bin histogram of the occupied range, then marking + on-chip resolution of the
+// threshold bin; see select_rows_fast).  The generic four-pass version serves the stand-alone top-J / pooling
+// kernels and degenerate columns.  A column is a stored key plane or, in the compact key layout of wide class sets
+// (include/moc_b200.h), L_c - lse from two planes.  The union of the 2C+2 selections of a slide is a bitmap over its
+// rows, so the ascending order of the reference's sorted(set(...)) falls out of the compaction for free and nothing
+// ever goes back to the host.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -829,8 +832,7 @@ extern "C" int moc_select_union(const float* keys, int64_t key_stride, const int
     cudaStream_t st = (cudaStream_t)stream;
     unsigned int* bitmap = reinterpret_cast<unsigned int*>(workspace);
     MOC_CUDA(cudaMemsetAsync(bitmap, 0, need, st));
-    MOC_CHECK_SHAPE(n_slides <= 65535, "moc_select_union: at most 65535 slides per call, got %d", n_slides);
-    const dim3 grid(2 * n_classes + 2, n_slides);
+    constexpr int MAX_GRID_Y = 65535;       // slides per launch of the marking kernel (grid.y)
     static int sampled = -1;        // MOC_SELECT_SAMPLED=0: three-scan selection only (developer A/B switch)
     if (sampled < 0) {
         const char* e = getenv("MOC_SELECT_SAMPLED");
@@ -841,8 +843,11 @@ extern "C" int moc_select_union(const float* keys, int64_t key_stride, const int
     do {                                                                                                                  \
         MOC_CUDA(cudaFuncSetAttribute(select_mark_kernel<MASKED, COMPACT_>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                       (int)sizeof(FastShared)));                                                          \
-        select_mark_kernel<MASKED, COMPACT_><<<grid, SEL_THREADS, sizeof(FastShared), st>>>(                              \
-            keys, key_stride, offsets, n_classes, topj, discard_mask, row_mask, bitmap, sampled);                         \
+        for (int s0 = 0; s0 < n_slides; s0 += MAX_GRID_Y) {                                                               \
+            const dim3 grid(2 * n_classes + 2, n_slides - s0 < MAX_GRID_Y ? n_slides - s0 : MAX_GRID_Y);                  \
+            select_mark_kernel<MASKED, COMPACT_><<<grid, SEL_THREADS, sizeof(FastShared), st>>>(                          \
+                keys, key_stride, offsets + s0, n_classes, topj, discard_mask, row_mask, bitmap, sampled);                \
+        }                                                                                                                 \
     } while (0)
     if (row_mask) {
         if (compact) MOC_SEL_LAUNCH(true, true); else MOC_SEL_LAUNCH(true, false);

@@ -232,6 +232,43 @@ def test_score_cta_calibration_changes_nothing_but_speed(monkeypatch):
     assert torch.equal(eng.keys_for(store), ref) and MocEngine._TUNED_CTAS == {}
 
 
+@pytest.mark.parametrize("c", [8, 9, 12, 30])
+def test_zero_shot_ablation_and_dict_api_across_the_key_layout_change(c):
+    """Class counts on both sides of MOC_KEYS_COMPACT_MIN_CLASSES (2C+3 key planes up to 8 classes, C+4 from 9 on: a
+    log-sum-exp plane instead of the softmax planes): the four zero-shot poolings, the three ablation combinations, the
+    evaluation pass and slide_process' dense planes against the oracle."""
+    import moc_b200 as M
+    from moc_b200 import ops, synthetic
+    from moc_b200.engine import MocEngine
+    j, k = 60, 7
+    w, we = synthetic.prompt_matrices(c)
+    sizes = [900, 1501, 333, 2048]
+    bags = [synthetic.make_bag(n, i % c, we, c, seed=700 + 10 * c + i) for i, n in enumerate(sizes)]
+    labels = [i % c for i in range(len(sizes))]
+    store = M.RaggedBagStore.from_bags(bags, labels, DEV)
+    assert ops.num_key_planes(c) == (2 * c + 3 if c < 9 else c + 4)
+    eng = MocEngine(w.to(DEV), we.to(DEV), j, k)
+    data = O.BagList(bags, labels)
+    for pooling in ("topj", "delta_softmax", "delta_diff", "bottomk_irrel"):
+        _, ref = O.zs_evaluation(data, w, we, c, k, pooling=pooling, return_logits=True)
+        close(eng.zero_shot_logits(store, pooling), ref, rtol=1e-3, atol=2e-6)
+    for how in ("avg", "sum", "max"):
+        ref = torch.cat([O.ablation_logits(x, w, we, c, j, k, how) for x in bags], 0)
+        close(eng.ablation_logits(store, how), ref, rtol=1e-3, atol=2e-6)
+    oprm = O.SenetParams.init(11)
+    prm = ops.HeadParams(oprm.w1.to(DEV), oprm.b1.to(DEV), oprm.w2.to(DEV), oprm.b2.to(DEV))
+    ref = torch.cat([O.slide_eval_logits(oprm, x, w, we, c, j, k) for x in bags], 0)
+    close(eng.eval_logits(store, prm, check_domain=True), ref, rtol=1e-3, atol=2e-6)
+    # the dict API: dense planes of the selected rows, as the reference returns them
+    loops_w, loops_we = w.to(DEV), we.to(DEV)
+    got = M.slide_process(bags[1].to(DEV), loops_w, loops_we, c, j)
+    want = O.slide_process(bags[1], w, we, c, j)
+    if got["selected_index"] == want["selected_index"]:
+        for name in ("logits_top_classifier", "logits_delta_softmax_classifier", "logits_delta_diff_classifier",
+                     "logits_bottomk_irrel_classifier"):
+            close(got[name], want[name], rtol=1e-3, atol=2e-6)
+
+
 def test_ext_class_columns_differ_from_w(golden):
     """zs_evaluation(pooling_func=bottomk_irrel_classifier_pooling) pools (feats @ W_ext)[:, :C] (main_moc.py:428-432):
     with a W_ext whose class columns are not W the engine must score those columns, not reuse the W planes.  Golden
