@@ -366,7 +366,11 @@ __device__ bool select_rows_fast(const Col& v, const uint8_t* __restrict__ mk, i
 }
 
 // Expected size of the candidate set the sampled path aims for, and whether a column qualifies for it.
-__device__ __forceinline__ int sampled_target(int j) { return 3 * j + 400; }
+#ifndef MOC_SEL_TARGET_MUL
+#define MOC_SEL_TARGET_MUL 3
+#define MOC_SEL_TARGET_ADD 400
+#endif
+__device__ __forceinline__ int sampled_target(int j) { return MOC_SEL_TARGET_MUL * j + MOC_SEL_TARGET_ADD; }
 __device__ __forceinline__ bool sampled_applies(int n, int j) {
     return n >= 8192 && sampled_target(j) <= 2560 && 4 * sampled_target(j) <= n;
 }
