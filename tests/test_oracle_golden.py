@@ -276,3 +276,28 @@ def test_dp_microbatch_variant_of_the_oracle(golden):
         total = grads if total is None else [x + y for x, y in zip(total, grads)]
     O.adam_step(p0, total, O.AdamState())
     assert lw == losses and all(torch.equal(x, y) for x, y in zip(p0.tensors(), whole.tensors()))
+
+
+@pytest.mark.parametrize("c,n", [(9, 5000), (30, 20000)])
+def test_log_softmax_ranks_a_slide_like_softmax(c, n):
+    """The compact key layout of wide class sets (include/moc_b200.h) stores lse = log sum exp(L) instead of the C softmax
+    planes; its softmax selection takes the top J of L_c - lse where the reference takes the top J of softmax(L)_c
+    (utils/patch_selection_classifier_index.py:28-36).  The two are the same ranking up to fp32 rounding among
+    near-equal keys: on the oracle's own scores the two top-J sets may differ only in rows whose softmax value lies
+    within the parity tolerance of the rank-J value; and expf(L_c - lse) reproduces the softmax plane within 1e-6."""
+    from moc_b200 import synthetic
+    from tests.helpers import assert_topj_set
+    j = 400
+    w, we = synthetic.prompt_matrices(c)
+    x = synthetic.make_bag(n, 1, we, c, seed=4242 + c)
+    lo, _ = O.score(x, w, we)
+    soft = torch.softmax(lo, dim=1)
+    m = lo.max(dim=1, keepdim=True).values
+    lse = m + torch.log(torch.exp(lo - m).sum(dim=1, keepdim=True))        # what the scoring epilogues store (fp32)
+    logsoft = lo - lse
+    assert (torch.exp(logsoft) - soft).abs().max().item() < 1e-6
+    for col in range(c):
+        ref = soft[:, col].topk(j).indices.tolist()
+        got = logsoft[:, col].topk(j).indices.tolist()
+        assert_topj_set(got, ref, soft[:, col].numpy(), j)
+
